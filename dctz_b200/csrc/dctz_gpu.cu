@@ -1,0 +1,690 @@
+// dctz_gpu.cu -- C-ABI of the B200-native DCTZ hot path (include/dctz_gpu.h).
+//
+// Host side of the kernels in kernels.cuh: context / scratch management, launch configuration,
+// the sf threshold tables (built with the host libm so that the device reproduces util.c:28/42
+// bit for bit without a host round trip), and the host-buffer entry points that the reference's
+// dctz_compress()/dctz_decompress() call at the seam described in include/dctz_gpu.h.
+//
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/dctz_gpu.h"
+#include "kernels.cuh"
+
+using namespace dctz;
+
+static_assert(sizeof(Info) == sizeof(dctz_gpu_info), "Info must mirror dctz_gpu_info");
+static_assert(DCTZ_GPU_BLK == BLK, "block size");
+
+static thread_local char g_err[512] = "";
+
+struct DevBuf {  // grow-only device allocation
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct dctz_gpu_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;  // used by the host-buffer API
+  char err[512] = "";
+  uint64_t launches = 0;
+  int opt_dct = 0;
+  unsigned epoch = 0;
+
+  // small fixed scratch
+  StatPartial *d_partials = nullptr;
+  int stat_grid = 0;
+  unsigned *d_done = nullptr;
+  double *d_stats3 = nullptr;
+  DevParams *d_params = nullptr;
+  Info *d_info = nullptr;
+  TileControl *d_ctl = nullptr;
+  unsigned long long *d_nconsumed = nullptr;
+  unsigned long long *d_mismatch = nullptr;
+  DevBuf status;        // look-back words, one per tile
+  DevBuf qt_raw, qt_j;  // QT: un-rescaled outliers + their coefficient position
+
+  // sf tables: host copies + device copies
+  std::vector<double> thr_d, sfv_d;
+  std::vector<float> thr_f, sfv_f;
+  double min_d = 0;
+  float min_f = 0;
+  SfTables tb{};
+
+  // buffers of the host-buffer API
+  DevBuf in, bins, dc, ac, qt, qtraw, out;
+  int occ[2][2][2] = {};  // resident CTAs/SM per [kernel][datatype][qt]
+};
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static int fail(dctz_gpu_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  snprintf(g_err, sizeof g_err, "%s", buf);
+  if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s", buf);
+  return code;
+}
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? DCTZ_GPU_ENOMEM : DCTZ_GPU_ECUDA, "%s: %s (%s:%d)", \
+                  #call, cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+  } while (0)
+#define TRY(call)            \
+  do {                       \
+    int r_ = (call);         \
+    if (r_ != DCTZ_GPU_OK) return r_; \
+  } while (0)
+
+static int grow(dctz_gpu_ctx *ctx, DevBuf &b, size_t bytes, bool zero = false) {
+  if (bytes <= b.cap) return DCTZ_GPU_OK;
+  if (b.p) { CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  size_t want = bytes + bytes / 8 + 256;
+  CU(cudaMalloc(&b.p, want));
+  b.cap = want;
+  if (zero) CU(cudaMemset(b.p, 0, want));
+  return DCTZ_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sf threshold tables.  sf = pow(10, ceil(log10(max)) - 1) (util.c:28); float: powf(10,
+// ceil(log10f(max)) - 1) (util.c:42).  T_k := smallest value whose libm log10 exceeds k, found by
+// bisection on the bit pattern around 10^k; then ceil(log10(max)) == k  <=>  T_{k-1} <= max < T_k.
+// ------------------------------------------------------------------------------------------
+static double bits_to_d(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
+static uint64_t d_to_bits(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
+static float bits_to_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static uint32_t f_to_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+static double threshold_d(int k) {
+  const double c = pow(10.0, (double)k);
+  uint64_t lo = d_to_bits(c * (1.0 - 1e-9)), hi = d_to_bits(c * (1.0 + 1e-9));  // log10(lo) <= k < log10(hi)
+  while (hi - lo > 1) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if (log10(bits_to_d(mid)) > (double)k) hi = mid; else lo = mid;
+  }
+  return bits_to_d(hi);
+}
+static float threshold_f(int k) {
+  const float c = powf(10.0f, (float)k);
+  uint32_t lo = f_to_bits(c * (1.0f - 1e-4f)), hi = f_to_bits(c * (1.0f + 1e-4f));
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if (log10f(bits_to_f(mid)) > (float)k) hi = mid; else lo = mid;
+  }
+  return bits_to_f(hi);
+}
+
+static void build_sf_tables(dctz_gpu_ctx *c) {
+  const int kmin_d = -306, kmax_d = 308;  // sf = 10^(k-1) stays a normal double
+  c->min_d = threshold_d(kmin_d - 1);
+  for (int k = kmin_d; k <= kmax_d; k++) {
+    c->thr_d.push_back(threshold_d(k));
+    c->sfv_d.push_back(pow(10, (double)k - 1));  // the literal expression of util.c:28 for ceil(.) == k
+  }
+  c->sfv_d.push_back(pow(10, (double)(kmax_d + 1) - 1));
+  const int kmin_f = -36, kmax_f = 38;
+  c->min_f = threshold_f(kmin_f - 1);
+  for (int k = kmin_f; k <= kmax_f; k++) {
+    c->thr_f.push_back(threshold_f(k));
+    c->sfv_f.push_back(powf(10, (double)k - 1));  // util.c:42: powf(10, ceil(..) - 1); the exponent is a double narrowed to float
+  }
+  c->sfv_f.push_back(powf(10, (double)(kmax_f + 1) - 1));
+}
+
+template <typename T> static int host_lookup(const std::vector<T> &thr, T mx) {
+  int lo = 0, hi = (int)thr.size();
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (mx < thr[mid]) hi = mid; else lo = mid + 1; }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------
+template <typename K> static int kernel_occupancy(K kernel, int threads, size_t smem) {
+  int n = 0;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int dctz_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" const char *dctz_gpu_last_error(const dctz_gpu_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  void *small[] = {ctx->d_partials, ctx->d_done, ctx->d_stats3, ctx->d_params, ctx->d_info, ctx->d_ctl,
+                   ctx->d_nconsumed, ctx->d_mismatch, (void *)ctx->tb.thr_d, (void *)ctx->tb.sf_d,
+                   (void *)ctx->tb.thr_f, (void *)ctx->tb.sf_f};
+  for (void *p : small) if (p) cudaFree(p);
+  DevBuf *bufs[] = {&ctx->status, &ctx->qt_raw, &ctx->qt_j, &ctx->in, &ctx->bins, &ctx->dc, &ctx->ac,
+                    &ctx->qt, &ctx->qtraw, &ctx->out};
+  for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+template <typename T> static int upload(dctz_gpu_ctx *ctx, const std::vector<T> &v, const T **dst) {
+  void *p = nullptr;
+  CU(cudaMalloc(&p, v.size() * sizeof(T)));
+  CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = (const T *)p;
+  return DCTZ_GPU_OK;
+}
+
+static int ctx_init(dctz_gpu_ctx *ctx, int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(ctx, DCTZ_GPU_ENODEV, "no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return fail(ctx, DCTZ_GPU_EINVAL, "device %d out of range [0,%d)", device, ndev);
+  ctx->device = device;
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(ctx, DCTZ_GPU_ENODEV, "device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major, prop.minor);
+  ctx->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->stat_grid = ctx->sm_count * 8;
+  CU(cudaMalloc(&ctx->d_partials, sizeof(StatPartial) * ctx->stat_grid));
+  CU(cudaMalloc(&ctx->d_done, sizeof(unsigned)));
+  CU(cudaMemset(ctx->d_done, 0, sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->d_stats3, 3 * sizeof(double)));
+  CU(cudaMalloc(&ctx->d_params, sizeof(DevParams)));
+  CU(cudaMalloc(&ctx->d_info, sizeof(Info)));
+  CU(cudaMalloc(&ctx->d_ctl, 2 * sizeof(TileControl)));
+  CU(cudaMemset(ctx->d_ctl, 0, 2 * sizeof(TileControl)));
+  CU(cudaMalloc(&ctx->d_nconsumed, sizeof(unsigned long long)));
+  CU(cudaMalloc(&ctx->d_mismatch, sizeof(unsigned long long)));
+  build_sf_tables(ctx);
+  TRY(upload(ctx, ctx->thr_d, &ctx->tb.thr_d));
+  TRY(upload(ctx, ctx->sfv_d, &ctx->tb.sf_d));
+  TRY(upload(ctx, ctx->thr_f, &ctx->tb.thr_f));
+  TRY(upload(ctx, ctx->sfv_f, &ctx->tb.sf_f));
+  ctx->tb.n_d = (int)ctx->thr_d.size();
+  ctx->tb.n_f = (int)ctx->thr_f.size();
+  ctx->tb.min_d = ctx->min_d;
+  ctx->tb.min_f = ctx->min_f;
+  // kernel attributes + residency (persistent grids are sized from these)
+  ctx->occ[0][1][0] = kernel_occupancy(k_compress<double, false>, TILE_BLOCKS, CompressCfg<double, false>::SMEM);
+  ctx->occ[0][1][1] = kernel_occupancy(k_compress<double, true>, TILE_BLOCKS, CompressCfg<double, true>::SMEM);
+  ctx->occ[0][0][0] = kernel_occupancy(k_compress<float, false>, TILE_BLOCKS, CompressCfg<float, false>::SMEM);
+  ctx->occ[0][0][1] = kernel_occupancy(k_compress<float, true>, TILE_BLOCKS, CompressCfg<float, true>::SMEM);
+  ctx->occ[1][1][0] = kernel_occupancy(k_decompress<double, false>, TILE_BLOCKS, DecompressCfg<double, false>::SMEM);
+  ctx->occ[1][1][1] = kernel_occupancy(k_decompress<double, true>, TILE_BLOCKS, DecompressCfg<double, true>::SMEM);
+  ctx->occ[1][0][0] = kernel_occupancy(k_decompress<float, false>, TILE_BLOCKS, DecompressCfg<float, false>::SMEM);
+  ctx->occ[1][0][1] = kernel_occupancy(k_decompress<float, true>, TILE_BLOCKS, DecompressCfg<float, true>::SMEM);
+  for (int a = 0; a < 2; a++)
+    for (int b = 0; b < 2; b++)
+      for (int c = 0; c < 2; c++)
+        if (ctx->occ[a][b][c] < 1)
+          return fail(ctx, DCTZ_GPU_ECUDA, "kernel [%d][%d][%d] cannot be made resident: %s", a, b, c,
+                      cudaGetErrorString(cudaGetLastError()));
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_create(dctz_gpu_ctx **out, int device) {
+  if (!out) return fail(nullptr, DCTZ_GPU_EINVAL, "ctx pointer is NULL");
+  *out = nullptr;
+  dctz_gpu_ctx *ctx = new (std::nothrow) dctz_gpu_ctx();
+  if (!ctx) return fail(nullptr, DCTZ_GPU_ENOMEM, "out of host memory");
+  const int r = ctx_init(ctx, device);
+  if (r != DCTZ_GPU_OK) {
+    snprintf(g_err, sizeof g_err, "%s", ctx->err);
+    dctz_gpu_destroy(ctx);
+    return r;
+  }
+  *out = ctx;
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_sm_count(const dctz_gpu_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" uint64_t dctz_gpu_launch_count(const dctz_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void *dctz_gpu_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void dctz_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" int dctz_gpu_set_option(dctz_gpu_ctx *ctx, const char *name, int value) {
+  if (!ctx || !name) return fail(ctx, DCTZ_GPU_EINVAL, "bad option call");
+  if (!strcmp(name, "dct")) {
+    if (value != 0) return fail(ctx, DCTZ_GPU_EINVAL, "dct variant %d not available in this build", value);
+    const int prev = ctx->opt_dct;
+    ctx->opt_dct = value;
+    return prev;
+  }
+  return fail(ctx, DCTZ_GPU_EINVAL, "unknown option '%s'", name);
+}
+
+extern "C" double dctz_gpu_sf_from_max(const dctz_gpu_ctx *ctx, double max_abs, int datatype) {
+  if (!ctx) return 0.0;
+  if (datatype == DCTZ_GPU_DOUBLE) {
+    if (!(max_abs >= ctx->min_d) || isinf(max_abs)) return 0.0;
+    return ctx->sfv_d[host_lookup(ctx->thr_d, max_abs)];
+  }
+  const float m = (float)max_abs;
+  if (!(m >= ctx->min_f) || isinf(m)) return 0.0;
+  return (double)ctx->sfv_f[host_lookup(ctx->thr_f, m)];
+}
+
+// ------------------------------------------------------------------------------------------
+// argument checks shared by the entry points
+// ------------------------------------------------------------------------------------------
+static int check_common(dctz_gpu_ctx *ctx, int datatype, double eb) {
+  if (!ctx) return fail(nullptr, DCTZ_GPU_EINVAL, "ctx is NULL");
+  if (datatype != DCTZ_GPU_FLOAT && datatype != DCTZ_GPU_DOUBLE) return fail(ctx, DCTZ_GPU_EINVAL, "datatype %d is neither FLOAT(0) nor DOUBLE(1)", datatype);
+  if (!(eb >= 1e-6)) return fail(ctx, DCTZ_GPU_EINVAL, "error bound %g is below 1E-6 (dctz-comp-lib.c:135)", eb);
+  return DCTZ_GPU_OK;
+}
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+static int next_epoch(dctz_gpu_ctx *ctx, size_t ntiles, cudaStream_t st) {
+  const bool fresh = (ntiles * 8 > ctx->status.cap);
+  TRY(grow(ctx, ctx->status, ntiles * 8));
+  if (fresh || ++ctx->epoch > 0xFFFFu) {  // new array or epoch wrap: clear every word once
+    ctx->epoch = 1;
+    CU(cudaMemsetAsync(ctx->status.p, 0, ctx->status.cap, st));
+  }
+  return DCTZ_GPU_OK;
+}
+
+template <typename T> static QuantConsts<T> make_quant(double eb);
+template <> QuantConsts<double> make_quant<double>(double eb) {
+  QuantConsts<double> q;
+  const int half = DCTZ_GPU_NBINS / 2;
+  q.bw = eb * 2.0 * 1.0;                   // dctz-comp-lib.c:273 (BRSF == 1.0)
+  q.rmin = -(half * 2 + 1) * (eb * 1.0);   // :274
+  q.rmax = (half * 2 + 1) * (eb * 1.0);    // :275
+  q.inv_bw = 1.0 / q.bw;
+  return q;
+}
+template <> QuantConsts<float> make_quant<float>(double eb) {
+  QuantConsts<float> q;
+  const int half = DCTZ_GPU_NBINS / 2;
+  q.bw = (float)(eb * 2.0 * 1.0);                 // :278
+  q.rmin = (float)(-(half * 2 + 1) * (eb * 1.0)); // :279
+  q.rmax = (float)((half * 2 + 1) * (eb * 1.0));  // :280
+  q.div = make_divisor(q.bw);
+  return q;
+}
+template <typename T> static QtConsts<T> make_qt(double eb) {
+  QtConsts<T> k;
+  const QuantConsts<T> q = make_quant<T>(eb);
+  k.eb = eb;
+  k.rmin = q.rmin;
+  k.rmax = q.rmax;
+  k.d_rmax = (T)(eb * DCTZ_GPU_NBINS);   // dctz-decomp-lib.c:373 / 378
+  k.d_rmin = (T)(-eb * DCTZ_GPU_NBINS);  // :374 / 379
+  k.den = eb * (sizeof(T) == 8 ? 10.0 : (double)10.0f);  // error_bound * qt_factor (:405, :450)
+  return k;
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1: statistics
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_stats(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double *d_stats3, int finalize_inline, size_t n_total,
+                        void *d_qtable_raw, Info *d_info, cudaStream_t st) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  size_t want = (N / VEC + 255) / 256 / 4 + 1;
+  int grid = (int)(want < (size_t)ctx->stat_grid ? want : (size_t)ctx->stat_grid);
+  SfTables tb = ctx->tb;
+  tb.qmax_words = (int)(BLK * sizeof(T) / 8);
+  k_stats<T><<<grid, 256, 0, st>>>(d_in, N, ctx->d_partials, ctx->d_done, d_stats3, finalize_inline,
+                                   (unsigned long long)n_total, 1, tb, ctx->d_params, d_info,
+                                   (unsigned long long *)d_qtable_raw);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_stats_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double *d_stats3, void *stream) {
+  TRY(check_common(ctx, datatype, 1.0));
+  if (!d_in || !d_stats3 || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "stats: NULL pointer or N == 0");
+  if (!aligned16(d_in)) return fail(ctx, DCTZ_GPU_EINVAL, "stats: input must be 16-byte aligned");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (datatype == DCTZ_GPU_DOUBLE) return launch_stats<double>(ctx, (const double *)d_in, N, d_stats3, 0, N, nullptr, ctx->d_info, st);
+  return launch_stats<float>(ctx, (const float *)d_in, N, d_stats3, 0, N, nullptr, ctx->d_info, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 2: fused compress
+// ------------------------------------------------------------------------------------------
+template <typename T, bool QT>
+static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb, uint8_t *d_bins, float *d_dc, float *d_ac,
+                           void *d_qtable_raw, Info *d_info, cudaStream_t st) {
+  typedef CompressCfg<T, QT> Cfg;
+  typedef typename BitsOf<T>::U U;
+  const unsigned long long nblk_full = N / BLK;
+  const int rem = (int)(N % BLK);
+  const QuantConsts<T> qc = make_quant<T>(eb);
+  T *raw = nullptr;
+  uint8_t *jpos = nullptr;
+  if (QT) {
+    TRY(grow(ctx, ctx->qt_raw, N * sizeof(T)));
+    TRY(grow(ctx, ctx->qt_j, N));
+    raw = (T *)ctx->qt_raw.p;
+    jpos = (uint8_t *)ctx->qt_j.p;
+  }
+  if (nblk_full) {
+    const size_t ntiles = (nblk_full + TILE_BLOCKS - 1) / TILE_BLOCKS;
+    if (ntiles > 0xFFFFFFF0ull) return fail(ctx, DCTZ_GPU_EINVAL, "slab too large: %zu tiles", ntiles);
+    TRY(next_epoch(ctx, ntiles, st));
+    const size_t resident = (size_t)ctx->sm_count * ctx->occ[0][sizeof(T) == 8][QT];
+    const int grid = (int)(ntiles < resident ? ntiles : resident);
+    k_compress<T, QT><<<grid, TILE_BLOCKS, Cfg::SMEM, st>>>(d_in, nblk_full, ctx->d_params, qc, d_bins, d_dc, d_ac, raw, jpos,
+                                                            (U *)d_qtable_raw, (T *)d_qtable_raw,
+                                                            (unsigned long long *)ctx->status.p, ctx->epoch, &ctx->d_ctl[0], d_info);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  if (rem) {
+    k_tail_compress<T, QT><<<1, 32, 0, st>>>(d_in + nblk_full * BLK, rem, nblk_full, ctx->d_params, qc, d_bins, d_dc, d_ac, raw,
+                                             jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, d_info);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  return DCTZ_GPU_OK;
+}
+
+static int compress_dispatch(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt, uint8_t *d_bins,
+                             float *d_dc, float *d_ac, void *d_qtable_raw, Info *d_info, cudaStream_t st) {
+  if (datatype == DCTZ_GPU_DOUBLE) {
+    if (mode_qt) return launch_compress<double, true>(ctx, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
+    return launch_compress<double, false>(ctx, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
+  }
+  if (mode_qt) return launch_compress<float, true>(ctx, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
+  return launch_compress<float, false>(ctx, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
+}
+
+static int check_compress_args(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt,
+                               const void *d_bins, const void *d_dc, const void *d_ac, const void *d_qtable_raw, const void *d_info) {
+  TRY(check_common(ctx, datatype, eb));
+  if (!d_in || !d_bins || !d_dc || !d_ac || !d_info || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "compress: NULL pointer or N == 0");
+  if (mode_qt && !d_qtable_raw) return fail(ctx, DCTZ_GPU_EINVAL, "compress: QT mode needs d_qtable_raw");
+  if (!aligned16(d_in) || !aligned16(d_bins)) return fail(ctx, DCTZ_GPU_EINVAL, "compress: input and bin_index must be 16-byte aligned");
+  if (!aligned16(d_ac) || ((uintptr_t)d_dc & 3u)) return fail(ctx, DCTZ_GPU_EINVAL, "compress: AC_exact / DC alignment");
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb,
+                                     int mode_qt, const double *d_stats_all, int nranks, int first_slab, uint8_t *d_bins,
+                                     float *d_dc, float *d_ac, void *d_qtable_raw, dctz_gpu_info *d_info, void *stream) {
+  TRY(check_compress_args(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, d_info));
+  if (!d_stats_all || nranks < 1 || N_total < N) return fail(ctx, DCTZ_GPU_EINVAL, "compress: bad statistics arguments");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  SfTables tb = ctx->tb;
+  tb.qmax_words = (int)(BLK * (datatype == DCTZ_GPU_DOUBLE ? 8 : 4) / 8);
+  k_finalize<<<1, 32, 0, st>>>(d_stats_all, nranks, (unsigned long long)N_total, datatype == DCTZ_GPU_DOUBLE, d_in, first_slab, tb,
+                               ctx->d_params, (Info *)d_info, mode_qt ? (unsigned long long *)d_qtable_raw : nullptr);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return compress_dispatch(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, (Info *)d_info, st);
+}
+
+template <typename T>
+static int launch_qt_finish(dctz_gpu_ctx *ctx, double eb, const T *d_qraw, T *d_qtable, float *d_ac, Info *d_info, cudaStream_t st) {
+  const QtConsts<T> k = make_qt<T>(eb);
+  const int grid = ctx->sm_count * 4;
+  k_qt_rescale<T><<<grid, 256, 0, st>>>((const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, d_qtable, k, d_ac, d_info);
+  k_qt_compact<T><<<1, 32, 0, st>>>((const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, k, d_ac, d_info);
+  ctx->launches += 2;
+  CU(cudaGetLastError());
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_qt_finish_dev(dctz_gpu_ctx *ctx, int datatype, double eb, const void *d_qtable_raw, void *d_qtable,
+                                      float *d_ac, dctz_gpu_info *d_info, void *stream) {
+  TRY(check_common(ctx, datatype, eb));
+  if (!d_qtable_raw || !d_ac || !d_info) return fail(ctx, DCTZ_GPU_EINVAL, "qt_finish: NULL pointer");
+  if (!ctx->qt_raw.p) return fail(ctx, DCTZ_GPU_EINVAL, "qt_finish: no QT compress call preceded");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (datatype == DCTZ_GPU_DOUBLE)
+    return launch_qt_finish<double>(ctx, eb, (const double *)d_qtable_raw, (double *)d_qtable, d_ac, (Info *)d_info, st);
+  return launch_qt_finish<float>(ctx, eb, (const float *)d_qtable_raw, (float *)d_qtable, d_ac, (Info *)d_info, st);
+}
+
+extern "C" int dctz_gpu_compress_field_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt,
+                                           uint8_t *d_bins, float *d_dc, float *d_ac, void *d_qtable, void *d_qtable_raw,
+                                           dctz_gpu_info *d_info, void *stream) {
+  TRY(check_compress_args(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, d_info));
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  void *qz = mode_qt ? d_qtable_raw : nullptr;
+  if (datatype == DCTZ_GPU_DOUBLE) TRY(launch_stats<double>(ctx, (const double *)d_in, N, ctx->d_stats3, 1, N, qz, (Info *)d_info, st));
+  else TRY(launch_stats<float>(ctx, (const float *)d_in, N, ctx->d_stats3, 1, N, qz, (Info *)d_info, st));
+  TRY(compress_dispatch(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, (Info *)d_info, st));
+  if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, d_qtable_raw, d_qtable, d_ac, d_info, stream));
+  return DCTZ_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// decompress
+// ------------------------------------------------------------------------------------------
+template <typename T, bool QT>
+static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const float *d_dc, const float *d_ac, const T *d_qtable,
+                             size_t N, double eb, double sf, T *d_out, cudaStream_t st) {
+  typedef DecompressCfg<T, QT> Cfg;
+  const unsigned long long nblk_full = N / BLK;
+  const int rem = (int)(N % BLK);
+  const QtConsts<T> qk = make_qt<T>(eb);
+  // gen_bins: bin_width = error_bound*2*BRSF (binning.c:16); gen_bins_f receives the bound as float (binning.c:32-36)
+  const T bw = (sizeof(T) == 8) ? (T)(eb * 2 * 1.0) : (T)(float)((float)eb * 2 * 1.0);
+  const T sfT = (T)sf;
+  if (nblk_full) {
+    const size_t ntiles = (nblk_full + TILE_BLOCKS - 1) / TILE_BLOCKS;
+    if (ntiles > 0xFFFFFFF0ull) return fail(ctx, DCTZ_GPU_EINVAL, "slab too large: %zu tiles", ntiles);
+    TRY(next_epoch(ctx, ntiles, st));
+    const size_t resident = (size_t)ctx->sm_count * ctx->occ[1][sizeof(T) == 8][QT];
+    const int grid = (int)(ntiles < resident ? ntiles : resident);
+    k_decompress<T, QT><<<grid, TILE_BLOCKS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, d_out,
+                                                              (unsigned long long *)ctx->status.p, ctx->epoch, &ctx->d_ctl[1],
+                                                              ctx->d_nconsumed);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  if (rem) {
+    k_tail_decompress<T, QT><<<1, 32, 0, st>>>(d_bins, d_dc, d_ac, d_qtable, rem, nblk_full, bw, sfT, qk, d_out,
+                                               nblk_full ? ctx->d_nconsumed : nullptr, 0ull);
+    ctx->launches++;
+    CU(cudaGetLastError());
+  }
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_decompress_dev(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const float *d_dc, const float *d_ac,
+                                       const void *d_qtable, size_t N, int datatype, double eb, double sf, int mode_qt, void *d_out,
+                                       void *stream) {
+  TRY(check_common(ctx, datatype, eb));
+  if (!d_bins || !d_dc || !d_out || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: NULL pointer or N == 0");
+  if (mode_qt && !d_qtable) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: QT mode needs the qtable");
+  if (!aligned16(d_bins) || !aligned16(d_out)) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: bin_index and output must be 16-byte aligned");
+  if (!(sf > 0.0) || isinf(sf)) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: scaling factor %g is not a positive finite number", sf);
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (datatype == DCTZ_GPU_DOUBLE) {
+    if (mode_qt) return launch_decompress<double, true>(ctx, d_bins, d_dc, d_ac, (const double *)d_qtable, N, eb, sf, (double *)d_out, st);
+    return launch_decompress<double, false>(ctx, d_bins, d_dc, d_ac, (const double *)d_qtable, N, eb, sf, (double *)d_out, st);
+  }
+  if (mode_qt) return launch_decompress<float, true>(ctx, d_bins, d_dc, d_ac, (const float *)d_qtable, N, eb, sf, (float *)d_out, st);
+  return launch_decompress<float, false>(ctx, d_bins, d_dc, d_ac, (const float *)d_qtable, N, eb, sf, (float *)d_out, st);
+}
+
+extern "C" int dctz_gpu_scale_dev(dctz_gpu_ctx *ctx, void *d_x, size_t N, int datatype, double sf, int multiply, void *stream) {
+  TRY(check_common(ctx, datatype, 1.0));
+  if (!d_x || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "scale: NULL pointer or N == 0");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t want = (N + 255) / 256;
+  const int grid = (int)(want < (size_t)ctx->sm_count * 16 ? want : (size_t)ctx->sm_count * 16);
+  if (datatype == DCTZ_GPU_DOUBLE) k_scale<double><<<grid, 256, 0, st>>>((double *)d_x, N, sf, multiply);
+  else k_scale<float><<<grid, 256, 0, st>>>((float *)d_x, N, (float)sf, multiply);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return DCTZ_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer API (the drop-in seam)
+// ------------------------------------------------------------------------------------------
+extern "C" int dctz_gpu_compress_core(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, double eb, int mode_qt,
+                                      void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact, void *qtable,
+                                      void *qtable_raw, dctz_gpu_info *info) {
+  TRY(check_common(ctx, datatype, eb));
+  if (!in || !bin_index || !DC || !AC_exact || !info || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "compress_core: NULL pointer or N == 0");
+  if (mode_qt && !qtable) return fail(ctx, DCTZ_GPU_EINVAL, "compress_core: QT mode needs a qtable output");
+  CU(cudaSetDevice(ctx->device));
+  const size_t es = datatype == DCTZ_GPU_DOUBLE ? 8 : 4;
+  const size_t nblk = (N + BLK - 1) / BLK;
+  cudaStream_t st = ctx->stream;
+  TRY(grow(ctx, ctx->in, N * es));
+  TRY(grow(ctx, ctx->bins, N));
+  TRY(grow(ctx, ctx->dc, nblk * 4));
+  TRY(grow(ctx, ctx->ac, N * 4));
+  TRY(grow(ctx, ctx->qt, BLK * 8));
+  TRY(grow(ctx, ctx->qtraw, BLK * 8));
+  CU(cudaMemcpyAsync(ctx->in.p, in, N * es, cudaMemcpyHostToDevice, st));
+  TRY(dctz_gpu_compress_field_dev(ctx, ctx->in.p, N, datatype, eb, mode_qt, (uint8_t *)ctx->bins.p, (float *)ctx->dc.p,
+                                  (float *)ctx->ac.p, ctx->qt.p, ctx->qtraw.p, (dctz_gpu_info *)ctx->d_info, st));
+  CU(cudaMemcpyAsync(info, ctx->d_info, sizeof(Info), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(bin_index, ctx->bins.p, N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(DC, ctx->dc.p, nblk * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (info->status != 0)
+    return fail(ctx, info->status, "compress_core: max|x| = %g gives no usable scaling factor (util.c:28 would yield 0/inf/NaN)", info->max_abs);
+  if (info->n_outliers) CU(cudaMemcpyAsync(AC_exact, ctx->ac.p, info->n_outliers * 4, cudaMemcpyDeviceToHost, st));
+  if (mode_qt) {
+    CU(cudaMemcpyAsync(qtable, ctx->qt.p, BLK * es, cudaMemcpyDeviceToHost, st));
+    if (qtable_raw) CU(cudaMemcpyAsync(qtable_raw, ctx->qtraw.p, BLK * es, cudaMemcpyDeviceToHost, st));
+  }
+  if (scaled_out) {  // the reference leaves x/sf in the caller's buffer (dctz-comp-lib.c:198,213)
+    if (info->sf != 1.0) {
+      TRY(dctz_gpu_scale_dev(ctx, ctx->in.p, N, datatype, info->sf, 0, st));
+      CU(cudaMemcpyAsync(scaled_out, ctx->in.p, N * es, cudaMemcpyDeviceToHost, st));
+    } else if (scaled_out != in) {
+      memcpy(scaled_out, in, N * es);
+    }
+  }
+  CU(cudaStreamSynchronize(st));
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_decompress_core(dctz_gpu_ctx *ctx, const uint8_t *bin_index, const float *DC, const float *AC_exact,
+                                        uint64_t n_outliers, const void *qtable, size_t N, int datatype, double eb, double sf,
+                                        int mode_qt, void *out) {
+  TRY(check_common(ctx, datatype, eb));
+  if (!bin_index || !DC || !out || N == 0 || (n_outliers && !AC_exact)) return fail(ctx, DCTZ_GPU_EINVAL, "decompress_core: NULL pointer or N == 0");
+  if (mode_qt && !qtable) return fail(ctx, DCTZ_GPU_EINVAL, "decompress_core: QT mode needs the qtable");
+  CU(cudaSetDevice(ctx->device));
+  const size_t es = datatype == DCTZ_GPU_DOUBLE ? 8 : 4;
+  const size_t nblk = (N + BLK - 1) / BLK;
+  cudaStream_t st = ctx->stream;
+  TRY(grow(ctx, ctx->bins, N));
+  TRY(grow(ctx, ctx->dc, nblk * 4));
+  TRY(grow(ctx, ctx->ac, (n_outliers ? n_outliers : 1) * 4));
+  TRY(grow(ctx, ctx->qt, BLK * 8));
+  TRY(grow(ctx, ctx->out, N * es));
+  CU(cudaMemcpyAsync(ctx->bins.p, bin_index, N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->dc.p, DC, nblk * 4, cudaMemcpyHostToDevice, st));
+  if (n_outliers) CU(cudaMemcpyAsync(ctx->ac.p, AC_exact, n_outliers * 4, cudaMemcpyHostToDevice, st));
+  if (mode_qt) CU(cudaMemcpyAsync(ctx->qt.p, qtable, BLK * es, cudaMemcpyHostToDevice, st));
+  TRY(dctz_gpu_decompress_dev(ctx, (const uint8_t *)ctx->bins.p, (const float *)ctx->dc.p, (const float *)ctx->ac.p, ctx->qt.p, N,
+                              datatype, eb, sf, mode_qt, ctx->out.p, st));
+  CU(cudaMemcpyAsync(out, ctx->out.p, N * es, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return DCTZ_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// DCT-only entry point (dct.h:17-27 equivalents) and utilities
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static int dct_blocks_impl(dctz_gpu_ctx *ctx, const T *in, T *out, size_t nblocks, int dn, int inverse) {
+  const size_t bytes = nblocks * (size_t)dn * sizeof(T);
+  cudaStream_t st = ctx->stream;
+  TRY(grow(ctx, ctx->in, bytes));
+  TRY(grow(ctx, ctx->out, bytes));
+  CU(cudaMemcpyAsync(ctx->in.p, in, bytes, cudaMemcpyHostToDevice, st));
+  if (dn == BLK) {
+    const unsigned grid = (unsigned)((nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS);
+    if (inverse) k_dct64_blocks<T, true><<<grid, TILE_BLOCKS, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, nblocks);
+    else k_dct64_blocks<T, false><<<grid, TILE_BLOCKS, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, nblocks);
+  } else {
+    if (inverse) k_dct_generic_blocks<T, true><<<(unsigned)nblocks, 32, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, dn);
+    else k_dct_generic_blocks<T, false><<<(unsigned)nblocks, 32, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, dn);
+  }
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, ctx->out.p, bytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_dct_blocks(dctz_gpu_ctx *ctx, const void *in, void *out, size_t nblocks, int dn, int datatype, int inverse) {
+  TRY(check_common(ctx, datatype, 1.0));
+  if (!in || !out || nblocks == 0 || dn < 1 || dn > BLK) return fail(ctx, DCTZ_GPU_EINVAL, "dct_blocks: bad arguments (1 <= dn <= 64)");
+  if (nblocks > 0x7FFFFFFFull) return fail(ctx, DCTZ_GPU_EINVAL, "dct_blocks: too many blocks");
+  CU(cudaSetDevice(ctx->device));
+  if (datatype == DCTZ_GPU_DOUBLE) return dct_blocks_impl<double>(ctx, (const double *)in, (double *)out, nblocks, dn, inverse);
+  return dct_blocks_impl<float>(ctx, (const float *)in, (float *)out, nblocks, dn, inverse);
+}
+
+extern "C" int dctz_gpu_fill_hash_field(dctz_gpu_ctx *ctx, double *d_out, uint64_t start, uint64_t count, uint32_t dim, uint32_t seed,
+                                        void *stream) {
+  if (!ctx) return fail(nullptr, DCTZ_GPU_EINVAL, "ctx is NULL");
+  if (!d_out || count == 0 || dim == 0 || (dim & (dim - 1))) return fail(ctx, DCTZ_GPU_EINVAL, "fill_hash_field: dim must be a power of two");
+  CU(cudaSetDevice(ctx->device));
+  k_fill_hash_field<<<ctx->sm_count * 16, 256, 0, (cudaStream_t)stream>>>(d_out, start, count, dim, seed);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_selftest_division(dctz_gpu_ctx *ctx, int datatype, double b, uint64_t count, uint32_t seed,
+                                          uint64_t *mismatches) {
+  TRY(check_common(ctx, datatype, 1.0));
+  if (!mismatches) return fail(ctx, DCTZ_GPU_EINVAL, "selftest: NULL pointer");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemsetAsync(ctx->d_mismatch, 0, 8, st));
+  if (datatype == DCTZ_GPU_DOUBLE) k_selftest_division<double><<<ctx->sm_count * 8, 256, 0, st>>>(b, count, seed, ctx->d_mismatch);
+  else k_selftest_division<float><<<ctx->sm_count * 8, 256, 0, st>>>((float)b, count, seed, ctx->d_mismatch);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  unsigned long long m = 0;
+  CU(cudaMemcpyAsync(&m, ctx->d_mismatch, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *mismatches = m;
+  return DCTZ_GPU_OK;
+}

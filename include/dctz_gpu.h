@@ -1,0 +1,174 @@
+/* dctz_gpu.h -- C-ABI boundary of the B200-native DCTZ hot path (libdctz_gpu.so).
+ *
+ * Plain C: opaque handle, raw pointers, sizes.  No CUDA or C++ types appear in any signature
+ * (streams travel as void*), so the reference's C host code -- or any FFI -- can bind it directly.
+ *
+ * What it replaces in the reference (swson/DCTZ v0.2.2), i.e. where a maintainer cuts the seam:
+ *   compress:   dctz-comp-lib.c:186-217  calc_data_stat + in-place scale          (util.c:12-44)
+ *               dctz-comp-lib.c:271-281  quantiser parameters
+ *               dctz-comp-lib.c:318-420  per-block DCT (dct.c:55-103 / dct-float.c:56-104),
+ *                                        DC, bin indices, qtable maxima
+ *               dctz-comp-lib.c:443-476  qtable clamp / qt_factor
+ *               dctz-comp-lib.c:478-544  ordered outlier ("AC_exact") compaction, QT rescale
+ *   decompress: dctz-decomp-lib.c:358-386 bin centres (binning.c:12-50), ranges
+ *               dctz-decomp-lib.c:389-483 dequantise + per-block inverse DCT (dct.c:115-205)
+ *               dctz-decomp-lib.c:494-511 de-scale
+ * Everything else of dctz_compress()/dctz_decompress() (allocation, debug dumps, the three zlib
+ * streams, header and stream assembly) stays host C and calls these entry points; see
+ * INTEGRATION.md for the exact edit and dctz_b200/csrc/host/ for a host library that does it.
+ *
+ * Conventions
+ *   - datatype uses the reference's t_datatype values (dctz.h:44-47): 0 = FLOAT, 1 = DOUBLE.
+ *   - mode_qt: 0 = error-controlled build ("ec", default), 1 = -DUSE_QTABLE build ("qt").
+ *   - every function returns 0 on success or a negative DCTZ_GPU_E* code;
+ *     dctz_gpu_last_error() gives the message.  There is NO CPU fallback: without a usable
+ *     CUDA device every call fails with DCTZ_GPU_ENODEV.
+ *   - N may exceed 2^31 (the reference's `int N` limit is a property of its stream header, not of
+ *     this layer); outlier counts are 64-bit.
+ *   - *_dev entry points take device pointers, enqueue on the given stream and do not
+ *     synchronise; host-buffer entry points are synchronous.
+ */
+#ifndef DCTZ_GPU_H
+#define DCTZ_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCTZ_GPU_FLOAT 0
+#define DCTZ_GPU_DOUBLE 1
+
+#define DCTZ_GPU_OK 0
+#define DCTZ_GPU_ENODEV (-1)    /* no CUDA device / driver */
+#define DCTZ_GPU_ECUDA (-2)     /* a CUDA call failed */
+#define DCTZ_GPU_EINVAL (-3)    /* bad argument (eb < 1e-6 like dctz-comp-lib.c:135, alignment, ...) */
+#define DCTZ_GPU_ENOMEM (-4)
+#define DCTZ_GPU_EDEGENERATE (-5) /* max|x| is 0, inf or NaN: the reference computes sf = 0/NaN (util.c:28) */
+
+#define DCTZ_GPU_BLK 64    /* BLK_SZ, dctz.h:28 */
+#define DCTZ_GPU_NBINS 255 /* NBINS,  dctz.h:66 */
+
+typedef struct dctz_gpu_ctx dctz_gpu_ctx;
+
+/* Result block of one compress call (device-resident in the *_dev API, copied out by the host API). */
+typedef struct dctz_gpu_info {
+  double sf;        /* scaling factor, util.c:28/42 (float path: the float value, widened)          */
+  double mean;      /* util.c:27/41; order-dependent in the reference -> compare with a tolerance   */
+  double max_abs;   /* bs.max */
+  double min_abs;   /* bs.min */
+  double sum;       /* sum over x[1..N-1] (util.c:21-25 skips element 0)                            */
+  uint64_t n_outliers; /* tot_AC_exact_count, dctz-comp-lib.c:323                                   */
+  uint64_t n_edge;     /* coefficients at ordinal 255 (item == range_max): the reference indexes
+                          conv_tbl[255] out of bounds; we clamp to ordinal 254 and count (double
+                          path only)                                                 */
+  uint64_t n_exact_path; /* double path: coefficients routed through the exact-division slow path   */
+  uint64_t n_qt_dropped; /* QT: rescaled outliers that fell back inside the bin range and are
+                            therefore not stored (dctz-comp-lib.c:494-506 quirk)                     */
+  int32_t status;      /* 0, or DCTZ_GPU_EDEGENERATE                                                */
+  int32_t scale_mode;  /* 0: sf == 1 (no scaling), 1/2: exact reciprocal division iterations, 3: IEEE div */
+} dctz_gpu_info;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int dctz_gpu_create(dctz_gpu_ctx **ctx, int device);
+void dctz_gpu_destroy(dctz_gpu_ctx *ctx);
+const char *dctz_gpu_last_error(const dctz_gpu_ctx *ctx); /* ctx may be NULL (creation errors) */
+int dctz_gpu_device_count(void);
+int dctz_gpu_sm_count(const dctz_gpu_ctx *ctx);
+
+/* pinned host memory for callers that want full-speed PCIe copies */
+void *dctz_gpu_host_alloc(size_t bytes);
+void dctz_gpu_host_free(void *p);
+
+/* ---- host-buffer API: the drop-in seam ------------------------------------------------------
+ * compress_core: `in` holds N elements (float or double).  Outputs, all caller-allocated host
+ * memory: bin_index[N]; DC[ceil(N/64)]; AC_exact[capacity N floats]; qtable / qtable_raw[64
+ * elements of the data type, may be NULL unless mode_qt] = the table after / before the >= 1.0
+ * clamp (stream trailer / qtable.bin dump).  If scaled_out is non-NULL it receives x[i]/sf, the
+ * value the reference leaves in the caller's input buffer (dctz-comp-lib.c:198,213); passing
+ * scaled_out == in reproduces the in-place mutation.                                          */
+int dctz_gpu_compress_core(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, double error_bound,
+                           int mode_qt, void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact,
+                           void *qtable, void *qtable_raw, dctz_gpu_info *info);
+
+/* decompress_core: inverse of the above; `out` receives N reconstructed elements.
+ * qtable (64 elements, clamped table from the stream trailer) is only read when mode_qt.      */
+int dctz_gpu_decompress_core(dctz_gpu_ctx *ctx, const uint8_t *bin_index, const float *DC,
+                             const float *AC_exact, uint64_t n_outliers, const void *qtable, size_t N,
+                             int datatype, double error_bound, double sf, int mode_qt, void *out);
+
+/* ---- device-resident API (benchmarks, multi-GPU slabs, pipelines) ---------------------------
+ * All pointers are device pointers on ctx's device; `stream` is a cudaStream_t passed as void*
+ * (NULL = default stream).  Input/outputs must be 16-byte aligned.
+ *
+ * Split phases so that a multi-GPU caller can exchange the global statistics between them
+ * (SURVEY.md §8e): stats_dev -> [all-gather 3 doubles per rank] -> compress_dev.               */
+
+/* Phase 1: local statistics of a slab.  d_stats3 receives {max|x|, min|x|, sum(x)} as doubles. */
+int dctz_gpu_stats_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double *d_stats3,
+                       void *stream);
+
+/* Phase 2: scale + DCT + quantise + ordered outlier compaction of a slab of `N` elements that is
+ * part of a field of `N_total` elements.  d_stats_all holds `nranks` triples from phase 1 in rank
+ * order (nranks = 1: the slab's own).  `first_slab` != 0 for the slab that contains element 0 of
+ * the field (its value is excluded from the sum like util.c:21-25 does).  Only the last slab may
+ * have N % 64 != 0.  In QT mode the outliers are left un-rescaled in internal scratch and
+ * d_qtable_raw receives this slab's per-position maxima; call dctz_gpu_qt_finish_dev afterwards.
+ * d_AC_exact needs room for N floats.  d_info receives the result block.                       */
+int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype,
+                          double error_bound, int mode_qt, const double *d_stats_all, int nranks,
+                          int first_slab, uint8_t *d_bin_index, float *d_DC, float *d_AC_exact,
+                          void *d_qtable_raw, dctz_gpu_info *d_info, void *stream);
+
+/* Phase 3 (QT only): d_qtable_raw now holds the GLOBAL maxima (after the caller's all-reduce;
+ * entry 0 = DC of the field's last block).  Writes the clamped table to d_qtable, rescales the
+ * slab's outliers into d_AC_exact and finalises d_info->n_outliers.                            */
+int dctz_gpu_qt_finish_dev(dctz_gpu_ctx *ctx, int datatype, double error_bound, const void *d_qtable_raw,
+                           void *d_qtable, float *d_AC_exact, dctz_gpu_info *d_info, void *stream);
+
+/* Convenience: phases 1+2(+3) for a whole field on one GPU, nothing leaves the device.          */
+int dctz_gpu_compress_field_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype,
+                                double error_bound, int mode_qt, uint8_t *d_bin_index, float *d_DC,
+                                float *d_AC_exact, void *d_qtable, void *d_qtable_raw,
+                                dctz_gpu_info *d_info, void *stream);
+
+/* Dequantise + inverse DCT + de-scale of a slab.  d_AC_exact points at the slab's first outlier. */
+int dctz_gpu_decompress_dev(dctz_gpu_ctx *ctx, const uint8_t *d_bin_index, const float *d_DC,
+                            const float *d_AC_exact, const void *d_qtable, size_t N, int datatype,
+                            double error_bound, double sf, int mode_qt, void *d_out, void *stream);
+
+/* x[i] <- x[i] / sf with IEEE division (the reference's in-place scaling, dctz-comp-lib.c:193-216),
+ * and its inverse x[i] <- x[i] * sf (dctz-test.c:186-210, dctz-decomp-lib.c:494-511).          */
+int dctz_gpu_scale_dev(dctz_gpu_ctx *ctx, void *d_x, size_t N, int datatype, double sf, int multiply,
+                       void *stream);
+
+/* ---- thin GPU-backed equivalents of the reference's DCT entry points (dct.h:17-27) -----------
+ * nblocks contiguous blocks of dn elements each (dn = 64 uses the register-resident kernels,
+ * any other 1 <= dn <= 64 the generic tail kernel).  Host buffers, synchronous.                */
+int dctz_gpu_dct_blocks(dctz_gpu_ctx *ctx, const void *in, void *out, size_t nblocks, int dn, int datatype,
+                        int inverse);
+
+/* ---- utilities ----------------------------------------------------------------------------- */
+/* Elements [start, start+count) of the exactly reproducible synthetic 3-D field of SURVEY.md §8d
+ * (config C5), written as doubles to d_out; host twin: dctz_b200/fields.py:hash_field.          */
+int dctz_gpu_fill_hash_field(dctz_gpu_ctx *ctx, double *d_out, uint64_t start, uint64_t count, uint32_t dim,
+                             uint32_t seed, void *stream);
+/* sf exactly as the host libm computes it (util.c:28/42) but through the device-side threshold
+ * tables; exported so the tables can be verified against libm on the CPU.                       */
+double dctz_gpu_sf_from_max(const dctz_gpu_ctx *ctx, double max_abs, int datatype);
+/* Self-test of the exact reciprocal division used by the kernels: compares a/b computed by the
+ * FMA sequence with IEEE division for `count` pseudo-random a; returns the mismatch count.      */
+int dctz_gpu_selftest_division(dctz_gpu_ctx *ctx, int datatype, double b, uint64_t count, uint32_t seed,
+                               uint64_t *mismatches);
+/* Number of kernels launched by this context so far (bench.py's gpu_launches).                  */
+uint64_t dctz_gpu_launch_count(const dctz_gpu_ctx *ctx);
+/* Kernel variant switches for A/B measurements: name = "dct" -> 0 butterfly (default), 1 FP64 DMMA
+ * matrix form (double only).  Returns the previous value or a negative error.                   */
+int dctz_gpu_set_option(dctz_gpu_ctx *ctx, const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCTZ_GPU_H */

@@ -1,0 +1,130 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes -> libdctz_gpu.so),
+against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from dctz_b200 import fields
+from tests import parity, reflib
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float64, np.float32]
+
+
+def _signal(n, dtype, seed=11, noise=0.01):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    return (3.0 + 2.5 * np.sin(t / 37.0) + 0.4 * np.cos(t / 3.3) + noise * rng.standard_normal(n)).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_division_selftest(ctx, dtype):
+    # the reciprocal-FMA division used for x/sf and (c - range_min)/bin_width must equal IEEE division
+    for b in (0.1, 10.0, 100.0, 1e-3, 1000.0, 2e-3, 2e-4, 2e-5, 1e7, 1e-7):
+        b = float(np.dtype(dtype).type(b))
+        assert ctx.selftest_division(dtype, b, 1 << 22, seed=3) == 0, b
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_sf_tables_match_libm_on_device_path(ctx, dtype):
+    # sf comes from device-side threshold tables; the compress result must carry libm's value
+    for scale in (1e-6, 0.003, 0.999, 1.0, 1.0001, 9.99, 10.0, 10.01, 123.0, 99999.0, 1e5, 3e7):
+        x = (np.linspace(-1, 1, 640) * scale).astype(dtype)
+        x[17] = dtype(scale)
+        g = ctx.compress_core(x, 1e-3)
+        o = reflib.oracle_stat(x)
+        assert g["sf"] == o["sf"], (scale, g["sf"], o["sf"])
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("inverse", [False, True])
+def test_dct64_coefficients(ctx, dtype, inverse):
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(64 * 4096) * rng.choice([1e-3, 1.0, 50.0], 64 * 4096)).astype(dtype)
+    got = ctx.dct_blocks(x, 64, inverse=inverse).astype(np.float64).reshape(-1, 64)
+    want = np.stack([reflib.oracle_dct(b, inverse=inverse) for b in x.reshape(-1, 64)[:512]]).astype(np.float64)
+    got = got[:512]
+    scale = np.max(np.abs(want), axis=1, keepdims=True)
+    assert np.max(np.abs(got - want) / scale) <= parity.RTOL[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("dn", [1, 2, 3, 12, 15, 17, 32, 37, 63])
+def test_dct_tail_lengths(ctx, dtype, dn):
+    rng = np.random.default_rng(dn)
+    x = rng.standard_normal(dn * 8).astype(dtype)
+    for inverse in (False, True):
+        got = ctx.dct_blocks(x, dn, inverse=inverse).astype(np.float64).reshape(-1, dn)
+        want = np.stack([reflib.oracle_dct(b, inverse=inverse) for b in x.reshape(-1, dn)]).astype(np.float64)
+        scale = np.max(np.abs(want), axis=1, keepdims=True)
+        assert np.max(np.abs(got - want) / scale) <= parity.RTOL[np.dtype(dtype)] * 4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("qt", [False, True])
+@pytest.mark.parametrize("eb", [1e-3, 1e-4, 1e-5])
+def test_compress_parity_signal(ctx, dtype, qt, eb):
+    x = _signal(64 * 3000 + 37, dtype)
+    rep = parity.check_compress(ctx, x, eb, qt)
+    assert rep["tie_fraction"] < (1e-6 if dtype == np.float64 else 5e-2), rep
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("qt", [False, True])
+def test_small_cases(ctx, dtype, qt):
+    for name, x in fields.small_cases(dtype).items():
+        try:
+            parity.check_compress(ctx, x, 1e-3, qt)
+            parity.check_decompress(ctx, x, 1e-3, qt)
+        except AssertionError as e:  # pragma: no cover
+            raise AssertionError(f"case {name}: {e}") from e
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("qt", [False, True])
+@pytest.mark.parametrize("eb", [1e-3, 1e-5])
+def test_decompress_parity(ctx, dtype, qt, eb):
+    x = _signal(64 * 3000 + 21, dtype, seed=5, noise=0.05)
+    parity.check_decompress(ctx, x, eb, qt)
+
+
+def test_degenerate_inputs_are_rejected(ctx):
+    import dctz_b200
+
+    with pytest.raises(dctz_b200.DctzGpuError):
+        ctx.compress_core(np.zeros(640), 1e-3)  # max|x| == 0: the reference computes sf = 0 (util.c:28)
+    with pytest.raises(dctz_b200.DctzGpuError):
+        ctx.compress_core(np.ones(640), 1e-7)  # eb < 1e-6: dctz-comp-lib.c:135 exits
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_roundtrip_error_bound(ctx, dtype):
+    """GPU compress -> GPU decompress; every non-outlier AC coefficient is reproduced within eb
+    (scaled domain) and the point-wise error obeys the orthonormal-basis bound."""
+    eb = 1e-3
+    x = _signal(64 * 5000, dtype, seed=9)
+    g = ctx.compress_core(x, eb)
+    r = ctx.decompress_core(g["bin_index"], g["dc"], g["ac"], x.size, dtype, eb, g["sf"])
+    err = np.abs(r.astype(np.float64) - x.astype(np.float64)) / g["sf"]
+    assert err.max() <= eb * (1 + 63 * np.sqrt(2)) / 8 * 1.01
+    cx = np.stack([reflib.oracle_dct_exact(b) for b in (x.astype(np.float64) / g["sf"]).reshape(-1, 64)[:256]])
+    cr = np.stack([reflib.oracle_dct_exact(b) for b in (r.astype(np.float64) / g["sf"]).reshape(-1, 64)[:256]])
+    bins = g["bin_index"].reshape(-1, 64)[:256]
+    inb = bins != 255
+    tol = eb * (1 + 1e-9) + (1e-12 if dtype == np.float64 else 2e-5)
+    assert np.max(np.abs(cx - cr)[inb]) <= tol
+
+
+def test_cesm_config_c1(ctx):
+    """configs[0]: CESM-ATM-shaped 1800x3600 double, eb 1E-3, EC -- full size against the oracle."""
+    x = fields.cesm_like()
+    rep = parity.check_compress(ctx, x, 1e-3, False)
+    assert rep["ties"] <= 8, rep
+    parity.check_decompress(ctx, x, 1e-3, False)
+
+
+def test_cesm_config_c2_qt_float(ctx):
+    """configs[1]: 1800x3600 float, QT mode, compress + decompress round trip."""
+    x = fields.cesm_like(dtype=np.float32)
+    parity.check_compress(ctx, x, 1e-3, True)
+    parity.check_decompress(ctx, x, 1e-3, True)
