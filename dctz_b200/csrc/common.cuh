@@ -7,8 +7,6 @@
 namespace dctz {
 
 constexpr int BLK = 64;            // BLK_SZ, dctz.h:28
-constexpr int TILE_BLOCKS = 128;   // blocks per CTA tile == threads per CTA (one block per thread)
-constexpr int NWARPS = TILE_BLOCKS / 32;
 
 // ------------------------------------------------------------------------------------------
 // Arithmetic policies for the generated DCT (dct64_gen.cuh).  Only *_rn intrinsics: nvcc never
@@ -45,8 +43,11 @@ template <> struct ArithOf<float> { typedef ArithF type; };
 //   q0 = RN(a*y); r = a - q0*b (exact, FMA); q1 = RN(q0 + r*y)
 // Markstein's theorem: if y is the correctly rounded reciprocal and q0 is a faithful rounding of
 // a/b, then q1 == RN(a/b) (b's significand not all ones; no under/overflow).  q0 is faithful when
-// the relative error rho of y is < 2^-(p+1); otherwise one more correction step makes it so.
-// The host / finalize kernel measures rho exactly and picks `iters` (see make_divisor()).
+// the relative error rho of y is <= 2^-(p+1): then |a*y - a/b| < ulp(a/b)/2 strictly, so RN(a*y) is one
+// of the two neighbours of a/b; otherwise one more correction step makes it so.
+// The host / finalize kernel measures rho EXACTLY (y*b - 1 is a multiple of 2^-105 (2^-47 for float)
+// and, near 2^-54 (2^-25), exactly representable, so the single-rounding fma returns it exactly)
+// and picks `iters` (see make_divisor()).  sf = 10 and sf = 0.1 both have rho == 2^-54 exactly.
 //   iters: 0 -> b == 1 (identity), 1, 2 -> FMA corrections, 3 -> IEEE division (degenerate b).
 // Deviation window (documented in DESIGN.md): |a| below 2^-969 (double) / 2^-102 (float) lets r
 // underflow, where the last bit of the quotient may differ from IEEE division.
@@ -54,24 +55,24 @@ template <> struct ArithOf<float> { typedef ArithF type; };
 template <typename T> struct Divisor { T b, y; int iters; };
 
 __device__ __forceinline__ double div_exact(double a, const Divisor<double> &d) {
+  if (d.iters == 3) return __ddiv_rn(a, d.b);  // degenerate divisor: kernel-uniform branch
   double q = __dmul_rn(a, d.y);
   double r = __fma_rn(-q, d.b, a);
   q = __fma_rn(r, d.y, q);
-  if (d.iters >= 2) {
+  if (d.iters == 2) {
     r = __fma_rn(-q, d.b, a);
     q = __fma_rn(r, d.y, q);
-    if (d.iters == 3) q = __ddiv_rn(a, d.b);
   }
   return q;
 }
 __device__ __forceinline__ float div_exact(float a, const Divisor<float> &d) {
+  if (d.iters == 3) return __fdiv_rn(a, d.b);
   float q = __fmul_rn(a, d.y);
   float r = __fmaf_rn(-q, d.b, a);
   q = __fmaf_rn(r, d.y, q);
-  if (d.iters >= 2) {
+  if (d.iters == 2) {
     r = __fmaf_rn(-q, d.b, a);
     q = __fmaf_rn(r, d.y, q);
-    if (d.iters == 3) q = __fdiv_rn(a, d.b);
   }
   return q;
 }
@@ -91,7 +92,7 @@ __host__ __device__ inline Divisor<double> make_divisor(double b) {
 #endif
   if (b == 1.0) d.iters = 0;
   else if (!(b == b) || b == 0.0 || m == 0xFFFFFFFFFFFFFull || !(rho < 1.0)) d.iters = 3;
-  else d.iters = (rho < 5.5511151231257e-17 /* 2^-54 (1 - 2^-20) */) ? 1 : 2;
+  else d.iters = (rho <= 5.5511151231257827e-17 /* 2^-54, exact */) ? 1 : 2;
   return d;
 }
 __host__ __device__ inline Divisor<float> make_divisor(float b) {
@@ -109,7 +110,7 @@ __host__ __device__ inline Divisor<float> make_divisor(float b) {
 #endif
   if (b == 1.0f) d.iters = 0;
   else if (!(b == b) || b == 0.0f || m == 0x7FFFFFu || !(rho < 1.0f)) d.iters = 3;
-  else d.iters = (rho < 2.9802294e-08f /* 2^-25 (1 - 2^-20) */) ? 1 : 2;
+  else d.iters = (rho <= 2.98023223876953125e-08f /* 2^-25, exact */) ? 1 : 2;
   return d;
 }
 
@@ -128,125 +129,98 @@ __host__ __device__ __forceinline__ int center_multiple(unsigned id) {
 }
 
 // ------------------------------------------------------------------------------------------
-// cp.async (LDGSTS) helpers: 16-byte global -> shared copies with a per-thread destination, which
-// lets us store a contiguous tile with an XOR swizzle so that the later one-row-per-thread
-// 128-bit shared loads are bank-conflict free.
+// Warp tiles and TMA bulk copies.  The hot kernels are WARP-AUTONOMOUS: each warp owns a tile of
+// 32 consecutive 64-element blocks (one block per lane) and its own slice of shared memory, and
+// never meets the other warps of its CTA at a barrier.  A lane's block (one row of the tile) moves
+// global <-> shared with ONE bulk-copy instruction (cp.async.bulk, SASS UBLKCP): the row is
+// contiguous in global memory and is placed at a row stride of ROW_BYTES + 16 in shared memory, so
+// that the later one-row-per-lane 128-bit shared accesses are bank-conflict free (the 16-byte bank
+// group of chunk c of row r is (r + c) mod 8).  Loads complete on a per-warp mbarrier.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-// Row r (one 64-element block) of a tile holds CH = 64*sizeof(T)/16 chunks of 16 bytes; logical
-// chunk c is stored at physical chunk c ^ (r & (CH-1)).
-template <typename T> struct TileLayout {
+constexpr int WTILE = 32;  // blocks per warp tile (one per lane)
+template <typename T> struct WarpTile {
   static constexpr int ROW_BYTES = BLK * (int)sizeof(T);
+  static constexpr int ROW_STRIDE = ROW_BYTES + 16;
   static constexpr int CH = ROW_BYTES / 16;
-  static constexpr int TILE_BYTES = TILE_BLOCKS * ROW_BYTES;
-  static __device__ __forceinline__ unsigned offset(int row, int chunk) {
-    return (unsigned)(row * ROW_BYTES + ((chunk ^ (row & (CH - 1))) << 4));
-  }
+  static constexpr int BYTES = WTILE * ROW_STRIDE;
 };
 
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned mb, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(mb), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity) {
+  while (!mbar_try_wait(mb, parity)) {}
+}
+// global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mb) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(mb)
+               : "memory");
+}
+// shared -> global, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA) that reads them next
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------
-// Decoupled look-back state, one 64-bit word per tile: [63:62] flag, [61:46] launch epoch,
-// [45:0] value.  A word from another epoch reads as "not ready", so the array never needs to be
-// cleared between launches (the host wraps the epoch and clears once every 65535 launches).
+// Ordered outlier compaction WITHOUT an in-kernel ordered chain.
+//
+// AC_exact must be in (block, j) order (dctz-comp-lib.c:478-544; the decoder consumes it with a serial
+// cursor, dctz-decomp-lib.c:370,402).  A single-pass decoupled look-back was measured first and
+// rejected: every warp tile has to wait for all earlier tiles to be counted, which turns the
+// persistent kernel into an in-order pipeline that runs at the pace of its slowest warp (2.5-6x
+// slower than the same kernel without the chain; profiles/README.md).  Instead:
+//   compress:   K2 writes each warp tile's outliers to a tile-strided scratch slot (TILE_SLOT
+//               floats per tile) plus the tile's count; k_scan_groups turns the counts into
+//               exclusive prefixes per group of 32 tiles; k_gather moves the runs to their final
+//               place (8 bytes of traffic per outlier -- nothing when there are none);
+//   decompress: k_count_bins counts the 255 markers per tile (1 byte/element of extra reads), the
+//               same scan follows, and K3 starts every tile with its offset already known.
+// No kernel ever waits for another warp.
 // ------------------------------------------------------------------------------------------
-constexpr unsigned long long LB_AGG = 1ull, LB_INC = 2ull;
-constexpr unsigned long long LB_VALUE_MASK = (1ull << 46) - 1;
-__device__ __forceinline__ unsigned long long lb_pack(unsigned long long flag, unsigned epoch, unsigned long long v) {
-  return (flag << 62) | ((unsigned long long)(epoch & 0xFFFFu) << 46) | (v & LB_VALUE_MASK);
-}
-__device__ __forceinline__ void lb_store(unsigned long long *p, unsigned long long w) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ unsigned long long lb_load(const unsigned long long *p) {
-  unsigned long long w;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(w) : "l"(p) : "memory");
-  return w;
-}
+constexpr int TILE_SLOT = 2048;  // scratch entries per warp tile (>= 63 * 32 = 2016 outliers worst case)
 
 // Control block shared by all CTAs of a persistent kernel.
 struct TileControl {
-  unsigned ticket;   // next tile index (dynamic scheduling; tickets are handed out in tile order)
+  unsigned ticket;   // next tile index (dynamic scheduling)
   unsigned done;     // CTAs that have exited; the last one resets both fields for the next launch
 };
 
-// Executed by warp 0 of a CTA: exclusive prefix of this tile's `total` over all previous tiles.
-__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long *status, unsigned tile,
-                                                                 unsigned epoch, unsigned long long total,
-                                                                 int lane) {
-  if (tile == 0) {
-    if (lane == 0) lb_store(&status[0], lb_pack(LB_INC, epoch, total));
-    return 0ull;
-  }
-  if (lane == 0) lb_store(&status[tile], lb_pack(LB_AGG, epoch, total));
-  unsigned long long excl = 0;
-  long long idx = (long long)tile - 1;
-  while (true) {
-    const long long my = idx - lane;
-    unsigned long long w;
-    bool ready;
-    do {
-      w = (my >= 0) ? lb_load(&status[my]) : lb_pack(LB_INC, epoch, 0);
-      ready = ((unsigned)(w >> 46) & 0xFFFFu) == (epoch & 0xFFFFu) && (w >> 62) != 0;
-    } while (!__all_sync(0xFFFFFFFFu, ready));
-    const unsigned inc_mask = __ballot_sync(0xFFFFFFFFu, (w >> 62) == LB_INC);
-    unsigned long long v = w & LB_VALUE_MASK;
-    if (inc_mask) {
-      const int first = __ffs(inc_mask) - 1;
-      if (lane > first) v = 0;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    excl += v;
-    if (inc_mask) break;
-    idx -= 32;
-  }
-  if (lane == 0) lb_store(&status[tile], lb_pack(LB_INC, epoch, excl + total));
-  return excl;
-}
-
-// CTA-wide exclusive scan of one small count per thread (TILE_BLOCKS threads) + look-back.
-// Returns this thread's exclusive offset inside the tile; *tile_total and *tile_base (global
-// exclusive prefix of the tile) are broadcast to every thread.  Contains two __syncthreads().
-struct ScanSmem {
-  unsigned wsum[NWARPS];
-  unsigned woff[NWARPS];
-  unsigned total;
-  unsigned long long base;
-};
-__device__ __forceinline__ unsigned tile_scan(unsigned cnt, ScanSmem &s, unsigned long long *status, unsigned tile,
-                                              unsigned epoch, unsigned *tile_total, unsigned long long *tile_base) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned incl = cnt;
+// inclusive warp scan of one small count per lane
+__device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const unsigned n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += n;
+    const unsigned n = __shfl_up_sync(0xFFFFFFFFu, v, o);
+    if (lane >= o) v += n;
   }
-  if (lane == 31) s.wsum[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    const unsigned w = (lane < NWARPS) ? s.wsum[lane] : 0u;
-    unsigned wi = w;
-#pragma unroll
-    for (int o = 1; o < NWARPS; o <<= 1) {
-      const unsigned n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-      if (lane >= o) wi += n;
-    }
-    const unsigned total = __shfl_sync(0xFFFFFFFFu, wi, NWARPS - 1);
-    if (lane < NWARPS) s.woff[lane] = wi - w;
-    const unsigned long long base = lookback_exclusive(status, tile, epoch, total, lane);
-    if (lane == 0) { s.total = total; s.base = base; }
-  }
-  __syncthreads();
-  *tile_total = s.total;
-  *tile_base = s.base;
-  return s.woff[warp] + incl - cnt;
+  return v;
+}
+
+// per 32-bit word of four bin ids: 0x01 in every byte that equals 0xFF (the outlier marker)
+__device__ __forceinline__ unsigned ff_bytes(unsigned w) {
+  unsigned y = w & (w >> 4);
+  y &= y >> 2;
+  y &= y >> 1;
+  return y & 0x01010101u;
 }
 
 }  // namespace dctz

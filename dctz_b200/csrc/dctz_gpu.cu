@@ -39,7 +39,6 @@ struct dctz_gpu_ctx {
   char err[512] = "";
   uint64_t launches = 0;
   int opt_dct = 0;
-  unsigned epoch = 0;
 
   // small fixed scratch
   StatPartial *d_partials = nullptr;
@@ -51,8 +50,10 @@ struct dctz_gpu_ctx {
   TileControl *d_ctl = nullptr;
   unsigned long long *d_nconsumed = nullptr;
   unsigned long long *d_mismatch = nullptr;
-  DevBuf status;        // look-back words, one per tile
-  DevBuf qt_raw, qt_j;  // QT: un-rescaled outliers + their coefficient position
+  DevBuf status;        // [group_prefix: u64 per 32 tiles][counts: u32 per warp tile]
+  DevBuf slots;         // EC: tile-strided outlier scratch (TILE_SLOT floats per warp tile)
+  DevBuf qt_raw, qt_j;  // QT: tile-strided un-rescaled outliers + their coefficient position
+  unsigned qt_entries = 0;  // tiles (incl. the tail slot) of the last QT compress call
 
   // sf tables: host copies + device copies
   std::vector<double> thr_d, sfv_d;
@@ -180,7 +181,7 @@ extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
                    ctx->d_nconsumed, ctx->d_mismatch, (void *)ctx->tb.thr_d, (void *)ctx->tb.sf_d,
                    (void *)ctx->tb.thr_f, (void *)ctx->tb.sf_f};
   for (void *p : small) if (p) cudaFree(p);
-  DevBuf *bufs[] = {&ctx->status, &ctx->qt_raw, &ctx->qt_j, &ctx->in, &ctx->bins, &ctx->dc, &ctx->ac,
+  DevBuf *bufs[] = {&ctx->status, &ctx->slots, &ctx->qt_raw, &ctx->qt_j, &ctx->in, &ctx->bins, &ctx->dc, &ctx->ac,
                     &ctx->qt, &ctx->qtraw, &ctx->out};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -231,14 +232,14 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   ctx->tb.min_d = ctx->min_d;
   ctx->tb.min_f = ctx->min_f;
   // kernel attributes + residency (persistent grids are sized from these)
-  ctx->occ[0][1][0] = kernel_occupancy(k_compress<double, false>, TILE_BLOCKS, CompressCfg<double, false>::SMEM);
-  ctx->occ[0][1][1] = kernel_occupancy(k_compress<double, true>, TILE_BLOCKS, CompressCfg<double, true>::SMEM);
-  ctx->occ[0][0][0] = kernel_occupancy(k_compress<float, false>, TILE_BLOCKS, CompressCfg<float, false>::SMEM);
-  ctx->occ[0][0][1] = kernel_occupancy(k_compress<float, true>, TILE_BLOCKS, CompressCfg<float, true>::SMEM);
-  ctx->occ[1][1][0] = kernel_occupancy(k_decompress<double, false>, TILE_BLOCKS, DecompressCfg<double, false>::SMEM);
-  ctx->occ[1][1][1] = kernel_occupancy(k_decompress<double, true>, TILE_BLOCKS, DecompressCfg<double, true>::SMEM);
-  ctx->occ[1][0][0] = kernel_occupancy(k_decompress<float, false>, TILE_BLOCKS, DecompressCfg<float, false>::SMEM);
-  ctx->occ[1][0][1] = kernel_occupancy(k_decompress<float, true>, TILE_BLOCKS, DecompressCfg<float, true>::SMEM);
+  ctx->occ[0][1][0] = kernel_occupancy(k_compress<double, false>, CompressCfg<double, false>::THREADS, CompressCfg<double, false>::SMEM);
+  ctx->occ[0][1][1] = kernel_occupancy(k_compress<double, true>, CompressCfg<double, true>::THREADS, CompressCfg<double, true>::SMEM);
+  ctx->occ[0][0][0] = kernel_occupancy(k_compress<float, false>, CompressCfg<float, false>::THREADS, CompressCfg<float, false>::SMEM);
+  ctx->occ[0][0][1] = kernel_occupancy(k_compress<float, true>, CompressCfg<float, true>::THREADS, CompressCfg<float, true>::SMEM);
+  ctx->occ[1][1][0] = kernel_occupancy(k_decompress<double, false>, DecompressCfg<double, false>::THREADS, DecompressCfg<double, false>::SMEM);
+  ctx->occ[1][1][1] = kernel_occupancy(k_decompress<double, true>, DecompressCfg<double, true>::THREADS, DecompressCfg<double, true>::SMEM);
+  ctx->occ[1][0][0] = kernel_occupancy(k_decompress<float, false>, DecompressCfg<float, false>::THREADS, DecompressCfg<float, false>::SMEM);
+  ctx->occ[1][0][1] = kernel_occupancy(k_decompress<float, true>, DecompressCfg<float, true>::THREADS, DecompressCfg<float, true>::SMEM);
   for (int a = 0; a < 2; a++)
     for (int b = 0; b < 2; b++)
       for (int c = 0; c < 2; c++)
@@ -306,13 +307,12 @@ static int check_common(dctz_gpu_ctx *ctx, int datatype, double eb) {
 }
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
-static int next_epoch(dctz_gpu_ctx *ctx, size_t ntiles, cudaStream_t st) {
-  const bool fresh = (ntiles * 8 > ctx->status.cap);
-  TRY(grow(ctx, ctx->status, ntiles * 8));
-  if (fresh || ++ctx->epoch > 0xFFFFu) {  // new array or epoch wrap: clear every word once
-    ctx->epoch = 1;
-    CU(cudaMemsetAsync(ctx->status.p, 0, ctx->status.cap, st));
-  }
+struct ScanBufs { unsigned *counts; unsigned long long *group_prefix; };
+static int scan_bufs(dctz_gpu_ctx *ctx, size_t n_entries, ScanBufs *sb) {
+  const size_t ngroups = (n_entries + 31) / 32;
+  TRY(grow(ctx, ctx->status, ngroups * 8 + n_entries * 4 + 128));
+  sb->group_prefix = (unsigned long long *)ctx->status.p;
+  sb->counts = (unsigned *)((char *)ctx->status.p + ((ngroups * 8 + 127) / 128) * 128);  // 16-byte aligned for the uint4 loads
   return DCTZ_GPU_OK;
 }
 
@@ -387,32 +387,48 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
   const unsigned long long nblk_full = N / BLK;
   const int rem = (int)(N % BLK);
   const QuantConsts<T> qc = make_quant<T>(eb);
+  const size_t ntiles = (nblk_full + WTILE - 1) / WTILE;
+  const size_t n_entries = ntiles + (rem ? 1 : 0);  // the partial tail block is one more "tile" of the scratch layout
+  if (n_entries > 0xFFFFF000ull) return fail(ctx, DCTZ_GPU_EINVAL, "slab too large: %zu tiles", n_entries);
+  ScanBufs sb;
+  TRY(scan_bufs(ctx, n_entries, &sb));
+  float *ac_slots = nullptr;
   T *raw = nullptr;
   uint8_t *jpos = nullptr;
   if (QT) {
-    TRY(grow(ctx, ctx->qt_raw, N * sizeof(T)));
-    TRY(grow(ctx, ctx->qt_j, N));
+    TRY(grow(ctx, ctx->qt_raw, n_entries * TILE_SLOT * sizeof(T)));
+    TRY(grow(ctx, ctx->qt_j, n_entries * TILE_SLOT));
     raw = (T *)ctx->qt_raw.p;
     jpos = (uint8_t *)ctx->qt_j.p;
+    ctx->qt_entries = (unsigned)n_entries;
+  } else {
+    TRY(grow(ctx, ctx->slots, n_entries * TILE_SLOT * sizeof(float)));
+    ac_slots = (float *)ctx->slots.p;
   }
   if (nblk_full) {
-    const size_t ntiles = (nblk_full + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    if (ntiles > 0xFFFFFFF0ull) return fail(ctx, DCTZ_GPU_EINVAL, "slab too large: %zu tiles", ntiles);
-    TRY(next_epoch(ctx, ntiles, st));
     const size_t resident = (size_t)ctx->sm_count * ctx->occ[0][sizeof(T) == 8][QT];
-    const int grid = (int)(ntiles < resident ? ntiles : resident);
-    k_compress<T, QT><<<grid, TILE_BLOCKS, Cfg::SMEM, st>>>(d_in, nblk_full, ctx->d_params, qc, d_bins, d_dc, d_ac, raw, jpos,
-                                                            (U *)d_qtable_raw, (T *)d_qtable_raw,
-                                                            (unsigned long long *)ctx->status.p, ctx->epoch, &ctx->d_ctl[0], d_info);
+    const size_t ctas = (ntiles + Cfg::WARPS - 1) / Cfg::WARPS;
+    const int grid = (int)(ctas < resident ? ctas : resident);
+    k_compress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_in, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts, ac_slots, raw,
+                                                             jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0], d_info);
     ctx->launches++;
     CU(cudaGetLastError());
   }
   if (rem) {
-    k_tail_compress<T, QT><<<1, 32, 0, st>>>(d_in + nblk_full * BLK, rem, nblk_full, ctx->d_params, qc, d_bins, d_dc, d_ac, raw,
-                                             jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, d_info);
+    k_tail_compress<T, QT><<<1, 32, 0, st>>>(d_in + nblk_full * BLK, rem, nblk_full, (unsigned)ntiles, ctx->d_params, qc, d_bins, d_dc,
+                                             sb.counts, ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, d_info);
     ctx->launches++;
     CU(cudaGetLastError());
   }
+  k_scan_groups<<<1, 1024, 0, st>>>(sb.counts, (unsigned)n_entries, sb.group_prefix, &d_info->n_outliers, nullptr);
+  ctx->launches++;
+  if (!QT) {
+    const size_t ngroups = (n_entries + 31) / 32, want = (ngroups + 7) / 8;
+    const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? want : (size_t)ctx->sm_count * 8);
+    k_gather_ec<<<grid, 256, 0, st>>>(sb.counts, sb.group_prefix, (unsigned)n_entries, ac_slots, d_ac);
+    ctx->launches++;
+  }
+  CU(cudaGetLastError());
   return DCTZ_GPU_OK;
 }
 
@@ -455,9 +471,14 @@ extern "C" int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t
 template <typename T>
 static int launch_qt_finish(dctz_gpu_ctx *ctx, double eb, const T *d_qraw, T *d_qtable, float *d_ac, Info *d_info, cudaStream_t st) {
   const QtConsts<T> k = make_qt<T>(eb);
-  const int grid = ctx->sm_count * 4;
-  k_qt_rescale<T><<<grid, 256, 0, st>>>((const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, d_qtable, k, d_ac, d_info);
-  k_qt_compact<T><<<1, 32, 0, st>>>((const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, k, d_ac, d_info);
+  const unsigned n_entries = ctx->qt_entries;
+  ScanBufs sb;
+  TRY(scan_bufs(ctx, n_entries, &sb));  // same layout as in the compress call: nothing is reallocated
+  const size_t ngroups = (n_entries + 31) / 32, want = (ngroups + 7) / 8;
+  const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? (want ? want : 1) : (size_t)ctx->sm_count * 8);
+  k_qt_gather<T><<<grid, 256, 0, st>>>(sb.counts, sb.group_prefix, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p,
+                                       d_qraw, d_qtable, k, d_ac, d_info);
+  k_qt_compact<T><<<1, 32, 0, st>>>(sb.counts, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, k, d_ac, d_info);
   ctx->launches += 2;
   CU(cudaGetLastError());
   return DCTZ_GPU_OK;
@@ -467,7 +488,7 @@ extern "C" int dctz_gpu_qt_finish_dev(dctz_gpu_ctx *ctx, int datatype, double eb
                                       float *d_ac, dctz_gpu_info *d_info, void *stream) {
   TRY(check_common(ctx, datatype, eb));
   if (!d_qtable_raw || !d_ac || !d_info) return fail(ctx, DCTZ_GPU_EINVAL, "qt_finish: NULL pointer");
-  if (!ctx->qt_raw.p) return fail(ctx, DCTZ_GPU_EINVAL, "qt_finish: no QT compress call preceded");
+  if (!ctx->qt_raw.p || !ctx->qt_entries) return fail(ctx, DCTZ_GPU_EINVAL, "qt_finish: no QT compress call preceded");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (datatype == DCTZ_GPU_DOUBLE)
@@ -503,14 +524,22 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
   const T bw = (sizeof(T) == 8) ? (T)(eb * 2 * 1.0) : (T)(float)((float)eb * 2 * 1.0);
   const T sfT = (T)sf;
   if (nblk_full) {
-    const size_t ntiles = (nblk_full + TILE_BLOCKS - 1) / TILE_BLOCKS;
-    if (ntiles > 0xFFFFFFF0ull) return fail(ctx, DCTZ_GPU_EINVAL, "slab too large: %zu tiles", ntiles);
-    TRY(next_epoch(ctx, ntiles, st));
+    const size_t ntiles = (nblk_full + WTILE - 1) / WTILE;
+    if (ntiles > 0xFFFFF000ull) return fail(ctx, DCTZ_GPU_EINVAL, "slab too large: %zu tiles", ntiles);
+    ScanBufs sb;
+    TRY(scan_bufs(ctx, ntiles, &sb));
+    {
+      const size_t want = (ntiles + 7) / 8;
+      const int grid = (int)(want < (size_t)ctx->sm_count * 16 ? want : (size_t)ctx->sm_count * 16);
+      k_count_bins<<<grid, 256, 0, st>>>(d_bins, nblk_full, sb.counts);
+      k_scan_groups<<<1, 1024, 0, st>>>(sb.counts, (unsigned)ntiles, sb.group_prefix, ctx->d_nconsumed, nullptr);
+      ctx->launches += 2;
+    }
     const size_t resident = (size_t)ctx->sm_count * ctx->occ[1][sizeof(T) == 8][QT];
-    const int grid = (int)(ntiles < resident ? ntiles : resident);
-    k_decompress<T, QT><<<grid, TILE_BLOCKS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, d_out,
-                                                              (unsigned long long *)ctx->status.p, ctx->epoch, &ctx->d_ctl[1],
-                                                              ctx->d_nconsumed);
+    const size_t ctas = (ntiles + Cfg::WARPS - 1) / Cfg::WARPS;
+    const int grid = (int)(ctas < resident ? ctas : resident);
+    k_decompress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, d_out, sb.counts,
+                                                               sb.group_prefix, &ctx->d_ctl[1]);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -637,9 +666,9 @@ static int dct_blocks_impl(dctz_gpu_ctx *ctx, const T *in, T *out, size_t nblock
   TRY(grow(ctx, ctx->out, bytes));
   CU(cudaMemcpyAsync(ctx->in.p, in, bytes, cudaMemcpyHostToDevice, st));
   if (dn == BLK) {
-    const unsigned grid = (unsigned)((nblocks + TILE_BLOCKS - 1) / TILE_BLOCKS);
-    if (inverse) k_dct64_blocks<T, true><<<grid, TILE_BLOCKS, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, nblocks);
-    else k_dct64_blocks<T, false><<<grid, TILE_BLOCKS, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, nblocks);
+    const unsigned grid = (unsigned)((nblocks + DCT_ONLY_THREADS - 1) / DCT_ONLY_THREADS);
+    if (inverse) k_dct64_blocks<T, true><<<grid, DCT_ONLY_THREADS, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, nblocks);
+    else k_dct64_blocks<T, false><<<grid, DCT_ONLY_THREADS, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, nblocks);
   } else {
     if (inverse) k_dct_generic_blocks<T, true><<<(unsigned)nblocks, 32, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, dn);
     else k_dct_generic_blocks<T, false><<<(unsigned)nblocks, 32, 0, st>>>((const T *)ctx->in.p, (T *)ctx->out.p, dn);

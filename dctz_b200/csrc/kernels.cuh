@@ -4,17 +4,19 @@
 //   k_finalize         reduce per-rank statistics, derive sf        (util.c:28/42)
 //   k_compress     K2  scale + DCT-II + quantise + ordered outliers (dctz-comp-lib.c:188-217, 318-544)
 //   k_tail             the partial last block (rem = N % 64)        (dctz-comp-lib.c:326-336)
-//   k_qt_rescale   K2b QT outlier rescale                           (dctz-comp-lib.c:450-533)
+//   k_scan_groups / k_gather_ec   ordered outlier compaction        (dctz-comp-lib.c:478-544)
+//   k_qt_gather    K2b QT outlier rescale + compaction              (dctz-comp-lib.c:450-533)
+//   k_count_bins       outlier markers per tile (decompress pre-pass)
 //   k_decompress   K3  dequantise + DCT-III + de-scale              (dctz-decomp-lib.c:389-511)
 //
 // Mapping: ONE THREAD OWNS ONE 64-ELEMENT BLOCK, all 64 values live in registers and go through
 // the generated straight-line transform (dct64_gen.cuh, 592 FP ops, no shuffles, no indexing).
-// A CTA of 128 threads works on a tile of 128 consecutive blocks: the tile is copied
-// global -> shared with fully coalesced 16-byte cp.async (XOR-swizzled so each thread can then
-// read "its" row with conflict-free 128-bit shared loads), and the next tile's copy is issued as
-// soon as the registers are loaded, so it overlaps the whole compute phase.  Kernels are
-// persistent (grid = resident CTAs), tiles are handed out by an atomic ticket, and the ordered
-// outlier offsets come from a single-pass decoupled look-back scan over the tiles.
+// The kernels are persistent and WARP-AUTONOMOUS: a warp takes a tile of 32 consecutive blocks from
+// an atomic ticket (fetched one iteration ahead), each lane's row arrives by one TMA bulk copy
+// (cp.async.bulk -> per-warp mbarrier) into a padded, bank-conflict-free shared-memory tile, and the
+// next tile's copy is issued as soon as the registers are loaded, so it overlaps the whole compute
+// phase.  There is no CTA-wide barrier inside the main loops; the ordered outlier offsets come from
+// a single-pass decoupled look-back scan over the warp tiles.
 #pragma once
 #include <type_traits>
 #include "common.cuh"
@@ -246,8 +248,9 @@ __global__ void k_finalize(const double *stats_all, int nranks, unsigned long lo
 // ------------------------------------------------------------------------------------------
 // Quantiser (dctz-comp-lib.c:363-414).  Returns the stream id 0..254, or 255 for an outlier.
 // ------------------------------------------------------------------------------------------
-// Exact restatement, used for the rare near-boundary coefficients and by the tail kernel.
-__device__ __noinline__ unsigned quant_exact_d(double c, double rmin, double rmax, double bw, unsigned *edge) {
+// Exact restatement on a scaled coefficient, used for the rare near-boundary coefficients and by
+// the tail kernel.
+__device__ __forceinline__ unsigned quant_exact_d(double c, double rmin, double rmax, double bw, unsigned *edge) {
   if (c < rmin || c > rmax) return 255u;
   const double q = __ddiv_rn(__dsub_rn(c, rmin), bw);
   int t = (int)q;  // (t_bin_id) truncation; q in [0, 255]
@@ -264,39 +267,8 @@ __device__ __forceinline__ unsigned quant_exact_f(float c, float rmin, float rma
   if (t > 254) t = 254;
   return conv_ordinal(t);
 }
-
 __device__ __forceinline__ unsigned quant_exact(float c, const QuantConsts<float> &q, unsigned *) {
   return quant_exact_f(c, q.rmin, q.rmax, q.bw);
-}
-
-// Double fast path: v ~ (c - rmin)/bw through one FMA, then the "magic add" turns v into 12.20
-// fixed point in the low word of z.  Unless the fraction is within 4 units (4e-6) of an integer --
-// where the approximate v could land on the other side of a bin or range boundary than the
-// reference's exactly rounded (c - rmin)/bw -- floor(v) and the range test are provably those of
-// the reference (|v - v_ref| < 1e-8 for |v| < 2^31).  The near-integer cases (~8e-6 of all
-// coefficients) take the exact path.
-__device__ __forceinline__ unsigned quantize(double c, const QuantConsts<double> &qc, unsigned &edge, unsigned &nexact) {
-  const double v = __fma_rn(c, qc.inv_bw, 127.5);
-  const double z = __dadd_rn(v, 6442450944.0 /* 1.5 * 2^32 */);
-  const unsigned lo = (unsigned)__double2loint(z), hi = (unsigned)__double2hiint(z);
-  if (__builtin_expect(((lo + 4u) & 0xFFFFFu) < 8u, 0)) {
-    nexact++;
-    return quant_exact_d(c, qc.rmin, qc.rmax, qc.bw, &edge);
-  }
-  const int t = (int)(lo >> 20);
-  const bool inrange = (hi == 0x41F80000u) && (lo < (255u << 20));
-  const unsigned id = conv_ordinal(t);
-  return inrange ? id : 255u;
-}
-
-// Float path: the reference's own float arithmetic, with the division done exactly through the
-// reciprocal-FMA sequence (cheaper than the fast/slow split at float precision).
-__device__ __forceinline__ unsigned quantize(float c, const QuantConsts<float> &qc, unsigned &, unsigned &) {
-  const bool out = (c < qc.rmin) || (c > qc.rmax);
-  const float q = div_exact(__fsub_rn(c, qc.rmin), qc.div);
-  int t = __float2int_rz(fminf(q, 254.5f));  // ordinal 255 (c == range_max) clamps to 254, see DESIGN.md
-  const unsigned id = conv_ordinal(t);
-  return out ? 255u : id;
 }
 
 template <typename T> struct BitsOf;
@@ -309,101 +281,189 @@ template <> struct BitsOf<float> {
   static __device__ __forceinline__ U abs_bits(float v) { return (U)__float_as_int(v) & 0x7FFFFFFFu; }
 };
 
+// Per-thread quantiser state.  DOUBLE: the transform runs on the UNSCALED block (the DCT is linear;
+// dividing afterwards instead of before changes a coefficient by ~1 ulp, far inside the 1e-12
+// tolerance, and saves three FP64 operations per element); the division by sf is folded into one
+// constant kq = 1/(sf*bw):  v = c_u*kq + 127.5 ~ (c_u/sf - rmin)/bw.  The "magic add" turns v into
+// 12.20 fixed point in the low word of z.  Unless the fraction is within 4 units (4e-6) of an
+// integer -- where the approximate v could land on the other side of a bin or range boundary than
+// the exactly rounded expression -- floor(v) and the range test are provably those of the exact
+// expression (|v - v_exact| < 1e-12).  Near-integer coefficients (~8e-6 of all) only raise a flag;
+// flagged blocks are re-quantised once through the exact path (quantize_block_exact).
+template <typename T> struct Quantizer;
+template <> struct Quantizer<double> {
+  double kq;
+  Divisor<double> sfdiv;
+  unsigned allok;  // stays 1 while no coefficient of the block came near a boundary
+  __device__ __forceinline__ void init(const DevParams *p, const QuantConsts<double> &qc) {
+    sfdiv.b = p->sf_d; sfdiv.y = p->inv_sf_d; sfdiv.iters = p->scale_iters;
+    kq = __ddiv_rn(1.0, __dmul_rn(p->sf_d, qc.bw));
+  }
+  __device__ __forceinline__ void pre_scale(double (&)[BLK]) const {}
+  __device__ __forceinline__ double scaled(double c_u) const { return div_exact(c_u, sfdiv); }
+  __device__ __forceinline__ void begin_block() { allok = 1u; }
+  __device__ __forceinline__ unsigned quantize(double c_u) {
+    const double v = __fma_rn(c_u, kq, 127.5);
+    const double z = __dadd_rn(v, 6442450944.0 /* 1.5 * 2^32 */);
+    const unsigned lo = (unsigned)__double2loint(z), hi = (unsigned)__double2hiint(z);
+    allok &= (((lo + 4u) & 0xFFFF8u) != 0u) ? 1u : 0u;
+    const unsigned u = (hi == 0x41F80000u) ? lo : 0xFFFFFFFFu;  // v outside [0, 4096) saturates
+    const int b = (int)(2u * (u >> 20)) - 255;                  // 2t - 255; conv(t) = max(2t-255, 254-2t) = max(b, ~b)
+    const int id = max(b, ~b);
+    return (unsigned)min(id, 255);                              // t >= 255 (out of range) -> 255
+  }
+  __device__ __forceinline__ bool needs_exact() const { return allok == 0u; }
+};
+// FLOAT: the reference's own float arithmetic on the scaled block, with both divisions done exactly
+// through the reciprocal-FMA sequence (cheap at FP32 rate).
+template <> struct Quantizer<float> {
+  Divisor<float> sfdiv;
+  __device__ __forceinline__ void init(const DevParams *p, const QuantConsts<float> &) {
+    sfdiv.b = p->sf_f; sfdiv.y = p->inv_sf_f; sfdiv.iters = p->scale_iters;
+  }
+  __device__ __forceinline__ void pre_scale(float (&x)[BLK]) const {
+    if (sfdiv.iters != 0) {
+#pragma unroll
+      for (int j = 0; j < BLK; j++) x[j] = div_exact(x[j], sfdiv);  // x / sf, bit-exact (dctz-comp-lib.c:208-216)
+    }
+  }
+  __device__ __forceinline__ float scaled(float c) const { return c; }
+  __device__ __forceinline__ void begin_block() {}
+  __device__ __forceinline__ bool needs_exact() const { return false; }
+};
+__device__ __forceinline__ unsigned quantize_f(float c, const QuantConsts<float> &qc) {
+  const bool out = (c < qc.rmin) || (c > qc.rmax);
+  const float q = div_exact(__fsub_rn(c, qc.rmin), qc.div);
+  const int t = __float2int_rz(fminf(q, 254.5f));  // ordinal 255 (c == range_max) clamps to 254, see DESIGN.md
+  return out ? 255u : conv_ordinal(t);
+}
+
+// Cold path of the double quantiser: re-quantise one block exactly.  The coefficients go through
+// local memory so that this rarely executed code stays small (no 63-fold unrolling).
+__device__ __noinline__ void quantize_block_exact(const double *xl, double sf_b, double sf_y, int sf_iters, double rmin,
+                                                  double rmax, double bw, unsigned *wl, unsigned *edge) {
+  Divisor<double> d;
+  d.b = sf_b; d.y = sf_y; d.iters = sf_iters;
+#pragma unroll 1
+  for (int q = 0; q < 16; q++) {
+    unsigned word = 0;
+#pragma unroll 1
+    for (int b = 0; b < 4; b++) {
+      const int j = 4 * q + b;
+      const unsigned id = (j == 0) ? 255u : quant_exact_d(div_exact(xl[j], d), rmin, rmax, bw, edge);
+      word |= id << (8 * b);
+    }
+    wl[q] = word;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K2: fused scale + DCT-II + quantise + ordered outlier compaction.
-// Shared memory: [ tile: 128 rows x 64 T, swizzled ][ outlier stage: CAP entries ][ QT: j stage ]
+// Shared memory per warp: [ tile: 32 padded rows ][ EC: outlier stage, 2016 floats ][ bin ids 2 KB ]
 // ------------------------------------------------------------------------------------------
 template <typename T, bool QT> struct CompressCfg {
-  typedef typename std::conditional<QT, T, float>::type StageT;  // QT keeps the raw coefficient
-  // worst case 63 outliers per block; QT-double stages half of that per round (two rounds max)
-  static constexpr int CAP = (QT && sizeof(T) == 8) ? 4032 : 8064;
-  static constexpr bool WINDOWED = (CAP < 63 * TILE_BLOCKS);
-  static constexpr int SMEM = TileLayout<T>::TILE_BYTES + CAP * (int)sizeof(StageT) + (QT ? CAP : 0);
+  static constexpr int WARPS = 4;
+  static constexpr int THREADS = WARPS * 32;
   static constexpr int CTAS_PER_SM = (sizeof(T) == 8) ? 2 : 3;
+  // EC stages a tile's outliers (worst case 63 per block) for coalesced stores; QT writes its raw
+  // outliers straight to scratch (they are re-read by K2b anyway)
+  static constexpr int CAP = QT ? 0 : 63 * WTILE;
+  static constexpr int OFF_STAGE = WarpTile<T>::BYTES;
+  static constexpr int OFF_BINS = OFF_STAGE + CAP * 4;
+  static constexpr int WARP_BYTES = ((OFF_BINS + WTILE * BLK + 127) / 128) * 128;
+  static constexpr int SMEM = WARPS * WARP_BYTES;
 };
 
 template <typename T, bool QT>
-__global__ void __launch_bounds__(TILE_BLOCKS, (sizeof(T) == 8 ? 2 : 3))
+__global__ void __launch_bounds__(CompressCfg<T, QT>::THREADS, CompressCfg<T, QT>::CTAS_PER_SM)
 k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevParams *__restrict__ params,
            QuantConsts<T> qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
-           float *__restrict__ ac_out,                       // EC: final AC_exact
-           T *__restrict__ raw_out, uint8_t *__restrict__ j_out,  // QT: raw outliers + their position j
+           unsigned *__restrict__ counts,                     // outliers per warp tile
+           float *__restrict__ ac_slots,                      // EC: tile-strided outlier scratch (TILE_SLOT per tile)
+           T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, tile-strided
            typename BitsOf<T>::U *__restrict__ qmax_bits,     // QT: 64 per-position maxima (bit patterns)
            T *__restrict__ qtable0,                           // QT: receives the last full block's DC
-           unsigned long long *__restrict__ status, unsigned epoch, TileControl *ctl, Info *info) {
+           TileControl *ctl, Info *info) {
   typedef typename ArithOf<T>::type A;
   typedef CompressCfg<T, QT> Cfg;
-  typedef typename Cfg::StageT StageT;
-  typedef TileLayout<T> L;
+  typedef WarpTile<T> L;
   typedef typename BitsOf<T>::U U;
+  constexpr unsigned FULL = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char *tile = smem;
-  StageT *stage = reinterpret_cast<StageT *>(smem + L::TILE_BYTES);
-  uint8_t *jstage = reinterpret_cast<uint8_t *>(smem + L::TILE_BYTES + Cfg::CAP * sizeof(StageT));
-  __shared__ ScanSmem scan;
-  __shared__ unsigned s_next;
+  __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
   __shared__ U s_qmax[QT ? BLK : 1];
 
-  const int tid = threadIdx.x;
-  const unsigned ntiles = (unsigned)((nblk_full + TILE_BLOCKS - 1) / TILE_BLOCKS);
-  const unsigned tile_base_smem = smem_u32(tile);
-  Divisor<T> sfdiv;
-  if (sizeof(T) == 8) { sfdiv.b = (T)params->sf_d; sfdiv.y = (T)params->inv_sf_d; }
-  else { sfdiv.b = (T)params->sf_f; sfdiv.y = (T)params->inv_sf_f; }
-  sfdiv.iters = params->scale_iters;
-  if (QT) { if (tid < BLK) s_qmax[tid] = 0; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wsm = smem + warp * Cfg::WARP_BYTES;
+  const unsigned tile_s = smem_u32(wsm);
+  float *stage = reinterpret_cast<float *>(wsm + Cfg::OFF_STAGE);
+  unsigned char *binbuf = wsm + Cfg::OFF_BINS;
+  const unsigned mb = smem_u32(&s_mbar[warp]);
+  const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
 
+  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
+  if (QT) { if (threadIdx.x < BLK) s_qmax[threadIdx.x] = 0; }
+  __syncthreads();  // the only CTA-wide barrier before the epilogue
+
+  Quantizer<T> qz;
+  qz.init(params, qc);
   unsigned edge = 0, nexact = 0;
 
+  auto rows_of = [&](unsigned t) -> unsigned {
+    const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
+    return left < (unsigned long long)WTILE ? (unsigned)left : (unsigned)WTILE;
+  };
   auto issue_tile = [&](unsigned t) {
-    // 128 rows * CH chunks, contiguous in global memory; thread copies chunk g = it*128 + tid
-    const unsigned long long first_blk = (unsigned long long)t * TILE_BLOCKS;
-    const unsigned long long rows = (nblk_full - first_blk < TILE_BLOCKS) ? (nblk_full - first_blk) : TILE_BLOCKS;
-    const unsigned nchunks = (unsigned)rows * L::CH;
-    const unsigned char *src = reinterpret_cast<const unsigned char *>(in) + first_blk * L::ROW_BYTES;
-#pragma unroll 8
-    for (unsigned g = tid; g < (unsigned)TILE_BLOCKS * L::CH; g += TILE_BLOCKS) {
-      if (g < nchunks) cp_async16(tile_base_smem + L::offset(g / L::CH, g % L::CH), src + (size_t)g * 16);
-    }
-    cp_async_commit();
+    const unsigned rows = rows_of(t);
+    if (lane == 0) mbar_expect_tx(mb, rows * L::ROW_BYTES);
+    __syncwarp();
+    if ((unsigned)lane < rows)
+      bulk_g2s(tile_s + lane * L::ROW_STRIDE, in + ((unsigned long long)t * WTILE + lane) * BLK, L::ROW_BYTES, mb);
+  };
+  auto take_ticket = [&]() -> unsigned {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(&ctl->ticket, 1u);
+    return t;  // valid in lane 0 only; broadcast when consumed
   };
 
-  if (tid == 0) s_next = atomicAdd(&ctl->ticket, 1u);
-  __syncthreads();
-  unsigned cur = s_next;
+  // The first tile of every warp is its global warp index; later tiles come from the ticket counter
+  // (which therefore starts at the number of warps).  A ticket is taken when the warp starts waiting for
+  // its current tile, so tiles t-1 and t are always picked up at about the same time by two warps that
+  // are at the same point of their loop: the look-back below never waits long.
+  const unsigned nwarps_grid = gridDim.x * Cfg::WARPS;
+  unsigned cur = blockIdx.x * Cfg::WARPS + warp;
   if (cur < ntiles) issue_tile(cur);
+  unsigned phase = 0;
 
   while (cur < ntiles) {
-    cp_async_wait_all();
-    __syncthreads();  // tile `cur` is complete and visible to all threads
+    const unsigned pending = take_ticket();  // latency overlaps the wait for the tile
+    mbar_wait(mb, phase);
+    phase ^= 1u;
     T x[BLK];
     {
-      const unsigned char *row = tile;
+      const unsigned char *row = wsm + lane * L::ROW_STRIDE;
 #pragma unroll
       for (int c = 0; c < L::CH; c++) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(row + L::offset(tid, c));
+        const uint4 v = *reinterpret_cast<const uint4 *>(row + 16 * c);
         const T *e = reinterpret_cast<const T *>(&v);
 #pragma unroll
         for (int k = 0; k < 16 / (int)sizeof(T); k++) x[c * (16 / (int)sizeof(T)) + k] = e[k];
       }
     }
-    if (tid == 0) s_next = atomicAdd(&ctl->ticket, 1u);
-    __syncthreads();  // every thread has its registers; the tile buffer may be overwritten
-    const unsigned nxt = s_next;
-    if (nxt < ntiles) issue_tile(nxt);  // overlaps everything below
+    __syncwarp();                        // every lane holds its row in registers
+    const unsigned nxt = nwarps_grid + __shfl_sync(FULL, pending, 0);
+    if (nxt < ntiles) issue_tile(nxt);   // refill the tile buffer; overlaps everything below
 
-    const unsigned long long blk = (unsigned long long)cur * TILE_BLOCKS + tid;
-    const bool active = blk < nblk_full;
+    const unsigned rows = rows_of(cur);
+    const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
+    const bool active = (unsigned)lane < rows;
     if (!active) {
 #pragma unroll
       for (int j = 0; j < BLK; j++) x[j] = (T)0;
     }
 
-    // ---- scale: x / sf, bit-exact IEEE division (dctz-comp-lib.c:193-216) ----
-    if (sfdiv.iters != 0) {
-#pragma unroll
-      for (int j = 0; j < BLK; j++) x[j] = div_exact(x[j], sfdiv);
-    }
+    // ---- scale (float: x / sf before the transform; double: folded into the quantiser) ----
+    qz.pre_scale(x);
     // ---- orthonormal DCT-II (dct.c:55-103) ----
     dct64_forward<A>(x);
 
@@ -412,79 +472,108 @@ k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevPara
 #pragma unroll
     for (int q = 0; q < 16; q++) w[q] = 0;
     w[0] = 255u;  // bin_index[i*64] = NBINS, :361
+    qz.begin_block();
 #pragma unroll
     for (int j = 1; j < BLK; j++) {
-      const unsigned id = quantize(x[j], qc, edge, nexact);
+      unsigned id;
+      if constexpr (sizeof(T) == 8) id = qz.quantize(x[j]);
+      else id = quantize_f(x[j], qc);
       w[j >> 2] |= id << (8 * (j & 3));
+    }
+    if constexpr (sizeof(T) == 8) {
+      if (qz.needs_exact()) {  // rare (~5e-4 of blocks): redo this block through the exact expression
+        double xl[BLK];
+        unsigned wl[16];
+#pragma unroll
+        for (int j = 0; j < BLK; j++) xl[j] = x[j];
+        quantize_block_exact(xl, qz.sfdiv.b, qz.sfdiv.y, qz.sfdiv.iters, qc.rmin, qc.rmax, qc.bw, wl, &edge);
+#pragma unroll
+        for (int q = 0; q < 16; q++) w[q] = wl[q];
+        nexact++;
+      }
     }
     unsigned cnt = 0;
 #pragma unroll
-    for (int q = 0; q < 16; q++) cnt += __popc(__vcmpeq4(w[q], 0xFFFFFFFFu) & 0x01010101u);
+    for (int q = 0; q < 16; q++) cnt += __popc(ff_bytes(w[q]));
     cnt -= 1;  // the DC marker
     if (!active) cnt = 0;
 
-    unsigned tile_total;
-    unsigned long long tile_base;
-    const unsigned my_off = tile_scan(cnt, scan, status, cur, epoch, &tile_total, &tile_base);
+    const unsigned incl = warp_inclusive_scan(cnt, lane);
+    const unsigned tile_total = __shfl_sync(FULL, incl, 31);
+    const unsigned my_off = incl - cnt;
+    if (lane == 0) counts[cur] = tile_total;
 
-    // ---- outputs that do not depend on the scan ----
-    if (active) {
-      uint4 *bp = reinterpret_cast<uint4 *>(bins + blk * BLK);
+    // ---- bin ids (via shared memory, one bulk store per tile) and DC ----
+    if (lane == 0) bulk_wait_read();  // the previous tile's bin ids have left shared memory
+    __syncwarp();
+    {
+      uint4 *bp = reinterpret_cast<uint4 *>(binbuf + lane * BLK);
 #pragma unroll
       for (int q = 0; q < 4; q++) bp[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-      dc_out[blk] = (float)x[0];  // :351 (USE_TRUNCATE)
-      if (QT && blk == nblk_full - 1) *qtable0 = x[0];  // :357/:359 (a later tail block overwrites it)
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(bins + (unsigned long long)cur * WTILE * BLK, smem_u32(binbuf), rows * BLK);
+      bulk_commit();
+    }
+    const T dcs = qz.scaled(x[0]);
+    if (active) {
+      dc_out[blk] = (float)dcs;  // :351 (USE_TRUNCATE)
+      if (QT && blk == nblk_full - 1) *qtable0 = dcs;  // :357/:359 (a later tail block overwrites it)
     }
 
-    // ---- ordered outlier emission through the shared stage (dctz-comp-lib.c:478-544) ----
-    for (unsigned win = 0; win < tile_total; win += Cfg::CAP) {
-      unsigned pos = my_off - win;  // wraps "negative" for entries before the window
+    // ---- outliers of this tile, in (block, j) order, to the tile's scratch slot (dctz-comp-lib.c:478-544) ----
+    if (tile_total != 0) {
+      const unsigned long long slot = (unsigned long long)cur * TILE_SLOT;
+      unsigned pos = my_off;
 #pragma unroll
-      for (int j = 1; j < BLK; j++) {
-        const unsigned sh = 8 * (j & 3);
-        if (((w[j >> 2] >> sh) & 0xFFu) == 0xFFu) {
-          if (!Cfg::WINDOWED || pos < (unsigned)Cfg::CAP) {
-            stage[pos] = (StageT)x[j];
-            if (QT) jstage[pos] = (uint8_t)j;
+      for (int q = 0; q < 16; q++) {
+        unsigned m = ff_bytes(w[q]);
+        if (q == 0) m &= ~1u;  // the DC marker is not an outlier
+        if (m) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int j = 4 * q + b;
+            if (j >= 1 && (m & (1u << (8 * b)))) {
+              const T c = qz.scaled(x[j]);
+              if (QT) {  // raw coefficient + position, rescaled by K2b once the global qtable is known
+                raw_slots[slot + pos] = c;
+                j_slots[slot + pos] = (uint8_t)j;
+                atomicMax(&s_qmax[j], BitsOf<T>::abs_bits(c));  // :371-372, 396-397
+              } else {
+                stage[pos] = (float)c;  // :537 (USE_TRUNCATE)
+              }
+              pos++;
+            }
           }
-          pos++;
         }
       }
-      __syncthreads();
-      const unsigned n_here = (tile_total - win < (unsigned)Cfg::CAP) ? (tile_total - win) : (unsigned)Cfg::CAP;
-      const unsigned long long g0 = tile_base + win;
-      if (QT) {
-        for (unsigned i = tid; i < n_here; i += TILE_BLOCKS) { raw_out[g0 + i] = (T)stage[i]; j_out[g0 + i] = jstage[i]; }
-      } else {
-        for (unsigned i = tid; i < n_here; i += TILE_BLOCKS) ac_out[g0 + i] = (float)stage[i];
-      }
-      __syncthreads();
-    }
-    if (QT && active) {  // per-position maximum of |outlier| (dctz-comp-lib.c:371-372, 396-397)
-#pragma unroll
-      for (int j = 1; j < BLK; j++) {
-        if (((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 0xFFu) atomicMax(&s_qmax[j], BitsOf<T>::abs_bits(x[j]));
+      if (!QT) {
+        __syncwarp();
+        for (unsigned i = lane; i < tile_total; i += 32) ac_slots[slot + i] = stage[i];
+        __syncwarp();
       }
     }
-    if (cur == ntiles - 1 && tid == 0) info->n_outliers = tile_base + tile_total;
     cur = nxt;
   }
 
   // ---- epilogue ----
-  if (QT) {
-    __syncthreads();
-    if (tid >= 1 && tid < BLK && s_qmax[tid] != 0) atomicMax(&qmax_bits[tid], s_qmax[tid]);
-  }
+  bulk_wait_all();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    edge += __shfl_xor_sync(0xFFFFFFFFu, edge, o);
-    nexact += __shfl_xor_sync(0xFFFFFFFFu, nexact, o);
+    edge += __shfl_xor_sync(FULL, edge, o);
+    nexact += __shfl_xor_sync(FULL, nexact, o);
   }
-  if ((tid & 31) == 0) {
+  if (lane == 0) {
     if (edge) atomicAdd(&info->n_edge, (unsigned long long)edge);
     if (nexact) atomicAdd(&info->n_exact_path, (unsigned long long)nexact);
   }
-  if (tid == 0) {
+  __syncthreads();
+  if (QT) {
+    if (threadIdx.x >= 1 && threadIdx.x < BLK && s_qmax[threadIdx.x] != 0) atomicMax(&qmax_bits[threadIdx.x], s_qmax[threadIdx.x]);
+  }
+  if (threadIdx.x == 0) {
     __threadfence();
     const unsigned prev = atomicAdd(&ctl->done, 1u);
     if (prev == gridDim.x - 1) { ctl->ticket = 0u; ctl->done = 0u; }
@@ -537,13 +626,14 @@ __device__ __forceinline__ void generic_idct(const double *cs /* shared, dn coef
   }
 }
 
-// Partial last block of the compress path (launched after k_compress on the same stream).
+// Partial last block of the compress path: it is warp tile number `slot_tile` of the scratch layout.
 template <typename T, bool QT>
 __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /* start of the tail block */, int rem,
-                                                      unsigned long long blk_index, const DevParams *params,
-                                                      QuantConsts<T> qc, uint8_t *bins, float *dc_out, float *ac_out,
-                                                      T *raw_out, uint8_t *j_out, typename BitsOf<T>::U *qmax_bits,
-                                                      T *qtable0, Info *info) {
+                                                      unsigned long long blk_index, unsigned slot_tile,
+                                                      const DevParams *params, QuantConsts<T> qc, uint8_t *bins,
+                                                      float *dc_out, unsigned *counts, float *ac_slots, T *raw_slots,
+                                                      uint8_t *j_slots, typename BitsOf<T>::U *qmax_bits, T *qtable0,
+                                                      Info *info) {
   __shared__ double xs[BLK];
   const int lane = threadIdx.x;
   const T sf = (sizeof(T) == 8) ? (T)params->sf_d : (T)params->sf_f;
@@ -555,7 +645,8 @@ __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /
   __syncwarp();
   double c2[2];
   generic_dct(xs, rem, lane, c2);
-  unsigned long long base = info->n_outliers;
+  const unsigned long long slot = (unsigned long long)slot_tile * TILE_SLOT;
+  unsigned base = 0;
   unsigned edge = 0;
   for (int h = 0; h < 2; h++) {
     const int j = lane + 32 * h;
@@ -575,18 +666,111 @@ __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /
     const bool outl = valid && j > 0 && id == 255u;
     const unsigned m = __ballot_sync(0xFFFFFFFFu, outl);
     if (outl) {
-      const unsigned long long p = base + __popc(m & ((1u << lane) - 1u));
+      const unsigned p = base + __popc(m & ((1u << lane) - 1u));
       if (QT) {
-        raw_out[p] = c; j_out[p] = (uint8_t)j;
+        raw_slots[slot + p] = c; j_slots[slot + p] = (uint8_t)j;
         atomicMax(&qmax_bits[j], BitsOf<T>::abs_bits(c));
       } else {
-        ac_out[p] = (float)c;
+        ac_slots[slot + p] = (float)c;
       }
     }
     base += __popc(m);
   }
   edge = (unsigned)warp_sum((double)edge);
-  if (lane == 0) { info->n_outliers = base; if (edge) info->n_edge += edge; }
+  if (lane == 0) { counts[slot_tile] = base; if (edge) info->n_edge += edge; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Scan + gather: per-tile counts -> exclusive prefix per group of 32 tiles -> final AC_exact order.
+// ------------------------------------------------------------------------------------------
+// One CTA.  group_prefix[g] = number of outliers in all tiles before group g; *total (and *total2 if
+// non-NULL) receive the grand total.  ntiles is at most a few million, the counts a few MB.
+__global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *__restrict__ counts, unsigned ntiles,
+                                                     unsigned long long *__restrict__ group_prefix,
+                                                     unsigned long long *total, unsigned long long *total2) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_carry;
+  const unsigned ngroups = (ntiles + 31u) / 32u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0ull;
+  __syncthreads();
+  for (unsigned g0 = 0; g0 < ngroups; g0 += 1024) {
+    const unsigned g = g0 + threadIdx.x;
+    unsigned long long sum = 0;
+    if (g < ngroups) {  // the 32 counts of a group are one 128-byte line
+      const unsigned first = g * 32u;
+      if (first + 32u <= ntiles) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(counts + first);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const uint4 v = __ldg(p + k); sum += (unsigned long long)v.x + v.y + v.z + v.w; }
+      } else {
+        for (unsigned t = first; t < ntiles; t++) sum += counts[t];
+      }
+    }
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = s_warp[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+        if (lane >= o) wi += n;
+      }
+      s_warp[lane] = wi - w;  // exclusive prefix of the warp sums
+    }
+    __syncthreads();
+    const unsigned long long carry = s_carry;
+    if (g < ngroups) group_prefix[g] = carry + s_warp[warp] + incl - sum;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *total = s_carry;
+    if (total2) *total2 = s_carry;
+  }
+}
+
+// Shared by the gather kernels: a warp owns one group; every lane learns the exclusive prefix of
+// "its" tile inside the group and the group's size.  Output position r of the group belongs to the
+// tile k with excl[k] <= r < excl[k+1], found by a 5-step binary search over the lanes' values.
+__device__ __forceinline__ unsigned group_tile_of(unsigned r, unsigned my_excl) {
+  int k = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const unsigned e = __shfl_sync(0xFFFFFFFFu, my_excl, k + step);
+    if (e <= r) k += step;
+  }
+  return (unsigned)k;
+}
+
+// EC: move the tile-strided runs to their final, contiguous place.
+__global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
+                                                   unsigned ntiles, const float *__restrict__ ac_slots, float *__restrict__ ac_out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned ngroups = (ntiles + 31u) / 32u;
+  const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngroups; g += wpg) {
+    const unsigned t = g * 32u + lane;
+    const unsigned c = (t < ntiles) ? __ldg(counts + t) : 0u;
+    const unsigned incl = warp_inclusive_scan(c, lane);
+    const unsigned gsize = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (gsize == 0) continue;
+    const unsigned my_excl = incl - c;
+    const unsigned long long gp = group_prefix[g];
+    for (unsigned r0 = 0; r0 < gsize; r0 += 32) {
+      const unsigned r = r0 + lane;
+      const unsigned k = group_tile_of(r < gsize ? r : gsize - 1, my_excl);  // all lanes take part in the shuffles
+      const unsigned ek = __shfl_sync(0xFFFFFFFFu, my_excl, k);
+      if (r < gsize) ac_out[gp + r] = __ldg(ac_slots + (unsigned long long)(g * 32u + k) * TILE_SLOT + (r - ek));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -616,11 +800,12 @@ __device__ __forceinline__ bool qt_rescale_one(float item, float q, const QtCons
   return (item < k.rmin || item > k.rmax);
 }
 
+// QT gather: rescale while moving to the final place.
 template <typename T>
-__global__ void __launch_bounds__(256) k_qt_rescale(const T *__restrict__ raw, const uint8_t *__restrict__ jidx,
-                                                    const T *__restrict__ qraw /* global maxima, [0] = last DC */,
-                                                    T *__restrict__ qtable_out, QtConsts<T> k,
-                                                    float *__restrict__ ac_out, Info *info) {
+__global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
+                                                   unsigned ntiles, const T *__restrict__ raw_slots, const uint8_t *__restrict__ j_slots,
+                                                   const T *__restrict__ qraw /* global maxima, [0] = last DC */,
+                                                   T *__restrict__ qtable_out, QtConsts<T> k, float *__restrict__ ac_out, Info *info) {
   __shared__ T qt[BLK];
   if (threadIdx.x < BLK) {
     T v = qraw[threadIdx.x];
@@ -629,42 +814,97 @@ __global__ void __launch_bounds__(256) k_qt_rescale(const T *__restrict__ raw, c
     if (blockIdx.x == 0 && qtable_out) qtable_out[threadIdx.x] = v;
   }
   __syncthreads();
-  const unsigned long long n = info->n_outliers;
+  const int lane = threadIdx.x & 31;
+  const unsigned ngroups = (ntiles + 31u) / 32u;
+  const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
   unsigned dropped = 0;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    float o;
-    const bool keep = qt_rescale_one(raw[i], qt[jidx[i]], k, &o);
-    ac_out[i] = o;
-    if (!keep) dropped++;
+  for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngroups; g += wpg) {
+    const unsigned t = g * 32u + lane;
+    const unsigned c = (t < ntiles) ? __ldg(counts + t) : 0u;
+    const unsigned incl = warp_inclusive_scan(c, lane);
+    const unsigned gsize = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (gsize == 0) continue;
+    const unsigned my_excl = incl - c;
+    const unsigned long long gp = group_prefix[g];
+    for (unsigned r0 = 0; r0 < gsize; r0 += 32) {
+      const unsigned r = r0 + lane;
+      const unsigned kt = group_tile_of(r < gsize ? r : gsize - 1, my_excl);
+      const unsigned ek = __shfl_sync(0xFFFFFFFFu, my_excl, kt);
+      if (r < gsize) {
+        const unsigned long long src = (unsigned long long)(g * 32u + kt) * TILE_SLOT + (r - ek);
+        float o;
+        const bool keep = qt_rescale_one(raw_slots[src], qt[j_slots[src]], k, &o);
+        ac_out[gp + r] = o;
+        if (!keep) dropped++;
+      }
+    }
   }
   if (dropped) atomicAdd(&info->n_qt_dropped, (unsigned long long)dropped);
 }
 
+// Serial fallback for the reference's "rescaled outlier fell back inside the bin range" quirk
+// (dctz-comp-lib.c:494-506: such a value is not stored although its bin index stays 255).  It is a
+// no-op unless that ever happens (it cannot for realistic data).
 template <typename T>
-__global__ void __launch_bounds__(32) k_qt_compact(const T *__restrict__ raw, const uint8_t *__restrict__ jidx,
-                                                   const T *__restrict__ qraw, QtConsts<T> k, float *ac_out, Info *info) {
+__global__ void __launch_bounds__(32) k_qt_compact(const unsigned *__restrict__ counts, unsigned ntiles, const T *__restrict__ raw_slots,
+                                                   const uint8_t *__restrict__ j_slots, const T *__restrict__ qraw, QtConsts<T> k,
+                                                   float *ac_out, Info *info) {
   if (info->n_qt_dropped == 0) return;  // the only path ever taken in practice
   if (threadIdx.x != 0) return;
-  const unsigned long long n = info->n_outliers;
   unsigned long long w = 0;
-  for (unsigned long long i = 0; i < n; i++) {
-    T q = qraw[jidx[i]];
-    if (jidx[i] >= 1 && q < (T)1.0) q = (T)1.0;
-    float o;
-    if (qt_rescale_one(raw[i], q, k, &o)) ac_out[w++] = o;
+  for (unsigned t = 0; t < ntiles; t++) {
+    const unsigned long long slot = (unsigned long long)t * TILE_SLOT;
+    for (unsigned i = 0; i < counts[t]; i++) {
+      T q = qraw[j_slots[slot + i]];
+      if (j_slots[slot + i] >= 1 && q < (T)1.0) q = (T)1.0;
+      float o;
+      if (qt_rescale_one(raw_slots[slot + i], q, k, &o)) ac_out[w++] = o;
+    }
   }
   info->n_outliers = w;
 }
 
+// Decompress pre-pass: number of 255 markers at positions j >= 1 per warp tile (32 blocks = 2 KB of bin ids).
+__global__ void __launch_bounds__(256) k_count_bins(const uint8_t *__restrict__ bins, unsigned long long nblk_full,
+                                                    unsigned *__restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
+  const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += wpg) {
+    const unsigned long long first = (unsigned long long)t * WTILE;
+    const unsigned rows = (nblk_full - first < (unsigned long long)WTILE) ? (unsigned)(nblk_full - first) : (unsigned)WTILE;
+    const uint4 *p = reinterpret_cast<const uint4 *>(bins + first * BLK);
+    unsigned cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const unsigned chunk = i * 32 + lane;  // 16-byte chunk of the tile; 4 chunks per block
+      if (chunk < rows * 4u) {
+        const uint4 v = __ldg(p + chunk);
+        const unsigned x0 = (chunk & 3u) ? v.x : (v.x & 0xFFFFFF00u);  // byte 0 of a block is the DC marker
+        cnt += __popc(ff_bytes(x0)) + __popc(ff_bytes(v.y)) + __popc(ff_bytes(v.z)) + __popc(ff_bytes(v.w));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (lane == 0) counts[t] = cnt;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K3: dequantise + DCT-III + de-scale (dctz-decomp-lib.c:389-511).
-// Shared memory: [ out tile: 128 rows x 64 T, swizzled ][ outlier stage ][ centre table 256 T ]
+// Shared memory: [ centre table 256 T ] + per warp [ tile: 32 padded rows; its first bytes double as
+// the outlier stage before the inverse transform ][ bin ids 2 KB ][ DC 128 B ]
 // ------------------------------------------------------------------------------------------
 template <typename T, bool QT> struct DecompressCfg {
-  typedef typename std::conditional<QT, T, float>::type StageT;  // QT stages the un-rescaled coefficient
-  static constexpr int CAP = 63 * TILE_BLOCKS;
-  static constexpr int SMEM = TileLayout<T>::TILE_BYTES + CAP * (int)sizeof(StageT) + 256 * (int)sizeof(T);
+  static constexpr int WARPS = 4;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int CTAS_PER_SM = (sizeof(T) == 8) ? 2 : 3;
+  static constexpr int OFF_BINS = WarpTile<T>::BYTES;          // >= 63*32 floats of outlier stage
+  static constexpr int OFF_DC = OFF_BINS + WTILE * BLK;
+  static constexpr int WARP_BYTES = ((OFF_DC + WTILE * 4 + 127) / 128) * 128;
+  static constexpr int OFF_WARPS = 256 * (int)sizeof(T);
+  static constexpr int SMEM = OFF_WARPS + WARPS * WARP_BYTES;
+  static_assert(WarpTile<T>::BYTES >= 63 * WTILE * 4, "the tile must hold a full tile of outliers");
 };
 
 __device__ __forceinline__ double qt_unscale_one(float acf, double q, const QtConsts<double> &k) {
@@ -678,129 +918,165 @@ __device__ __forceinline__ float qt_unscale_one(float acf, float q, const QtCons
   return (float)__dmul_rn(__ddiv_rn((double)__fsub_rn(acf, k.d_rmin), k.den), (double)q);
 }
 
+template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+
 template <typename T, bool QT>
-__global__ void __launch_bounds__(TILE_BLOCKS, (sizeof(T) == 8 ? 2 : 3))
+__global__ void __launch_bounds__(DecompressCfg<T, QT>::THREADS, DecompressCfg<T, QT>::CTAS_PER_SM)
 k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, const float *__restrict__ ac_in,
              const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
-             T *__restrict__ out, unsigned long long *__restrict__ status, unsigned epoch, TileControl *ctl,
-             unsigned long long *n_consumed) {
+             T *__restrict__ out, const unsigned *__restrict__ counts,
+             const unsigned long long *__restrict__ group_prefix, TileControl *ctl) {
   typedef typename ArithOf<T>::type A;
   typedef DecompressCfg<T, QT> Cfg;
-  typedef typename Cfg::StageT StageT;
-  typedef TileLayout<T> L;
+  typedef WarpTile<T> L;
+  constexpr unsigned FULL = 0xFFFFFFFFu;
   extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char *tile = smem;
-  StageT *stage = reinterpret_cast<StageT *>(smem + L::TILE_BYTES);
-  T *center = reinterpret_cast<T *>(smem + L::TILE_BYTES + Cfg::CAP * sizeof(StageT));
-  __shared__ ScanSmem scan;
-  __shared__ unsigned s_next;
+  __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
   __shared__ T s_qt[QT ? BLK : 1];
 
-  const int tid = threadIdx.x;
-  const unsigned ntiles = (unsigned)((nblk_full + TILE_BLOCKS - 1) / TILE_BLOCKS);
-  // bin centres: gen_bins / gen_bins_f (binning.c:19-22, 39-42): centre = (int multiple) * bin_width
-  for (int i = tid; i < 256; i += TILE_BLOCKS) {
-    if (sizeof(T) == 8) center[i] = (T)__dmul_rn((double)center_multiple((unsigned)i), (double)bin_width);
-    else center[i] = (T)__fmul_rn((float)center_multiple((unsigned)i), (float)bin_width);
-  }
-  if (QT && tid < BLK) s_qt[tid] = qtable[tid];
-  if (tid == 0) s_next = atomicAdd(&ctl->ticket, 1u);
-  __syncthreads();
-  unsigned cur = s_next;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T *center = reinterpret_cast<T *>(smem);
+  unsigned char *wsm = smem + Cfg::OFF_WARPS + warp * Cfg::WARP_BYTES;
+  float *stage = reinterpret_cast<float *>(wsm);  // aliases the tile rows; dead before they are written
+  unsigned char *binbuf = wsm + Cfg::OFF_BINS;
+  float *dcbuf = reinterpret_cast<float *>(wsm + Cfg::OFF_DC);
+  const unsigned mb = smem_u32(&s_mbar[warp]);
+  const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
+
+  // bin centres: gen_bins / gen_bins_f (binning.c:19-22, 39-42): centre = (int multiple) * bin_width.  The de-scale
+  // (x * sf, dctz-decomp-lib.c:494-511) is folded into the coefficients -- the inverse transform is linear, the
+  // result moves by ~1 ulp -- so the table holds centre * sf.
+  for (int i = threadIdx.x; i < 256; i += Cfg::THREADS) center[i] = mul_rn<T>(mul_rn<T>((T)center_multiple((unsigned)i), bin_width), sf);
+  if (QT && threadIdx.x < BLK) s_qt[threadIdx.x] = qtable[threadIdx.x];
+  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
+  __syncthreads();  // the only CTA-wide barrier before the epilogue
+
+  auto rows_of = [&](unsigned t) -> unsigned {
+    const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
+    return left < (unsigned long long)WTILE ? (unsigned)left : (unsigned)WTILE;
+  };
+  auto issue_tile = [&](unsigned t) {  // bin ids (2 KB) + DC (128 B) of tile t, two bulk copies by lane 0
+    if (lane == 0) {
+      const unsigned rows = rows_of(t);
+      // the DC slice is 4*rows bytes: bulk copies need a multiple of 16, so partial tiles load DC directly
+      const bool dc_bulk = (rows == WTILE);
+      mbar_expect_tx(mb, rows * BLK + (dc_bulk ? WTILE * 4 : 0));
+      bulk_g2s(smem_u32(binbuf), bins + (unsigned long long)t * WTILE * BLK, rows * BLK, mb);
+      if (dc_bulk) bulk_g2s(smem_u32(dcbuf), dc_in + (unsigned long long)t * WTILE, WTILE * 4, mb);
+    }
+  };
+  auto take_ticket = [&]() -> unsigned {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(&ctl->ticket, 1u);
+    return t;
+  };
+
+  const unsigned nwarps_grid = gridDim.x * Cfg::WARPS;  // ticket discipline: see k_compress
+  unsigned cur = blockIdx.x * Cfg::WARPS + warp;
+  if (cur < ntiles) issue_tile(cur);
+  unsigned phase = 0;
 
   while (cur < ntiles) {
-    const unsigned long long blk = (unsigned long long)cur * TILE_BLOCKS + tid;
-    const bool active = blk < nblk_full;
+    const unsigned pending = take_ticket();
+    const unsigned rows = rows_of(cur);
+    const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
+    const bool active = (unsigned)lane < rows;
+    mbar_wait(mb, phase);
+    phase ^= 1u;
     unsigned w[16];
-    if (active) {
-      const uint4 *bp = reinterpret_cast<const uint4 *>(bins + blk * BLK);
+    {
+      const uint4 *bp = reinterpret_cast<const uint4 *>(binbuf + lane * BLK);
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const uint4 v = __ldg(bp + q);
+        const uint4 v = bp[q];
         w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
       }
-    } else {
+    }
+    float dcv = (rows == WTILE) ? dcbuf[lane] : (active ? __ldg(dc_in + blk) : 0.f);
+    if (!active) {
 #pragma unroll
       for (int q = 0; q < 16; q++) w[q] = 0;
     }
-    const float dcv = active ? __ldg(dc_in + blk) : 0.f;
+    __syncwarp();                        // bin ids and DC are in registers
+    const unsigned nxt = nwarps_grid + __shfl_sync(FULL, pending, 0);
+    if (nxt < ntiles) issue_tile(nxt);   // prefetch the next tile's bin ids
+
     unsigned cnt = 0;
 #pragma unroll
-    for (int q = 0; q < 16; q++) {
-      const unsigned word = (q == 0) ? (w[0] & 0xFFFFFF00u) : w[q];  // position 0 is the DC marker
-      cnt += __popc(__vcmpeq4(word, 0xFFFFFFFFu) & 0x01010101u);
+    for (int q = 0; q < 16; q++) cnt += __popc(ff_bytes(q == 0 ? (w[0] & 0xFFFFFF00u) : w[q]));  // position 0 is the DC marker
+    const unsigned incl = warp_inclusive_scan(cnt, lane);
+    const unsigned tile_total = __shfl_sync(FULL, incl, 31);
+    const unsigned my_off = incl - cnt;
+    // offset of the tile's first outlier: scanned group prefix + the counts of the earlier tiles of the group
+    unsigned long long tile_base = group_prefix[cur >> 5];
+    {
+      unsigned e = ((unsigned)lane < (cur & 31u)) ? __ldg(counts + (cur & ~31u) + lane) : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
+      tile_base += e;
     }
-    if (tid == 0) s_next = atomicAdd(&ctl->ticket, 1u);
-
-    unsigned tile_total;
-    unsigned long long tile_base;
-    const unsigned my_off = tile_scan(cnt, scan, status, cur, epoch, &tile_total, &tile_base);
-    const unsigned nxt = s_next;  // written before the barriers inside tile_scan
+    bulk_wait_read();  // this lane's previous output row has left shared memory (it aliases the stage)
+    __syncwarp();
 
     // ---- stage this tile's outliers (coalesced) ----
-    if (!QT) {
-      for (unsigned i = tid; i < tile_total; i += TILE_BLOCKS) stage[i] = (StageT)__ldg(ac_in + tile_base + i);
-    } else {
-      // un-rescale while staging (dctz-decomp-lib.c:404-409 / 450-454): needs each outlier's j
+    for (unsigned i = lane; i < tile_total; i += 32) stage[i] = __ldg(ac_in + tile_base + i);
+    __syncwarp();
+
+    // ---- rebuild coefficients (dctz-decomp-lib.c:392-416), already multiplied by sf ----
+    T x[BLK];
+    x[0] = mul_rn<T>((T)dcv, sf);  // :392
+#pragma unroll
+    for (int j = 1; j < BLK; j++) {
+      const unsigned id = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+      x[j] = center[id];  // entry 255 is a dummy, fixed below
+    }
+    if (cnt != 0) {
       unsigned p = my_off;
 #pragma unroll
-      for (int q = 0; q < 16; q++) {  // fully unrolled: w[] must stay in registers
-        unsigned m = __vcmpeq4((q == 0) ? (w[0] & 0xFFFFFF00u) : w[q], 0xFFFFFFFFu) & 0x01010101u;
-        while (m) {
-          const int b = (__ffs(m) - 1) >> 3;
-          m &= m - 1;
-          const int j = 4 * q + b;
-          stage[p] = (StageT)qt_unscale_one(__ldg(ac_in + tile_base + p), s_qt[j], qk);
-          p++;
+      for (int q = 0; q < 16; q++) {
+        unsigned m = ff_bytes(w[q]);
+        if (q == 0) m &= ~1u;
+        if (m) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int j = 4 * q + b;
+            if (j >= 1 && (m & (1u << (8 * b)))) {
+              const float a = stage[p++];  // :402-403
+              T v;
+              if (QT) v = qt_unscale_one(a, s_qt[j], qk); else v = (T)a;
+              x[j] = mul_rn<T>(v, sf);
+            }
+          }
         }
       }
     }
-    __syncthreads();
+    __syncwarp();  // every lane is done with the stage before the rows are overwritten
 
-    // ---- rebuild coefficients ----
-    T x[BLK];
-    x[0] = (T)dcv;  // :392
-    {
-      unsigned p = my_off;
-#pragma unroll
-      for (int j = 1; j < BLK; j++) {
-        const unsigned id = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-        T v = center[id];  // entry 255 is a dummy
-        if (id == 255u) { v = (T)stage[p]; p++; }
-        x[j] = v;
-      }
-    }
-    // ---- orthonormal DCT-III (dct.c:115-205) and de-scale (:494-511) ----
+    // ---- orthonormal DCT-III (dct.c:115-205) ----
     dct64_inverse<A>(x);
-    if (sf != (T)1) {
-#pragma unroll
-      for (int j = 0; j < BLK; j++) x[j] = (sizeof(T) == 8) ? (T)__dmul_rn((double)x[j], (double)sf) : (T)__fmul_rn((float)x[j], (float)sf);
-    }
-    // ---- registers -> swizzled shared tile -> coalesced 128-bit global stores ----
-#pragma unroll
-    for (int c = 0; c < L::CH; c++) {
-      uint4 v;
-      T *e = reinterpret_cast<T *>(&v);
-#pragma unroll
-      for (int k = 0; k < 16 / (int)sizeof(T); k++) e[k] = x[c * (16 / (int)sizeof(T)) + k];
-      *reinterpret_cast<uint4 *>(tile + L::offset(tid, c)) = v;
-    }
-    __syncthreads();
+
+    // ---- registers -> own padded row -> one bulk store per lane ----
     {
-      const unsigned long long first_blk = (unsigned long long)cur * TILE_BLOCKS;
-      const unsigned long long rows = (nblk_full - first_blk < TILE_BLOCKS) ? (nblk_full - first_blk) : TILE_BLOCKS;
-      const unsigned nchunks = (unsigned)rows * L::CH;
-      uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(out) + first_blk * L::ROW_BYTES);
-#pragma unroll 8
-      for (unsigned g = tid; g < (unsigned)TILE_BLOCKS * L::CH; g += TILE_BLOCKS) {
-        if (g < nchunks) dst[g] = *reinterpret_cast<const uint4 *>(tile + L::offset(g / L::CH, g % L::CH));
+      unsigned char *row = wsm + lane * L::ROW_STRIDE;
+#pragma unroll
+      for (int c = 0; c < L::CH; c++) {
+        uint4 v;
+        T *e = reinterpret_cast<T *>(&v);
+#pragma unroll
+        for (int k = 0; k < 16 / (int)sizeof(T); k++) e[k] = x[c * (16 / (int)sizeof(T)) + k];
+        *reinterpret_cast<uint4 *>(row + 16 * c) = v;
       }
+      fence_async_smem();
+      if (active) bulk_s2g(out + blk * BLK, smem_u32(row), L::ROW_BYTES);
+      bulk_commit();
     }
-    if (cur == ntiles - 1 && tid == 0 && n_consumed) *n_consumed = tile_base + tile_total;
-    __syncthreads();  // tile and stage are reused by the next iteration
     cur = nxt;
   }
-  if (tid == 0) {
+  bulk_wait_all();
+  __syncthreads();
+  if (threadIdx.x == 0) {
     __threadfence();
     const unsigned prev = atomicAdd(&ctl->done, 1u);
     if (prev == gridDim.x - 1) { ctl->ticket = 0u; ctl->done = 0u; }
@@ -862,8 +1138,9 @@ __global__ void __launch_bounds__(256) k_scale(T *x, size_t n, T sf, int multipl
 }
 
 // DCT-only kernels behind dctz_gpu_dct_blocks (dct.h:17-27 equivalents)
+constexpr int DCT_ONLY_THREADS = 128;
 template <typename T, bool INVERSE>
-__global__ void __launch_bounds__(TILE_BLOCKS) k_dct64_blocks(const T *__restrict__ in, T *__restrict__ out, size_t nblocks) {
+__global__ void __launch_bounds__(DCT_ONLY_THREADS) k_dct64_blocks(const T *__restrict__ in, T *__restrict__ out, size_t nblocks) {
   typedef typename ArithOf<T>::type A;
   const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nblocks) return;
