@@ -213,8 +213,8 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->stat_grid = ctx->sm_count * 8;
   CU(cudaMalloc(&ctx->d_partials, sizeof(StatPartial) * ctx->stat_grid));
-  CU(cudaMalloc(&ctx->d_done, sizeof(unsigned)));
-  CU(cudaMemset(ctx->d_done, 0, sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->d_done, 2 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups
+  CU(cudaMemset(ctx->d_done, 0, 2 * sizeof(unsigned)));
   CU(cudaMalloc(&ctx->d_stats3, 3 * sizeof(double)));
   CU(cudaMalloc(&ctx->d_params, sizeof(DevParams)));
   CU(cudaMalloc(&ctx->d_info, sizeof(Info)));
@@ -229,6 +229,8 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   TRY(upload(ctx, ctx->sfv_f, &ctx->tb.sf_f));
   ctx->tb.n_d = (int)ctx->thr_d.size();
   ctx->tb.n_f = (int)ctx->thr_f.size();
+  ctx->tb.kmin_d = -306;
+  ctx->tb.kmin_f = -36;
   ctx->tb.min_d = ctx->min_d;
   ctx->tb.min_f = ctx->min_f;
   // kernel attributes + residency (persistent grids are sized from these)
@@ -307,12 +309,17 @@ static int check_common(dctz_gpu_ctx *ctx, int datatype, double eb) {
 }
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
-struct ScanBufs { unsigned *counts; unsigned long long *group_prefix; };
+struct ScanBufs { unsigned *counts; ScanOut out; unsigned nchunks; };
+static size_t up128(size_t v) { return (v + 127) / 128 * 128; }
 static int scan_bufs(dctz_gpu_ctx *ctx, size_t n_entries, ScanBufs *sb) {
-  const size_t ngroups = (n_entries + 31) / 32;
-  TRY(grow(ctx, ctx->status, ngroups * 8 + n_entries * 4 + 128));
-  sb->group_prefix = (unsigned long long *)ctx->status.p;
-  sb->counts = (unsigned *)((char *)ctx->status.p + ((ngroups * 8 + 127) / 128) * 128);  // 16-byte aligned for the uint4 loads
+  const size_t ngroups = (n_entries + 31) / 32, nchunks = (ngroups + 1023) / 1024;
+  TRY(grow(ctx, ctx->status, up128(ngroups * 8) + up128(nchunks * 8) + n_entries * 4));
+  char *p = (char *)ctx->status.p;
+  sb->out.group_prefix = (unsigned long long *)p;
+  sb->out.chunk_prefix = (unsigned long long *)(p + up128(ngroups * 8));
+  sb->out.done = ctx->d_done + 1;
+  sb->counts = (unsigned *)(p + up128(ngroups * 8) + up128(nchunks * 8));  // 16-byte aligned for the uint4 loads
+  sb->nchunks = (unsigned)nchunks;
   return DCTZ_GPU_OK;
 }
 
@@ -420,12 +427,12 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     ctx->launches++;
     CU(cudaGetLastError());
   }
-  k_scan_groups<<<1, 1024, 0, st>>>(sb.counts, (unsigned)n_entries, sb.group_prefix, &d_info->n_outliers, nullptr);
+  k_scan_groups<<<sb.nchunks, 1024, 0, st>>>(sb.counts, (unsigned)n_entries, sb.out, &d_info->n_outliers);
   ctx->launches++;
   if (!QT) {
     const size_t ngroups = (n_entries + 31) / 32, want = (ngroups + 7) / 8;
     const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? want : (size_t)ctx->sm_count * 8);
-    k_gather_ec<<<grid, 256, 0, st>>>(sb.counts, sb.group_prefix, (unsigned)n_entries, ac_slots, d_ac);
+    k_gather_ec<<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, (unsigned)n_entries, ac_slots, d_ac);
     ctx->launches++;
   }
   CU(cudaGetLastError());
@@ -476,7 +483,7 @@ static int launch_qt_finish(dctz_gpu_ctx *ctx, double eb, const T *d_qraw, T *d_
   TRY(scan_bufs(ctx, n_entries, &sb));  // same layout as in the compress call: nothing is reallocated
   const size_t ngroups = (n_entries + 31) / 32, want = (ngroups + 7) / 8;
   const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? (want ? want : 1) : (size_t)ctx->sm_count * 8);
-  k_qt_gather<T><<<grid, 256, 0, st>>>(sb.counts, sb.group_prefix, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p,
+  k_qt_gather<T><<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p,
                                        d_qraw, d_qtable, k, d_ac, d_info);
   k_qt_compact<T><<<1, 32, 0, st>>>(sb.counts, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, k, d_ac, d_info);
   ctx->launches += 2;
@@ -532,14 +539,14 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
       const size_t want = (ntiles + 7) / 8;
       const int grid = (int)(want < (size_t)ctx->sm_count * 16 ? want : (size_t)ctx->sm_count * 16);
       k_count_bins<<<grid, 256, 0, st>>>(d_bins, nblk_full, sb.counts);
-      k_scan_groups<<<1, 1024, 0, st>>>(sb.counts, (unsigned)ntiles, sb.group_prefix, ctx->d_nconsumed, nullptr);
+      k_scan_groups<<<sb.nchunks, 1024, 0, st>>>(sb.counts, (unsigned)ntiles, sb.out, ctx->d_nconsumed);
       ctx->launches += 2;
     }
     const size_t resident = (size_t)ctx->sm_count * ctx->occ[1][sizeof(T) == 8][QT];
     const size_t ctas = (ntiles + Cfg::WARPS - 1) / Cfg::WARPS;
     const int grid = (int)(ctas < resident ? ctas : resident);
     k_decompress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, d_out, sb.counts,
-                                                               sb.group_prefix, &ctx->d_ctl[1]);
+                                                               sb.out.group_prefix, sb.out.chunk_prefix, &ctx->d_ctl[1]);
     ctx->launches++;
     CU(cudaGetLastError());
   }

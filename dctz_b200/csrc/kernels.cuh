@@ -45,8 +45,8 @@ template <> struct QuantConsts<float> {
 };
 
 struct SfTables {         // host libm results, see build_sf_tables() in dctz_gpu.cu
-  const double *thr_d; const double *sf_d; int n_d; double min_d;  // valid for max|x| >= min_d
-  const float *thr_f; const float *sf_f; int n_f; float min_f;
+  const double *thr_d; const double *sf_d; int n_d, kmin_d; double min_d;  // thr[i] = T_{kmin+i}; valid for max|x| >= min_d
+  const float *thr_f; const float *sf_f; int n_f, kmin_f; float min_f;
   int qmax_words;          // 64-bit words of the QT per-position maxima to clear (64 elements of T)
 };
 
@@ -186,15 +186,20 @@ __global__ void __launch_bounds__(256) k_stats(const T *__restrict__ in, size_t 
 
 // sf = pow(10, ceil(log10(max)) - 1) through threshold tables built with the host libm, so the
 // result is bit-identical to util.c:28 (double) / util.c:42 (float) without a host round trip.
+// Smallest index i with mx < thr[i] (n if none): a linear search from the guess the binary exponent
+// gives (log10(mx) ~ 0.30103 * ilogb(mx), off by at most one), i.e. two or three loads instead of ten.
+template <typename T> __device__ __forceinline__ int sf_index(T mx, const T *thr, int n, int kmin, int e2) {
+  int lo = (int)floorf((float)e2 * 0.30103f) - kmin;
+  lo = lo < 0 ? 0 : (lo > n ? n : lo);
+  while (lo < n && !(mx < thr[lo])) lo++;
+  while (lo > 0 && mx < thr[lo - 1]) lo--;
+  return lo;
+}
 __device__ __forceinline__ double sf_lookup_d(double mx, const SfTables &tb) {
-  int lo = 0, hi = tb.n_d;  // smallest k with mx < thr[k]; n_d if none
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (mx < tb.thr_d[mid]) hi = mid; else lo = mid + 1; }
-  return tb.sf_d[lo];
+  return tb.sf_d[sf_index<double>(mx, tb.thr_d, tb.n_d, tb.kmin_d, ilogb(mx))];
 }
 __device__ __forceinline__ float sf_lookup_f(float mx, const SfTables &tb) {
-  int lo = 0, hi = tb.n_f;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (mx < tb.thr_f[mid]) hi = mid; else lo = mid + 1; }
-  return tb.sf_f[lo];
+  return tb.sf_f[sf_index<float>(mx, tb.thr_f, tb.n_f, tb.kmin_f, ilogbf(mx))];
 }
 
 __device__ __forceinline__ void finalize_params(const double *stats_all, int nranks, unsigned long long n_total,
@@ -683,58 +688,87 @@ __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /
 // ------------------------------------------------------------------------------------------
 // Scan + gather: per-tile counts -> exclusive prefix per group of 32 tiles -> final AC_exact order.
 // ------------------------------------------------------------------------------------------
-// One CTA.  group_prefix[g] = number of outliers in all tiles before group g; *total (and *total2 if
-// non-NULL) receive the grand total.  ntiles is at most a few million, the counts a few MB.
-__global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *__restrict__ counts, unsigned ntiles,
-                                                     unsigned long long *__restrict__ group_prefix,
-                                                     unsigned long long *total, unsigned long long *total2) {
-  __shared__ unsigned long long s_warp[32];
-  __shared__ unsigned long long s_carry;
-  const unsigned ngroups = (ntiles + 31u) / 32u;
+// Chunk c = 1024 consecutive groups, one per thread of CTA c.  group_prefix[g] = outliers in the earlier
+// groups of the same chunk; the last CTA to finish turns the chunk totals into chunk_prefix[c] and
+// writes the grand total to *total.  Consumers add the two: prefix_of_group().
+struct ScanOut {
+  unsigned long long *group_prefix;  // one per group
+  unsigned long long *chunk_prefix;  // one per chunk (first used as chunk totals)
+  unsigned *done;                    // CTAs finished; reset by the last one
+};
+__device__ __forceinline__ unsigned long long prefix_of_group(const unsigned long long *__restrict__ group_prefix,
+                                                              const unsigned long long *__restrict__ chunk_prefix, unsigned g) {
+  return __ldg(chunk_prefix + (g >> 10)) + __ldg(group_prefix + g);
+}
+__device__ __forceinline__ unsigned long long block_exclusive_scan_1024(unsigned long long v, unsigned long long *s_warp,
+                                                                        unsigned long long *total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0ull;
-  __syncthreads();
-  for (unsigned g0 = 0; g0 < ngroups; g0 += 1024) {
-    const unsigned g = g0 + threadIdx.x;
-    unsigned long long sum = 0;
-    if (g < ngroups) {  // the 32 counts of a group are one 128-byte line
-      const unsigned first = g * 32u;
-      if (first + 32u <= ntiles) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(counts + first);
+  unsigned long long incl = v;
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const uint4 v = __ldg(p + k); sum += (unsigned long long)v.x + v.y + v.z + v.w; }
-      } else {
-        for (unsigned t = first; t < ntiles; t++) sum += counts[t];
-      }
-    }
-    unsigned long long incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long w = s_warp[lane];
+    unsigned long long wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += n;
+      const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+      if (lane >= o) wi += n;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      unsigned long long w = s_warp[lane], wi = w;
+    s_warp[lane] = wi - w;
+    if (lane == 31) s_warp[32] = wi;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[warp] + incl - v;
+}
+__global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *__restrict__ counts, unsigned ntiles, ScanOut out,
+                                                     unsigned long long *total) {
+  __shared__ unsigned long long s_warp[33];
+  __shared__ bool s_last;
+  const unsigned ngroups = (ntiles + 31u) / 32u;
+  const unsigned g = blockIdx.x * 1024u + threadIdx.x;
+  unsigned long long sum = 0;
+  if (g < ngroups) {  // the 32 counts of a group are one 128-byte line
+    const unsigned first = g * 32u;
+    if (first + 32u <= ntiles) {
+      const uint4 *p = reinterpret_cast<const uint4 *>(counts + first);
+      uint4 v[8];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-        if (lane >= o) wi += n;
-      }
-      s_warp[lane] = wi - w;  // exclusive prefix of the warp sums
+      for (int k = 0; k < 8; k++) v[k] = __ldg(p + k);
+#pragma unroll
+      for (int k = 0; k < 8; k++) sum += (unsigned long long)v[k].x + v[k].y + v[k].z + v[k].w;
+    } else {
+      for (unsigned t = first; t < ntiles; t++) sum += counts[t];
     }
-    __syncthreads();
-    const unsigned long long carry = s_carry;
-    if (g < ngroups) group_prefix[g] = carry + s_warp[warp] + incl - sum;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + incl;
-    __syncthreads();
   }
+  unsigned long long chunk_total;
+  const unsigned long long excl = block_exclusive_scan_1024(sum, s_warp, &chunk_total);
+  if (g < ngroups) out.group_prefix[g] = excl;
   if (threadIdx.x == 0) {
-    *total = s_carry;
-    if (total2) *total2 = s_carry;
+    out.chunk_prefix[blockIdx.x] = chunk_total;
+    __threadfence();
+    s_last = (atomicAdd(out.done, 1u) == gridDim.x - 1);
   }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: exclusive scan of the chunk totals (any number of chunks, 1024 at a time)
+  unsigned long long carry = 0;
+  for (unsigned c0 = 0; c0 < gridDim.x; c0 += 1024u) {
+    const unsigned c = c0 + threadIdx.x;
+    const unsigned long long v = (c < gridDim.x) ? *(volatile unsigned long long *)(out.chunk_prefix + c) : 0ull;
+    unsigned long long tot;
+    __syncthreads();
+    const unsigned long long e = block_exclusive_scan_1024(v, s_warp, &tot);
+    if (c < gridDim.x) out.chunk_prefix[c] = carry + e;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) { *total = carry; *out.done = 0u; }
 }
 
 // Shared by the gather kernels: a warp owns one group; every lane learns the exclusive prefix of
@@ -752,7 +786,7 @@ __device__ __forceinline__ unsigned group_tile_of(unsigned r, unsigned my_excl) 
 
 // EC: move the tile-strided runs to their final, contiguous place.
 __global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
-                                                   unsigned ntiles, const float *__restrict__ ac_slots, float *__restrict__ ac_out) {
+                                                   const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles, const float *__restrict__ ac_slots, float *__restrict__ ac_out) {
   const int lane = threadIdx.x & 31;
   const unsigned ngroups = (ntiles + 31u) / 32u;
   const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
@@ -763,7 +797,7 @@ __global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ 
     const unsigned gsize = __shfl_sync(0xFFFFFFFFu, incl, 31);
     if (gsize == 0) continue;
     const unsigned my_excl = incl - c;
-    const unsigned long long gp = group_prefix[g];
+    const unsigned long long gp = prefix_of_group(group_prefix, chunk_prefix, g);
     for (unsigned r0 = 0; r0 < gsize; r0 += 32) {
       const unsigned r = r0 + lane;
       const unsigned k = group_tile_of(r < gsize ? r : gsize - 1, my_excl);  // all lanes take part in the shuffles
@@ -803,7 +837,7 @@ __device__ __forceinline__ bool qt_rescale_one(float item, float q, const QtCons
 // QT gather: rescale while moving to the final place.
 template <typename T>
 __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
-                                                   unsigned ntiles, const T *__restrict__ raw_slots, const uint8_t *__restrict__ j_slots,
+                                                   const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles, const T *__restrict__ raw_slots, const uint8_t *__restrict__ j_slots,
                                                    const T *__restrict__ qraw /* global maxima, [0] = last DC */,
                                                    T *__restrict__ qtable_out, QtConsts<T> k, float *__restrict__ ac_out, Info *info) {
   __shared__ T qt[BLK];
@@ -825,7 +859,7 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
     const unsigned gsize = __shfl_sync(0xFFFFFFFFu, incl, 31);
     if (gsize == 0) continue;
     const unsigned my_excl = incl - c;
-    const unsigned long long gp = group_prefix[g];
+    const unsigned long long gp = prefix_of_group(group_prefix, chunk_prefix, g);
     for (unsigned r0 = 0; r0 < gsize; r0 += 32) {
       const unsigned r = r0 + lane;
       const unsigned kt = group_tile_of(r < gsize ? r : gsize - 1, my_excl);
@@ -927,7 +961,8 @@ __global__ void __launch_bounds__(DecompressCfg<T, QT>::THREADS, DecompressCfg<T
 k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, const float *__restrict__ ac_in,
              const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
              T *__restrict__ out, const unsigned *__restrict__ counts,
-             const unsigned long long *__restrict__ group_prefix, TileControl *ctl) {
+             const unsigned long long *__restrict__ group_prefix, const unsigned long long *__restrict__ chunk_prefix,
+             TileControl *ctl) {
   typedef typename ArithOf<T>::type A;
   typedef DecompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -1010,7 +1045,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     const unsigned tile_total = __shfl_sync(FULL, incl, 31);
     const unsigned my_off = incl - cnt;
     // offset of the tile's first outlier: scanned group prefix + the counts of the earlier tiles of the group
-    unsigned long long tile_base = group_prefix[cur >> 5];
+    unsigned long long tile_base = prefix_of_group(group_prefix, chunk_prefix, cur >> 5);
     {
       unsigned e = ((unsigned)lane < (cur & 31u)) ? __ldg(counts + (cur & ~31u) + lane) : 0u;
 #pragma unroll
