@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdctz_gpu
 # every symbol include/dctz_gpu.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
     "dctz_gpu_create", "dctz_gpu_destroy", "dctz_gpu_last_error", "dctz_gpu_device_count", "dctz_gpu_sm_count",
-    "dctz_gpu_host_alloc", "dctz_gpu_host_free", "dctz_gpu_compress_core", "dctz_gpu_decompress_core",
+    "dctz_gpu_host_alloc", "dctz_gpu_host_free", "dctz_gpu_compress_core", "dctz_gpu_decompress_core", "dctz_gpu_stats",
     "dctz_gpu_stats_dev", "dctz_gpu_compress_dev", "dctz_gpu_qt_finish_dev", "dctz_gpu_compress_field_dev",
     "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_fill_hash_field",
     "dctz_gpu_sf_from_max", "dctz_gpu_selftest_division", "dctz_gpu_launch_count", "dctz_gpu_set_option",
@@ -62,6 +62,7 @@ def load_library():
         "dctz_gpu_host_free": (None, [vp]),
         "dctz_gpu_compress_core": (i32, [vp, vp, sz, i32, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(GpuInfo)]),
         "dctz_gpu_decompress_core": (i32, [vp, vp, vp, vp, u64, vp, sz, i32, dbl, dbl, i32, vp]),
+        "dctz_gpu_stats": (i32, [vp, vp, sz, i32, C.POINTER(GpuInfo)]),
         "dctz_gpu_stats_dev": (i32, [vp, vp, sz, i32, vp, vp]),
         "dctz_gpu_compress_dev": (i32, [vp, vp, sz, sz, i32, dbl, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "dctz_gpu_qt_finish_dev": (i32, [vp, i32, dbl, vp, vp, vp, vp, vp]),
@@ -201,6 +202,12 @@ class Context:
         if want_scaled:
             res["scaled"] = scaled
         return res
+
+    def stats(self, x):
+        x = np.ascontiguousarray(x)
+        info = GpuInfo()
+        self._check(self._lib.dctz_gpu_stats(self._h, _p(x), x.size, _code(x.dtype), C.byref(info)))
+        return info.as_dict()
 
     def decompress_core(self, bin_index, dc, ac, n, dtype, eb, sf, qt=False, qtable=None, out=None):
         dtype = np.dtype(dtype)

@@ -636,6 +636,21 @@ extern "C" int dctz_gpu_compress_core(dctz_gpu_ctx *ctx, const void *in, size_t 
   return DCTZ_GPU_OK;
 }
 
+extern "C" int dctz_gpu_stats(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, dctz_gpu_info *info) {
+  TRY(check_common(ctx, datatype, 1.0));
+  if (!in || !info || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "stats: NULL pointer or N == 0");
+  CU(cudaSetDevice(ctx->device));
+  const size_t es = datatype == DCTZ_GPU_DOUBLE ? 8 : 4;
+  cudaStream_t st = ctx->stream;
+  TRY(grow(ctx, ctx->in, N * es));
+  CU(cudaMemcpyAsync(ctx->in.p, in, N * es, cudaMemcpyHostToDevice, st));
+  if (datatype == DCTZ_GPU_DOUBLE) TRY(launch_stats<double>(ctx, (const double *)ctx->in.p, N, ctx->d_stats3, 1, N, nullptr, ctx->d_info, st));
+  else TRY(launch_stats<float>(ctx, (const float *)ctx->in.p, N, ctx->d_stats3, 1, N, nullptr, ctx->d_info, st));
+  CU(cudaMemcpyAsync(info, ctx->d_info, sizeof(Info), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return DCTZ_GPU_OK;
+}
+
 extern "C" int dctz_gpu_decompress_core(dctz_gpu_ctx *ctx, const uint8_t *bin_index, const float *DC, const float *AC_exact,
                                         uint64_t n_outliers, const void *qtable, size_t N, int datatype, double eb, double sf,
                                         int mode_qt, void *out) {

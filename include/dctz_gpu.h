@@ -99,6 +99,10 @@ int dctz_gpu_decompress_core(dctz_gpu_ctx *ctx, const uint8_t *bin_index, const 
                              const float *AC_exact, uint64_t n_outliers, const void *qtable, size_t N,
                              int datatype, double error_bound, double sf, int mode_qt, void *out);
 
+/* stats: the GPU-backed equivalent of calc_data_stat() (util.c:12-44) on a host buffer; fills
+ * info->max_abs / min_abs / sum / mean / sf (the other fields are zero).                        */
+int dctz_gpu_stats(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, dctz_gpu_info *info);
+
 /* ---- device-resident API (benchmarks, multi-GPU slabs, pipelines) ---------------------------
  * All pointers are device pointers on ctx's device; `stream` is a cudaStream_t passed as void*
  * (NULL = default stream).  Input/outputs must be 16-byte aligned.

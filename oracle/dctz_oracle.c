@@ -347,7 +347,8 @@ int oracle_compress_core_d(double *buf, long n, double eb, int qt, unsigned char
         double item = ax[i * ORACLE_BLK + j];
         if (item < range_min) item = (item / qtab[j]) * eb * qt_factor + range_min;      /* :489 */
         else if (item > range_max) item = (item / qtab[j]) * eb * qt_factor + range_max; /* :491 */
-        ax[i * ORACLE_BLK + j] = item;
+        /* the reference also stores the rescaled value back into a_x (:493); nothing reads it afterwards, and `coef`
+         * is meant to equal the -DDCT_FILE_DEBUG dump taken before this loop (:422-433), so it is not mirrored */
         if (item < range_min || item > range_max) ac_exact[cnt++] = (float)item; /* :494-497 */
         /* else: the reference computes a bin id and drops it (:502-506): nothing is stored */
       } else {
@@ -419,8 +420,7 @@ int oracle_compress_core_f(float *buf, long n, double eb, int qt, unsigned char 
         /* :515/:517 -- (float/float) is float, then promoted to double by error_bound */
         if (item < range_min) item = (item / qtab[j]) * eb * qt_factor + range_min;
         else if (item > range_max) item = (item / qtab[j]) * eb * qt_factor + range_max;
-        ax[i * ORACLE_BLK + j] = item;
-        if (item < range_min || item > range_max) ac_exact[cnt++] = item; /* :520-523 */
+        if (item < range_min || item > range_max) ac_exact[cnt++] = item; /* :520-523 (write-back to a_x not mirrored, see above) */
       } else {
         ac_exact[cnt++] = ax[i * ORACLE_BLK + j]; /* :537 */
       }

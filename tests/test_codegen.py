@@ -1,0 +1,61 @@
+"""CPU: the generated straight-line DCT-64 (tools/gen_dct64.py -> dctz_b200/csrc/dct64_gen.cuh)."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import gen_dct64 as g  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def progs():
+    return g.build_forward(64), g.build_inverse(64)
+
+
+def test_flow_graph_is_the_orthonormal_dct(progs):
+    from scipy.fft import dct
+
+    f, i = progs
+    x = np.random.default_rng(0).standard_normal((500, 64))
+    want = dct(x, type=2, norm="ortho", axis=-1)
+    got = g.evaluate(f, x, np.float64)
+    assert np.max(np.abs(got - want)) <= 2e-15 * np.max(np.abs(want))
+    back = g.evaluate(i, want, np.float64)
+    assert np.max(np.abs(back - x)) <= 4e-15 * np.max(np.abs(x))
+
+
+def test_float_accuracy_inside_tolerance(progs):
+    from scipy.fft import dct
+
+    f, i = progs
+    x = np.random.default_rng(1).standard_normal((500, 64))
+    want = dct(x, type=2, norm="ortho", axis=-1)
+    got = g.evaluate(f, x.astype(np.float32), np.float32)
+    scale = np.max(np.abs(want), axis=-1, keepdims=True)
+    assert np.max(np.abs(got - want) / scale) <= 1e-6  # 1e-5 is the stated tolerance
+    back = g.evaluate(i, want.astype(np.float32), np.float32)
+    assert np.max(np.abs(back - x)) <= 4e-6
+
+
+def test_operation_count_and_symmetry(progs):
+    f, i = progs
+    cf, ci = g.op_counts(f), g.op_counts(i)
+    assert cf["total"] == 592 and ci["total"] == 592  # documented in DESIGN.md (9.25 flop-instructions / element)
+    assert cf["fma"] == ci["fma"] and cf["mul"] == ci["mul"]
+
+
+def test_committed_header_is_up_to_date():
+    path = os.path.join(ROOT, "dctz_b200", "csrc", "dct64_gen.cuh")
+    with tempfile.TemporaryDirectory() as d:
+        tmp = os.path.join(d, "dct64_gen.cuh")
+        old = sys.argv
+        sys.argv = ["gen_dct64.py", tmp]
+        try:
+            g.main()
+        finally:
+            sys.argv = old
+        assert open(tmp).read() == open(path).read(), "run tools/gen_dct64.py and commit the result"

@@ -1,0 +1,155 @@
+"""GPU: the device-resident C-ABI (what bench.py and a multi-GPU caller use) -- slabs with exchanged
+statistics must reproduce the single-field result bit for bit; size-independent properties at a
+BASELINE-sized field."""
+import numpy as np
+import pytest
+import torch
+
+from dctz_b200 import DOUBLE, FLOAT, binding, fields, slabs
+from tests import parity, reflib
+
+pytestmark = pytest.mark.gpu
+
+
+def _info(t):
+    return binding.GpuInfo.from_buffer_copy(t.cpu().numpy().tobytes()).as_dict()
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def compress_slabs(ctx, x, eb, qt, world):
+    """Emulate `world` ranks on one GPU, one after the other (no inter-kernel waiting is involved)."""
+    code = DOUBLE if x.dtype == np.float64 else FLOAT
+    tdt = torch.float64 if code == DOUBLE else torch.float32
+    parts = slabs.partition(x.size, world)
+    s = torch.cuda.current_stream().cuda_stream
+    xs = [_dev(x[a:a + c]) if c else None for a, c in parts]
+    stats_all = torch.zeros(3 * world, dtype=torch.float64, device="cuda")
+    for r, (a, c) in enumerate(parts):
+        assert c > 0
+        ctx.stats_dev(xs[r].data_ptr(), c, code, stats_all[3 * r:].data_ptr(), s)
+    outs = []
+    for r, (a, c) in enumerate(parts):
+        nblk = (c + 63) // 64
+        o = dict(bins=torch.empty(c, dtype=torch.uint8, device="cuda"), dc=torch.empty(nblk, dtype=torch.float32, device="cuda"),
+                 ac=torch.empty(c, dtype=torch.float32, device="cuda"), qraw=torch.zeros(64, dtype=tdt, device="cuda"),
+                 qt=torch.zeros(64, dtype=tdt, device="cuda"), info=torch.zeros(binding.INFO_BYTES, dtype=torch.uint8, device="cuda"))
+        ctx.compress_dev(xs[r].data_ptr(), c, x.size, code, eb, qt, stats_all.data_ptr(), world, r == 0, o["bins"].data_ptr(),
+                         o["dc"].data_ptr(), o["ac"].data_ptr(), o["qraw"].data_ptr(), o["info"].data_ptr(), s)
+        outs.append(o)
+    return parts, xs, stats_all, outs, code
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("world", [2, 3])
+def test_slabs_reproduce_the_single_field_result_ec(ctx, dtype, world):
+    x = fields.small_cases(dtype)["tail32"]
+    x = np.concatenate([x, fields.small_cases(dtype)["heavy_outliers"] * 0.02 + 3]).astype(dtype)
+    eb = 1e-3
+    whole = ctx.compress_core(x, eb)
+    parts, xs, stats_all, outs, code = compress_slabs(ctx, x, eb, False, world)
+    torch.cuda.synchronize()
+    infos = [_info(o["info"]) for o in outs]
+    assert all(i["sf"] == whole["sf"] and i["status"] == 0 for i in infos)
+    bins = np.concatenate([o["bins"].cpu().numpy() for o in outs])
+    dc = np.concatenate([o["dc"].cpu().numpy() for o in outs])
+    ac = np.concatenate([o["ac"][: i["n_outliers"]].cpu().numpy() for o, i in zip(outs, infos)])
+    assert np.array_equal(bins, whole["bin_index"]) and np.array_equal(dc, whole["dc"]) and np.array_equal(ac, whole["ac"])
+    assert infos[0]["max_abs"] == whole["info"]["max_abs"] and infos[-1]["min_abs"] == whole["info"]["min_abs"]
+    assert abs(infos[0]["mean"] - whole["mean"]) <= 1e-6 * abs(whole["mean"]) + 1e-12
+    # decompress slab by slab: each slab starts at its own outlier offset
+    s = torch.cuda.current_stream().cuda_stream
+    tdt = torch.float64 if code == DOUBLE else torch.float32
+    rec = []
+    for (a, c), o in zip(parts, outs):
+        out = torch.empty(c, dtype=tdt, device="cuda")
+        ctx.decompress_dev(o["bins"].data_ptr(), o["dc"].data_ptr(), o["ac"].data_ptr(), 0, c, code, eb, whole["sf"], False, out.data_ptr(), s)
+        rec.append(out.cpu().numpy())
+    want = ctx.decompress_core(whole["bin_index"], whole["dc"], whole["ac"], x.size, dtype, eb, whole["sf"])
+    assert np.array_equal(np.concatenate(rec), want)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_single_slab_device_api_equals_host_api_qt(ctx, dtype):
+    x = (fields.small_cases(dtype)["heavy_outliers"] * 0.05 + 2).astype(dtype)
+    eb = 1e-3
+    whole = ctx.compress_core(x, eb, qt=True)
+    code = DOUBLE if dtype == np.float64 else FLOAT
+    tdt = torch.float64 if code == DOUBLE else torch.float32
+    s = torch.cuda.current_stream().cuda_stream
+    d = _dev(x)
+    n = x.size
+    bins = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dc = torch.empty((n + 63) // 64, dtype=torch.float32, device="cuda")
+    ac = torch.empty(n, dtype=torch.float32, device="cuda")
+    q, qraw = torch.zeros(64, dtype=tdt, device="cuda"), torch.zeros(64, dtype=tdt, device="cuda")
+    info = torch.zeros(binding.INFO_BYTES, dtype=torch.uint8, device="cuda")
+    stats = torch.zeros(3, dtype=torch.float64, device="cuda")
+    ctx.stats_dev(d.data_ptr(), n, code, stats.data_ptr(), s)
+    ctx.compress_dev(d.data_ptr(), n, n, code, eb, True, stats.data_ptr(), 1, True, bins.data_ptr(), dc.data_ptr(), ac.data_ptr(),
+                     qraw.data_ptr(), info.data_ptr(), s)
+    qraw = slabs.all_reduce_qtable(qraw, 0, 1)  # where the NCCL max-reduction sits when there are several ranks
+    ctx.qt_finish_dev(code, eb, qraw.data_ptr(), q.data_ptr(), ac.data_ptr(), info.data_ptr(), s)
+    torch.cuda.synchronize()
+    i = _info(info)
+    assert np.array_equal(bins.cpu().numpy(), whole["bin_index"]) and np.array_equal(dc.cpu().numpy(), whole["dc"])
+    assert np.array_equal(ac[: i["n_outliers"]].cpu().numpy(), whole["ac"]) and np.array_equal(q.cpu().numpy(), whole["qtable"])
+    o = reflib.oracle_compress(x, eb, True)
+    # the table holds max |outlier| per position: the oracle's value up to the DCT tolerance
+    assert np.allclose(q.cpu().numpy()[1:], o["qtable"][1:], rtol=parity.RTOL[np.dtype(dtype)] * 8, atol=0)
+
+
+def test_hash_field_device_twin_is_bit_exact(ctx):
+    n = 1 << 20
+    for start in (0, 12345 * 64, (1 << 32) + 64 * 7):
+        d = torch.empty(n, dtype=torch.float64, device="cuda")
+        ctx.fill_hash_field(d.data_ptr(), start, n, 2048, fields.SEED, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy(), fields.hash_field(start, n, 2048, fields.SEED))
+
+
+def test_full_size_properties_nyx_like(ctx):
+    """config[3]-sized field (512^3 doubles, 1 GiB) generated on the device: round trip honours the bound
+    per coefficient, the outlier count is consistent, compress is deterministic (two runs, same bytes),
+    and a 2^20-element window agrees with the oracle."""
+    n = 1 << 27
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(7)
+    t = torch.arange(n, device="cuda", dtype=torch.float64)
+    x = torch.exp(1.5 * (0.6 * torch.sin(t / 97.0) * torch.cos(t / 1013.0) + 0.1 * torch.randn(n, generator=g, device="cuda", dtype=torch.float64)))
+    del t
+    eb = 1e-3
+    bufs = []
+    for _ in range(2):
+        bins = torch.empty(n, dtype=torch.uint8, device="cuda")
+        dc = torch.empty(n // 64, dtype=torch.float32, device="cuda")
+        ac = torch.empty(n, dtype=torch.float32, device="cuda")
+        info = torch.zeros(binding.INFO_BYTES, dtype=torch.uint8, device="cuda")
+        ctx.compress_field_dev(x.data_ptr(), n, DOUBLE, eb, False, bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), 0, 0, info.data_ptr(), s)
+        torch.cuda.synchronize()
+        bufs.append((bins, dc, ac, _info(info)))
+    (b0, d0, a0, i0), (b1, d1, a1, i1) = bufs
+    k = i0["n_outliers"]
+    assert i0 == i1 and torch.equal(b0, b1) and torch.equal(d0, d1) and torch.equal(a0[:k], a1[:k])
+    pos = torch.arange(n, device="cuda") % 64
+    assert int(((b0 == 255) & (pos != 0)).sum()) == k and bool(torch.all(b0[::64] == 255))
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    ctx.decompress_dev(b0.data_ptr(), d0.data_ptr(), a0.data_ptr(), 0, n, DOUBLE, eb, i0["sf"], False, out.data_ptr(), s)
+    torch.cuda.synchronize()
+    err = ((out - x).abs().max() / i0["sf"]).item()
+    assert err <= eb * (1 + 63 * np.sqrt(2)) / 8 * 1.01
+    # a window against the oracle (same sf because the window is compressed with the field's statistics? no:
+    # the oracle computes its own; pick the window holding the global maximum so that sf agrees)
+    w0 = (int(torch.argmax(x.abs()).item()) // (1 << 20)) * (1 << 20)
+    xw = x[w0:w0 + (1 << 20)].cpu().numpy()
+    o = reflib.oracle_compress(xw, eb, False)
+    assert o["stat"]["sf"] == i0["sf"]
+    gb = b0[w0:w0 + (1 << 20)].cpu().numpy()
+    diff = np.nonzero(gb != o["bin_index"])[0]
+    if diff.size:
+        dist = parity.boundary_distance(o["coef"][diff], eb, np.float64)
+        assert np.all(dist <= 1e-12 * np.maximum(parity.block_max(o["coef"])[diff], 1e-300))
+    assert np.array_equal(d0[w0 // 64:(w0 + (1 << 20)) // 64].cpu().numpy(), o["dc"]) or np.allclose(
+        d0[w0 // 64:(w0 + (1 << 20)) // 64].cpu().numpy(), o["dc"], rtol=2e-7)
