@@ -44,7 +44,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["c5-slab", "c1", "c2", "c3", "c4"], default="c5-slab")
@@ -223,7 +223,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 

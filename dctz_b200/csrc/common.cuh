@@ -129,20 +129,32 @@ __host__ __device__ __forceinline__ int center_multiple(unsigned id) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp tiles and TMA bulk copies.  The hot kernels are WARP-AUTONOMOUS: each warp owns a tile of
-// 32 consecutive 64-element blocks (one block per lane) and its own slice of shared memory, and
-// never meets the other warps of its CTA at a barrier.  A lane's block (one row of the tile) moves
-// global <-> shared with ONE bulk-copy instruction (cp.async.bulk, SASS UBLKCP): the row is
-// contiguous in global memory and is placed at a row stride of ROW_BYTES + 16 in shared memory, so
-// that the later one-row-per-lane 128-bit shared accesses are bank-conflict free (the 16-byte bank
-// group of chunk c of row r is (r + c) mod 8).  Loads complete on a per-warp mbarrier.
+// Warp tiles and TMA.  The hot kernels are WARP-AUTONOMOUS: each warp owns a tile of 32 consecutive
+// 64-element blocks (one block per lane) and its own slice of shared memory, and never meets the
+// other warps of its CTA at a barrier.
+//
+// A tile moves global <-> shared with TMA TENSOR copies (cp.async.bulk.tensor.2d, SASS UTMALDG /
+// UTMASTG) issued by one lane.  The field is described to the TMA unit as a 2-D byte tensor
+// [blocks][64*sizeof(T)]; a tile is fetched as SLABS of [32 blocks][128 bytes] with the 128-byte
+// swizzle, i.e. slab q holds bytes [128q, 128q+128) of each of the 32 rows, row r at offset 128 r,
+// its 16-byte chunk c stored at chunk position c ^ (r & 7).  A lane reading chunk c of "its" row r
+// therefore hits bank group c ^ (r & 7): the 8 lanes of a quarter-warp touch 8 different bank
+// groups -- conflict-free 128-bit shared loads with compile-time register indices.  Rows beyond the
+// end of the field are zero-filled on load and clipped on store by the TMA unit, so partial tiles
+// need no special path.  (Per-lane cp.async.bulk row copies were tried first: UBLKCP takes uniform
+// operands, so the compiler serialises them into a 32-trip loop, ~10% of the kernel's instructions.)
 // ------------------------------------------------------------------------------------------
 constexpr int WTILE = 32;  // blocks per warp tile (one per lane)
 template <typename T> struct WarpTile {
   static constexpr int ROW_BYTES = BLK * (int)sizeof(T);
-  static constexpr int ROW_STRIDE = ROW_BYTES + 16;
-  static constexpr int CH = ROW_BYTES / 16;
-  static constexpr int BYTES = WTILE * ROW_STRIDE;
+  static constexpr int SLABS = ROW_BYTES / 128;     // 4 (double) or 2 (float)
+  static constexpr int SLAB_BYTES = WTILE * 128;    // 4 KB
+  static constexpr int BYTES = SLABS * SLAB_BYTES;  // 16 KB / 8 KB, must sit at a 1024-byte aligned address
+  static constexpr int PER_CHUNK = 16 / (int)sizeof(T);
+  // byte offset of 16-byte chunk `c` (0..7) of slab `q` of row (lane) `r`
+  static __device__ __forceinline__ unsigned chunk_offset(int q, int r, int c) {
+    return (unsigned)(q * SLAB_BYTES + r * 128 + ((c ^ (r & 7)) << 4));
+  }
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -174,6 +186,16 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
 // shared -> global, tracked by the thread's bulk async-group
 __device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+// TMA tensor copies: 2-D box {128 bytes, 32 rows} at byte column c0, row c1 of the tensor map
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int c0, int c1, unsigned mb) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(mb)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int c0, int c1, unsigned src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tmap), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }

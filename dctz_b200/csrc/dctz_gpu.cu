@@ -6,6 +6,7 @@
 // dctz_compress()/dctz_decompress() call at the seam described in include/dctz_gpu.h.
 //
 // There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -299,6 +300,36 @@ extern "C" double dctz_gpu_sf_from_max(const dctz_gpu_ctx *ctx, double max_abs, 
 }
 
 // ------------------------------------------------------------------------------------------
+// TMA tensor maps.  A field (or slab) of nblk full blocks is described as a 2-D byte tensor
+// [nblk rows][64*sizeof(T) bytes]; the kernels move [32 rows x 128 bytes] boxes with the 128-byte
+// swizzle (common.cuh, WarpTile).  The encoder lives in the driver: fetched once through the runtime,
+// so the library does not link libcuda.
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int make_tile_map(dctz_gpu_ctx *ctx, CUtensorMap *map, const void *base, size_t row_bytes, unsigned long long nrows) {
+  if (!g_encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+      return fail(ctx, DCTZ_GPU_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    g_encode = (EncodeTiledFn)fn;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)nrows};
+  const cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  const cuuint32_t box[2] = {128u, (cuuint32_t)WTILE};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, DCTZ_GPU_ECUDA, "cuTensorMapEncodeTiled failed with %d (base %p, %llu rows)", (int)r, base, nrows);
+  return DCTZ_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // argument checks shared by the entry points
 // ------------------------------------------------------------------------------------------
 static int check_common(dctz_gpu_ctx *ctx, int datatype, double eb) {
@@ -416,7 +447,9 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     const size_t resident = (size_t)ctx->sm_count * ctx->occ[0][sizeof(T) == 8][QT];
     const size_t ctas = (ntiles + Cfg::WARPS - 1) / Cfg::WARPS;
     const int grid = (int)(ctas < resident ? ctas : resident);
-    k_compress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_in, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts, ac_slots, raw,
+    CUtensorMap tmap;
+    TRY(make_tile_map(ctx, &tmap, d_in, BLK * sizeof(T), nblk_full));
+    k_compress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts, ac_slots, raw,
                                                              jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0], d_info);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -545,7 +578,9 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
     const size_t resident = (size_t)ctx->sm_count * ctx->occ[1][sizeof(T) == 8][QT];
     const size_t ctas = (ntiles + Cfg::WARPS - 1) / Cfg::WARPS;
     const int grid = (int)(ctas < resident ? ctas : resident);
-    k_decompress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, d_out, sb.counts,
+    CUtensorMap tmap;
+    TRY(make_tile_map(ctx, &tmap, d_out, BLK * sizeof(T), nblk_full));
+    k_decompress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, tmap, sb.counts,
                                                                sb.out.group_prefix, sb.out.chunk_prefix, &ctx->d_ctl[1]);
     ctx->launches++;
     CU(cudaGetLastError());

@@ -18,6 +18,7 @@
 // phase.  There is no CTA-wide barrier inside the main loops; the ordered outlier offsets come from
 // a single-pass decoupled look-back scan over the warp tiles.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched from the driver at run time)
 #include <type_traits>
 #include "common.cuh"
 #include "dct64_gen.cuh"
@@ -375,13 +376,13 @@ template <typename T, bool QT> struct CompressCfg {
   static constexpr int CAP = QT ? 0 : 63 * WTILE;
   static constexpr int OFF_STAGE = WarpTile<T>::BYTES;
   static constexpr int OFF_BINS = OFF_STAGE + CAP * 4;
-  static constexpr int WARP_BYTES = ((OFF_BINS + WTILE * BLK + 127) / 128) * 128;
-  static constexpr int SMEM = WARPS * WARP_BYTES;
+  static constexpr int WARP_BYTES = ((OFF_BINS + WTILE * BLK + 1023) / 1024) * 1024;  // tiles need 1 KB alignment (swizzle atom)
+  static constexpr int SMEM = WARPS * WARP_BYTES + 1024;                             // + slack to align the base
 };
 
 template <typename T, bool QT>
 __global__ void __launch_bounds__(CompressCfg<T, QT>::THREADS, CompressCfg<T, QT>::CTAS_PER_SM)
-k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevParams *__restrict__ params,
+k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_full, const DevParams *__restrict__ params,
            QuantConsts<T> qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
            unsigned *__restrict__ counts,                     // outliers per warp tile
            float *__restrict__ ac_slots,                      // EC: tile-strided outlier scratch (TILE_SLOT per tile)
@@ -394,11 +395,12 @@ k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevPara
   typedef WarpTile<T> L;
   typedef typename BitsOf<T>::U U;
   constexpr unsigned FULL = 0xFFFFFFFFu;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
   __shared__ U s_qmax[QT ? BLK : 1];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char *wsm = smem + warp * Cfg::WARP_BYTES;
   const unsigned tile_s = smem_u32(wsm);
   float *stage = reinterpret_cast<float *>(wsm + Cfg::OFF_STAGE);
@@ -418,12 +420,12 @@ k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevPara
     const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
     return left < (unsigned long long)WTILE ? (unsigned)left : (unsigned)WTILE;
   };
-  auto issue_tile = [&](unsigned t) {
-    const unsigned rows = rows_of(t);
-    if (lane == 0) mbar_expect_tx(mb, rows * L::ROW_BYTES);
-    __syncwarp();
-    if ((unsigned)lane < rows)
-      bulk_g2s(tile_s + lane * L::ROW_STRIDE, in + ((unsigned long long)t * WTILE + lane) * BLK, L::ROW_BYTES, mb);
+  auto issue_tile = [&](unsigned t) {  // one lane: 4 (double) / 2 (float) tensor copies of a [32 rows x 128 B] slab each
+    if (lane == 0) {
+      mbar_expect_tx(mb, L::BYTES);  // rows beyond the field are zero-filled and still counted
+#pragma unroll
+      for (int q = 0; q < L::SLABS; q++) tma_load_2d(tile_s + q * L::SLAB_BYTES, &tmap_in, q * 128, (int)(t * WTILE), mb);
+    }
   };
   auto take_ticket = [&]() -> unsigned {
     unsigned t = 0;
@@ -445,14 +447,14 @@ k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevPara
     mbar_wait(mb, phase);
     phase ^= 1u;
     T x[BLK];
-    {
-      const unsigned char *row = wsm + lane * L::ROW_STRIDE;
 #pragma unroll
-      for (int c = 0; c < L::CH; c++) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(row + 16 * c);
+    for (int q = 0; q < L::SLABS; q++) {
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(wsm + L::chunk_offset(q, lane, c));
         const T *e = reinterpret_cast<const T *>(&v);
 #pragma unroll
-        for (int k = 0; k < 16 / (int)sizeof(T); k++) x[c * (16 / (int)sizeof(T)) + k] = e[k];
+        for (int k = 0; k < L::PER_CHUNK; k++) x[(q * 8 + c) * L::PER_CHUNK + k] = e[k];
       }
     }
     __syncwarp();                        // every lane holds its row in registers
@@ -462,28 +464,39 @@ k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevPara
     const unsigned rows = rows_of(cur);
     const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
     const bool active = (unsigned)lane < rows;
-    if (!active) {
-#pragma unroll
-      for (int j = 0; j < BLK; j++) x[j] = (T)0;
-    }
+    // (rows beyond the field arrive zero-filled: they quantise to bin 0 and are never stored)
 
     // ---- scale (float: x / sf before the transform; double: folded into the quantiser) ----
     qz.pre_scale(x);
     // ---- orthonormal DCT-II (dct.c:55-103) ----
     dct64_forward<A>(x);
 
-    // ---- quantise (dctz-comp-lib.c:350-414) ----
-    unsigned w[16];
-#pragma unroll
-    for (int q = 0; q < 16; q++) w[q] = 0;
-    w[0] = 255u;  // bin_index[i*64] = NBINS, :361
+    // ---- quantise (dctz-comp-lib.c:350-414); the ids go straight to the warp's bin-id buffer in shared
+    //      memory (four at a time), which keeps 16 registers free and is where the bulk store reads them ----
+    if (lane == 0) bulk_wait_read();  // the previous tile's bin ids have left shared memory
+    __syncwarp();
+    uint4 *brow = reinterpret_cast<uint4 *>(binbuf + lane * BLK);
+    unsigned cnt = 0;
     qz.begin_block();
 #pragma unroll
-    for (int j = 1; j < BLK; j++) {
-      unsigned id;
-      if constexpr (sizeof(T) == 8) id = qz.quantize(x[j]);
-      else id = quantize_f(x[j], qc);
-      w[j >> 2] |= id << (8 * (j & 3));
+    for (int q4 = 0; q4 < 4; q4++) {
+      unsigned wq[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        unsigned word = (q4 == 0 && k == 0) ? 255u : 0u;  // bin_index[i*64] = NBINS, :361
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const int j = 16 * q4 + 4 * k + b;
+          if (j == 0) continue;
+          unsigned id;
+          if constexpr (sizeof(T) == 8) id = qz.quantize(x[j]);
+          else id = quantize_f(x[j], qc);
+          word |= id << (8 * b);
+        }
+        cnt += __popc(ff_bytes(word));
+        wq[k] = word;
+      }
+      brow[q4] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
     }
     if constexpr (sizeof(T) == 8) {
       if (qz.needs_exact()) {  // rare (~5e-4 of blocks): redo this block through the exact expression
@@ -492,14 +505,15 @@ k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevPara
 #pragma unroll
         for (int j = 0; j < BLK; j++) xl[j] = x[j];
         quantize_block_exact(xl, qz.sfdiv.b, qz.sfdiv.y, qz.sfdiv.iters, qc.rmin, qc.rmax, qc.bw, wl, &edge);
-#pragma unroll
-        for (int q = 0; q < 16; q++) w[q] = wl[q];
+        cnt = 0;
+#pragma unroll 1
+        for (int q4 = 0; q4 < 4; q4++) {
+          brow[q4] = make_uint4(wl[4 * q4], wl[4 * q4 + 1], wl[4 * q4 + 2], wl[4 * q4 + 3]);
+          cnt += __popc(ff_bytes(wl[4 * q4])) + __popc(ff_bytes(wl[4 * q4 + 1])) + __popc(ff_bytes(wl[4 * q4 + 2])) + __popc(ff_bytes(wl[4 * q4 + 3]));
+        }
         nexact++;
       }
     }
-    unsigned cnt = 0;
-#pragma unroll
-    for (int q = 0; q < 16; q++) cnt += __popc(ff_bytes(w[q]));
     cnt -= 1;  // the DC marker
     if (!active) cnt = 0;
 
@@ -508,14 +522,7 @@ k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevPara
     const unsigned my_off = incl - cnt;
     if (lane == 0) counts[cur] = tile_total;
 
-    // ---- bin ids (via shared memory, one bulk store per tile) and DC ----
-    if (lane == 0) bulk_wait_read();  // the previous tile's bin ids have left shared memory
-    __syncwarp();
-    {
-      uint4 *bp = reinterpret_cast<uint4 *>(binbuf + lane * BLK);
-#pragma unroll
-      for (int q = 0; q < 4; q++) bp[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-    }
+    // ---- bin ids: one bulk store per tile; DC ----
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -532,9 +539,10 @@ k_compress(const T *__restrict__ in, unsigned long long nblk_full, const DevPara
     if (tile_total != 0) {
       const unsigned long long slot = (unsigned long long)cur * TILE_SLOT;
       unsigned pos = my_off;
+      const unsigned *wrow = reinterpret_cast<const unsigned *>(binbuf + lane * BLK);
 #pragma unroll
       for (int q = 0; q < 16; q++) {
-        unsigned m = ff_bytes(w[q]);
+        unsigned m = ff_bytes(wrow[q]);
         if (q == 0) m &= ~1u;  // the DC marker is not an outlier
         if (m) {
 #pragma unroll
@@ -935,9 +943,9 @@ template <typename T, bool QT> struct DecompressCfg {
   static constexpr int CTAS_PER_SM = (sizeof(T) == 8) ? 2 : 3;
   static constexpr int OFF_BINS = WarpTile<T>::BYTES;          // >= 63*32 floats of outlier stage
   static constexpr int OFF_DC = OFF_BINS + WTILE * BLK;
-  static constexpr int WARP_BYTES = ((OFF_DC + WTILE * 4 + 127) / 128) * 128;
-  static constexpr int OFF_WARPS = 256 * (int)sizeof(T);
-  static constexpr int SMEM = OFF_WARPS + WARPS * WARP_BYTES;
+  static constexpr int WARP_BYTES = ((OFF_DC + WTILE * 4 + 1023) / 1024) * 1024;  // tiles need 1 KB alignment (swizzle atom)
+  static constexpr int OFF_WARPS = 2048;                                         // centre table: 256 T
+  static constexpr int SMEM = OFF_WARPS + WARPS * WARP_BYTES + 1024;             // + slack to align the base
   static_assert(WarpTile<T>::BYTES >= 63 * WTILE * 4, "the tile must hold a full tile of outliers");
 };
 
@@ -960,18 +968,19 @@ template <typename T, bool QT>
 __global__ void __launch_bounds__(DecompressCfg<T, QT>::THREADS, DecompressCfg<T, QT>::CTAS_PER_SM)
 k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, const float *__restrict__ ac_in,
              const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
-             T *__restrict__ out, const unsigned *__restrict__ counts,
+             const __grid_constant__ CUtensorMap tmap_out, const unsigned *__restrict__ counts,
              const unsigned long long *__restrict__ group_prefix, const unsigned long long *__restrict__ chunk_prefix,
              TileControl *ctl) {
   typedef typename ArithOf<T>::type A;
   typedef DecompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
   constexpr unsigned FULL = 0xFFFFFFFFu;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
   __shared__ T s_qt[QT ? BLK : 1];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   T *center = reinterpret_cast<T *>(smem);
   unsigned char *wsm = smem + Cfg::OFF_WARPS + warp * Cfg::WARP_BYTES;
   float *stage = reinterpret_cast<float *>(wsm);  // aliases the tile rows; dead before they are written
@@ -1052,7 +1061,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
       for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
       tile_base += e;
     }
-    bulk_wait_read();  // this lane's previous output row has left shared memory (it aliases the stage)
+    if (lane == 0) bulk_wait_read();  // the previous tile's output has left shared memory (it aliases the stage)
     __syncwarp();
 
     // ---- stage this tile's outliers (coalesced) ----
@@ -1092,19 +1101,23 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     // ---- orthonormal DCT-III (dct.c:115-205) ----
     dct64_inverse<A>(x);
 
-    // ---- registers -> own padded row -> one bulk store per lane ----
-    {
-      unsigned char *row = wsm + lane * L::ROW_STRIDE;
+    // ---- registers -> own row of the swizzled tile -> TMA tensor stores (rows beyond the field are clipped) ----
 #pragma unroll
-      for (int c = 0; c < L::CH; c++) {
+    for (int q = 0; q < L::SLABS; q++) {
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
         uint4 v;
         T *e = reinterpret_cast<T *>(&v);
 #pragma unroll
-        for (int k = 0; k < 16 / (int)sizeof(T); k++) e[k] = x[c * (16 / (int)sizeof(T)) + k];
-        *reinterpret_cast<uint4 *>(row + 16 * c) = v;
+        for (int k = 0; k < L::PER_CHUNK; k++) e[k] = x[(q * 8 + c) * L::PER_CHUNK + k];
+        *reinterpret_cast<uint4 *>(wsm + L::chunk_offset(q, lane, c)) = v;
       }
-      fence_async_smem();
-      if (active) bulk_s2g(out + blk * BLK, smem_u32(row), L::ROW_BYTES);
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < L::SLABS; q++) tma_store_2d(&tmap_out, q * 128, (int)(cur * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES);
       bulk_commit();
     }
     cur = nxt;
