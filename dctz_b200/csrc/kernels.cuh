@@ -307,6 +307,9 @@ template <> struct Quantizer<double> {
   }
   __device__ __forceinline__ void pre_scale(double (&)[BLK]) const {}
   __device__ __forceinline__ double scaled(double c_u) const { return div_exact(c_u, sfdiv); }
+  // outliers are stored as float (USE_TRUNCATE): c_u * RN(1/sf) differs from c_u / sf by at most one double ulp,
+  // i.e. the float it rounds to differs with probability ~2^-29 -- one multiply instead of the division sequence
+  __device__ __forceinline__ float outlier(double c_u) const { return (float)__dmul_rn(c_u, sfdiv.y); }
   __device__ __forceinline__ void begin_block() { allok = 1u; }
   __device__ __forceinline__ unsigned quantize(double c_u) {
     const double v = __fma_rn(c_u, kq, 127.5);
@@ -334,6 +337,7 @@ template <> struct Quantizer<float> {
     }
   }
   __device__ __forceinline__ float scaled(float c) const { return c; }
+  __device__ __forceinline__ float outlier(float c) const { return c; }
   __device__ __forceinline__ void begin_block() {}
   __device__ __forceinline__ bool needs_exact() const { return false; }
 };
@@ -365,17 +369,13 @@ __device__ __noinline__ void quantize_block_exact(const double *xl, double sf_b,
 
 // ------------------------------------------------------------------------------------------
 // K2: fused scale + DCT-II + quantise + ordered outlier compaction.
-// Shared memory per warp: [ tile: 32 padded rows ][ EC: outlier stage, 2016 floats ][ bin ids 2 KB ]
+// Shared memory per warp: [ tile: 4 (2) swizzled slabs ][ bin ids 2 KB ]
 // ------------------------------------------------------------------------------------------
 template <typename T, bool QT> struct CompressCfg {
   static constexpr int WARPS = 4;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int CTAS_PER_SM = (sizeof(T) == 8) ? 2 : 3;
-  // EC stages a tile's outliers (worst case 63 per block) for coalesced stores; QT writes its raw
-  // outliers straight to scratch (they are re-read by K2b anyway)
-  static constexpr int CAP = QT ? 0 : 63 * WTILE;
-  static constexpr int OFF_STAGE = WarpTile<T>::BYTES;
-  static constexpr int OFF_BINS = OFF_STAGE + CAP * 4;
+  static constexpr int OFF_BINS = WarpTile<T>::BYTES;
   static constexpr int WARP_BYTES = ((OFF_BINS + WTILE * BLK + 1023) / 1024) * 1024;  // tiles need 1 KB alignment (swizzle atom)
   static constexpr int SMEM = WARPS * WARP_BYTES + 1024;                             // + slack to align the base
 };
@@ -385,8 +385,9 @@ __global__ void __launch_bounds__(CompressCfg<T, QT>::THREADS, CompressCfg<T, QT
 k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_full, const DevParams *__restrict__ params,
            QuantConsts<T> qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
            unsigned *__restrict__ counts,                     // outliers per warp tile
-           float *__restrict__ ac_slots,                      // EC: tile-strided outlier scratch (TILE_SLOT per tile)
-           T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, tile-strided
+           uint8_t *__restrict__ blk_counts,                  // outliers per block (32 per tile slot)
+           float *__restrict__ ac_slots,                      // EC: outlier scratch, TILE_SLOT per tile, LANE_SLOT per block
+           T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
            typename BitsOf<T>::U *__restrict__ qmax_bits,     // QT: 64 per-position maxima (bit patterns)
            T *__restrict__ qtable0,                           // QT: receives the last full block's DC
            TileControl *ctl, Info *info) {
@@ -403,7 +404,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
   unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char *wsm = smem + warp * Cfg::WARP_BYTES;
   const unsigned tile_s = smem_u32(wsm);
-  float *stage = reinterpret_cast<float *>(wsm + Cfg::OFF_STAGE);
   unsigned char *binbuf = wsm + Cfg::OFF_BINS;
   const unsigned mb = smem_u32(&s_mbar[warp]);
   const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
@@ -517,10 +517,11 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     cnt -= 1;  // the DC marker
     if (!active) cnt = 0;
 
-    const unsigned incl = warp_inclusive_scan(cnt, lane);
-    const unsigned tile_total = __shfl_sync(FULL, incl, 31);
-    const unsigned my_off = incl - cnt;
+    unsigned tile_total = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tile_total += __shfl_xor_sync(FULL, tile_total, o);
     if (lane == 0) counts[cur] = tile_total;
+    blk_counts[(unsigned long long)cur * WTILE + lane] = (uint8_t)cnt;
 
     // ---- bin ids: one bulk store per tile; DC ----
     fence_async_smem();
@@ -535,11 +536,12 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
       if (QT && blk == nblk_full - 1) *qtable0 = dcs;  // :357/:359 (a later tail block overwrites it)
     }
 
-    // ---- outliers of this tile, in (block, j) order, to the tile's scratch slot (dctz-comp-lib.c:478-544) ----
+    // ---- outliers (dctz-comp-lib.c:478-544): each lane appends its block's outliers, in ascending j, to the
+    //      block's own run of the tile slot, straight from registers; k_gather_* puts the runs in order ----
     if (tile_total != 0) {
-      const unsigned long long slot = (unsigned long long)cur * TILE_SLOT;
-      unsigned pos = my_off;
+      const unsigned long long run = (unsigned long long)cur * TILE_SLOT + (unsigned)lane * LANE_SLOT;
       const unsigned *wrow = reinterpret_cast<const unsigned *>(binbuf + lane * BLK);
+      unsigned pos = 0;
 #pragma unroll
       for (int q = 0; q < 16; q++) {
         unsigned m = ff_bytes(wrow[q]);
@@ -549,23 +551,18 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
           for (int b = 0; b < 4; b++) {
             const int j = 4 * q + b;
             if (j >= 1 && (m & (1u << (8 * b)))) {
-              const T c = qz.scaled(x[j]);
               if (QT) {  // raw coefficient + position, rescaled by K2b once the global qtable is known
-                raw_slots[slot + pos] = c;
-                j_slots[slot + pos] = (uint8_t)j;
+                const T c = qz.scaled(x[j]);
+                raw_slots[run + pos] = c;
+                j_slots[run + pos] = (uint8_t)j;
                 atomicMax(&s_qmax[j], BitsOf<T>::abs_bits(c));  // :371-372, 396-397
               } else {
-                stage[pos] = (float)c;  // :537 (USE_TRUNCATE)
+                ac_slots[run + pos] = qz.outlier(x[j]);  // :537 (USE_TRUNCATE)
               }
               pos++;
             }
           }
         }
-      }
-      if (!QT) {
-        __syncwarp();
-        for (unsigned i = lane; i < tile_total; i += 32) ac_slots[slot + i] = stage[i];
-        __syncwarp();
       }
     }
     cur = nxt;
@@ -644,9 +641,9 @@ template <typename T, bool QT>
 __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /* start of the tail block */, int rem,
                                                       unsigned long long blk_index, unsigned slot_tile,
                                                       const DevParams *params, QuantConsts<T> qc, uint8_t *bins,
-                                                      float *dc_out, unsigned *counts, float *ac_slots, T *raw_slots,
-                                                      uint8_t *j_slots, typename BitsOf<T>::U *qmax_bits, T *qtable0,
-                                                      Info *info) {
+                                                      float *dc_out, unsigned *counts, uint8_t *blk_counts, float *ac_slots,
+                                                      T *raw_slots, uint8_t *j_slots, typename BitsOf<T>::U *qmax_bits,
+                                                      T *qtable0, Info *info) {
   __shared__ double xs[BLK];
   const int lane = threadIdx.x;
   const T sf = (sizeof(T) == 8) ? (T)params->sf_d : (T)params->sf_f;
@@ -691,6 +688,7 @@ __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /
   }
   edge = (unsigned)warp_sum((double)edge);
   if (lane == 0) { counts[slot_tile] = base; if (edge) info->n_edge += edge; }
+  blk_counts[(unsigned long long)slot_tile * WTILE + lane] = (uint8_t)(lane == 0 ? base : 0u);  // the block is run 0 of its slot
 }
 
 // ------------------------------------------------------------------------------------------
@@ -779,38 +777,35 @@ __global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *__restrict
   if (threadIdx.x == 0) { *total = carry; *out.done = 0u; }
 }
 
-// Shared by the gather kernels: a warp owns one group; every lane learns the exclusive prefix of
-// "its" tile inside the group and the group's size.  Output position r of the group belongs to the
-// tile k with excl[k] <= r < excl[k+1], found by a 5-step binary search over the lanes' values.
-__device__ __forceinline__ unsigned group_tile_of(unsigned r, unsigned my_excl) {
-  int k = 0;
+// Gather: one warp per tile.  Lane l holds the count of block l of the tile; run l of the slot holds that
+// block's outliers.  The runs are copied, in block order, to the tile's final position
+// prefix_of_group + (totals of the earlier tiles of the group).
+__device__ __forceinline__ unsigned long long tile_base_of(const unsigned *__restrict__ counts,
+                                                           const unsigned long long *__restrict__ group_prefix,
+                                                           const unsigned long long *__restrict__ chunk_prefix, unsigned tile, int lane) {
+  unsigned e = ((unsigned)lane < (tile & 31u)) ? __ldg(counts + (tile & ~31u) + lane) : 0u;
 #pragma unroll
-  for (int step = 16; step > 0; step >>= 1) {
-    const unsigned e = __shfl_sync(0xFFFFFFFFu, my_excl, k + step);
-    if (e <= r) k += step;
-  }
-  return (unsigned)k;
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+  return prefix_of_group(group_prefix, chunk_prefix, tile >> 5) + e;
 }
 
-// EC: move the tile-strided runs to their final, contiguous place.
-__global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
-                                                   const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles, const float *__restrict__ ac_slots, float *__restrict__ ac_out) {
+__global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ counts, const uint8_t *__restrict__ blk_counts,
+                                                   const unsigned long long *__restrict__ group_prefix,
+                                                   const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles,
+                                                   const float *__restrict__ ac_slots, float *__restrict__ ac_out) {
   const int lane = threadIdx.x & 31;
-  const unsigned ngroups = (ntiles + 31u) / 32u;
   const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
-  for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngroups; g += wpg) {
-    const unsigned t = g * 32u + lane;
-    const unsigned c = (t < ntiles) ? __ldg(counts + t) : 0u;
-    const unsigned incl = warp_inclusive_scan(c, lane);
-    const unsigned gsize = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (gsize == 0) continue;
-    const unsigned my_excl = incl - c;
-    const unsigned long long gp = prefix_of_group(group_prefix, chunk_prefix, g);
-    for (unsigned r0 = 0; r0 < gsize; r0 += 32) {
-      const unsigned r = r0 + lane;
-      const unsigned k = group_tile_of(r < gsize ? r : gsize - 1, my_excl);  // all lanes take part in the shuffles
-      const unsigned ek = __shfl_sync(0xFFFFFFFFu, my_excl, k);
-      if (r < gsize) ac_out[gp + r] = __ldg(ac_slots + (unsigned long long)(g * 32u + k) * TILE_SLOT + (r - ek));
+  for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += wpg) {
+    if (__ldg(counts + t) == 0) continue;
+    const unsigned c = __ldg(blk_counts + (unsigned long long)t * WTILE + lane);
+    const unsigned excl = warp_inclusive_scan(c, lane) - c;
+    float *dst = ac_out + tile_base_of(counts, group_prefix, chunk_prefix, t, lane);
+    const float *src = ac_slots + (unsigned long long)t * TILE_SLOT;
+#pragma unroll 8
+    for (int s = 0; s < WTILE; s++) {
+      const unsigned n = __shfl_sync(0xFFFFFFFFu, c, s), off = __shfl_sync(0xFFFFFFFFu, excl, s);
+      if ((unsigned)lane < n) dst[off + lane] = __ldg(src + s * LANE_SLOT + lane);
+      if ((unsigned)lane + 32u < n) dst[off + lane + 32] = __ldg(src + s * LANE_SLOT + lane + 32);
     }
   }
 }
@@ -844,8 +839,10 @@ __device__ __forceinline__ bool qt_rescale_one(float item, float q, const QtCons
 
 // QT gather: rescale while moving to the final place.
 template <typename T>
-__global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
-                                                   const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles, const T *__restrict__ raw_slots, const uint8_t *__restrict__ j_slots,
+__global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ counts, const uint8_t *__restrict__ blk_counts,
+                                                   const unsigned long long *__restrict__ group_prefix,
+                                                   const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles,
+                                                   const T *__restrict__ raw_slots, const uint8_t *__restrict__ j_slots,
                                                    const T *__restrict__ qraw /* global maxima, [0] = last DC */,
                                                    T *__restrict__ qtable_out, QtConsts<T> k, float *__restrict__ ac_out, Info *info) {
   __shared__ T qt[BLK];
@@ -857,27 +854,21 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const unsigned ngroups = (ntiles + 31u) / 32u;
   const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
   unsigned dropped = 0;
-  for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < ngroups; g += wpg) {
-    const unsigned t = g * 32u + lane;
-    const unsigned c = (t < ntiles) ? __ldg(counts + t) : 0u;
-    const unsigned incl = warp_inclusive_scan(c, lane);
-    const unsigned gsize = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (gsize == 0) continue;
-    const unsigned my_excl = incl - c;
-    const unsigned long long gp = prefix_of_group(group_prefix, chunk_prefix, g);
-    for (unsigned r0 = 0; r0 < gsize; r0 += 32) {
-      const unsigned r = r0 + lane;
-      const unsigned kt = group_tile_of(r < gsize ? r : gsize - 1, my_excl);
-      const unsigned ek = __shfl_sync(0xFFFFFFFFu, my_excl, kt);
-      if (r < gsize) {
-        const unsigned long long src = (unsigned long long)(g * 32u + kt) * TILE_SLOT + (r - ek);
+  for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += wpg) {
+    if (__ldg(counts + t) == 0) continue;
+    const unsigned c = __ldg(blk_counts + (unsigned long long)t * WTILE + lane);
+    const unsigned excl = warp_inclusive_scan(c, lane) - c;
+    float *dst = ac_out + tile_base_of(counts, group_prefix, chunk_prefix, t, lane);
+    const unsigned long long src = (unsigned long long)t * TILE_SLOT;
+    for (int s = 0; s < WTILE; s++) {
+      const unsigned n = __shfl_sync(0xFFFFFFFFu, c, s), off = __shfl_sync(0xFFFFFFFFu, excl, s);
+      for (unsigned i = lane; i < n; i += 32) {
+        const unsigned long long e = src + s * LANE_SLOT + i;
         float o;
-        const bool keep = qt_rescale_one(raw_slots[src], qt[j_slots[src]], k, &o);
-        ac_out[gp + r] = o;
-        if (!keep) dropped++;
+        if (!qt_rescale_one(raw_slots[e], qt[j_slots[e]], k, &o)) dropped++;
+        dst[off + i] = o;
       }
     }
   }
@@ -888,19 +879,19 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
 // (dctz-comp-lib.c:494-506: such a value is not stored although its bin index stays 255).  It is a
 // no-op unless that ever happens (it cannot for realistic data).
 template <typename T>
-__global__ void __launch_bounds__(32) k_qt_compact(const unsigned *__restrict__ counts, unsigned ntiles, const T *__restrict__ raw_slots,
+__global__ void __launch_bounds__(32) k_qt_compact(const uint8_t *__restrict__ blk_counts, unsigned ntiles, const T *__restrict__ raw_slots,
                                                    const uint8_t *__restrict__ j_slots, const T *__restrict__ qraw, QtConsts<T> k,
                                                    float *ac_out, Info *info) {
   if (info->n_qt_dropped == 0) return;  // the only path ever taken in practice
   if (threadIdx.x != 0) return;
   unsigned long long w = 0;
-  for (unsigned t = 0; t < ntiles; t++) {
-    const unsigned long long slot = (unsigned long long)t * TILE_SLOT;
-    for (unsigned i = 0; i < counts[t]; i++) {
-      T q = qraw[j_slots[slot + i]];
-      if (j_slots[slot + i] >= 1 && q < (T)1.0) q = (T)1.0;
+  for (unsigned long long b = 0; b < (unsigned long long)ntiles * WTILE; b++) {
+    const unsigned long long run = (b / WTILE) * TILE_SLOT + (b % WTILE) * LANE_SLOT;
+    for (unsigned i = 0; i < blk_counts[b]; i++) {
+      T q = qraw[j_slots[run + i]];
+      if (j_slots[run + i] >= 1 && q < (T)1.0) q = (T)1.0;
       float o;
-      if (qt_rescale_one(raw_slots[slot + i], q, k, &o)) ac_out[w++] = o;
+      if (qt_rescale_one(raw_slots[run + i], q, k, &o)) ac_out[w++] = o;
     }
   }
   info->n_outliers = w;
@@ -1054,13 +1045,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     const unsigned tile_total = __shfl_sync(FULL, incl, 31);
     const unsigned my_off = incl - cnt;
     // offset of the tile's first outlier: scanned group prefix + the counts of the earlier tiles of the group
-    unsigned long long tile_base = prefix_of_group(group_prefix, chunk_prefix, cur >> 5);
-    {
-      unsigned e = ((unsigned)lane < (cur & 31u)) ? __ldg(counts + (cur & ~31u) + lane) : 0u;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(FULL, e, o);
-      tile_base += e;
-    }
+    const unsigned long long tile_base = tile_base_of(counts, group_prefix, chunk_prefix, cur, lane);
     if (lane == 0) bulk_wait_read();  // the previous tile's output has left shared memory (it aliases the stage)
     __syncwarp();
 
