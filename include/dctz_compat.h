@@ -72,6 +72,8 @@ void idct_finish_f(void);
  * DCTZ_GPU_DEVICE environment variable).  */
 int dctz_build_is_qt(void);
 void dctz_set_device(int device);
+/* deflate one stream section the way dctz_compress does (chunk-parallel above 2 MiB); returns the size or 0 */
+size_t dctz_host_deflate(const void *src, size_t n, void *dst, size_t cap);
 
 #ifdef __cplusplus
 }
