@@ -925,14 +925,20 @@ __global__ void __launch_bounds__(256) k_count_bins(const uint8_t *__restrict__ 
 
 // ------------------------------------------------------------------------------------------
 // K3: dequantise + DCT-III + de-scale (dctz-decomp-lib.c:389-511).
-// Shared memory: [ centre table 256 T ] + per warp [ tile: 32 padded rows; its first bytes double as
-// the outlier stage before the inverse transform ][ bin ids 2 KB ][ DC 128 B ]
+// Shared memory: [ centre table 256 T ] + per warp [ tile: swizzled slabs ][ double: outlier stage 8 KB;
+// float: the stage aliases the tile ][ bin ids 2 KB ][ DC 128 B ]
 // ------------------------------------------------------------------------------------------
 template <typename T, bool QT> struct DecompressCfg {
   static constexpr int WARPS = 4;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int CTAS_PER_SM = (sizeof(T) == 8) ? 2 : 3;
-  static constexpr int OFF_BINS = WarpTile<T>::BYTES;          // >= 63*32 floats of outlier stage
+  // double: registers limit residency to 2 CTAs/SM anyway, so each warp affords its own outlier stage and the
+  // next tile's outliers are PREFETCHED by TMA together with its bin ids.  float: the stage aliases the tile
+  // (dead until the inverse transform writes it) so that 3 CTAs/SM stay resident; outliers are loaded late.
+  static constexpr bool PREFETCH = (sizeof(T) == 8);
+  static constexpr int STAGE_BYTES = PREFETCH ? 8192 : 0;      // 16 B lead-in + 63*32 floats + alignment slack
+  static constexpr int OFF_STAGE = PREFETCH ? WarpTile<T>::BYTES : 0;
+  static constexpr int OFF_BINS = WarpTile<T>::BYTES + STAGE_BYTES;
   static constexpr int OFF_DC = OFF_BINS + WTILE * BLK;
   static constexpr int WARP_BYTES = ((OFF_DC + WTILE * 4 + 1023) / 1024) * 1024;  // tiles need 1 KB alignment (swizzle atom)
   static constexpr int OFF_WARPS = 2048;                                         // centre table: 256 T
@@ -974,7 +980,8 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   T *center = reinterpret_cast<T *>(smem);
   unsigned char *wsm = smem + Cfg::OFF_WARPS + warp * Cfg::WARP_BYTES;
-  float *stage = reinterpret_cast<float *>(wsm);  // aliases the tile rows; dead before they are written
+  constexpr bool PF = Cfg::PREFETCH;
+  float *stage = reinterpret_cast<float *>(wsm + Cfg::OFF_STAGE);
   unsigned char *binbuf = wsm + Cfg::OFF_BINS;
   float *dcbuf = reinterpret_cast<float *>(wsm + Cfg::OFF_DC);
   const unsigned mb = smem_u32(&s_mbar[warp]);
@@ -992,14 +999,44 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
     return left < (unsigned long long)WTILE ? (unsigned)left : (unsigned)WTILE;
   };
-  auto issue_tile = [&](unsigned t) {  // bin ids (2 KB) + DC (128 B) of tile t, two bulk copies by lane 0
+  // Outlier extent of a tile (warp-uniform): offset of its first outlier = scanned group prefix + the counts of
+  // the earlier tiles of its group; its size is the tile's count from k_count_bins.
+  struct Extent { unsigned long long base; unsigned total; };
+  auto extent_of = [&](unsigned t) -> Extent {
+    Extent e;
+    e.base = tile_base_of(counts, group_prefix, chunk_prefix, t, lane);
+    e.total = __ldg(counts + t);
+    return e;
+  };
+  // Stage layout (PF): outlier i of the tile lives at stage[lead + i], lead = 4 - (elements up to the next 16-byte
+  // boundary of its global address), so that the 16-byte aligned middle of the run can be fetched by ONE bulk copy to
+  // stage + 16 bytes; the ragged head and tail (at most 3 elements each) are fetched by plain loads.
+  auto lead_of = [&](const Extent &e) -> unsigned {
+    if (!PF) return 0u;
+    const unsigned long long a = (unsigned long long)(uintptr_t)(ac_in + e.base);
+    return 4u - (unsigned)(((16u - (unsigned)(a & 15u)) & 15u) >> 2);
+  };
+  auto issue_tile = [&](unsigned t, const Extent &e) {  // bin ids (2 KB) + DC (128 B) [+ outliers] of tile t
+    const unsigned rows = rows_of(t);
+    // the DC slice is 4*rows bytes: bulk copies need a multiple of 16, so partial tiles load DC directly
+    const bool dc_bulk = (rows == WTILE);
+    unsigned head = 0, mid = 0, lead = 0;
+    if (PF) {
+      lead = lead_of(e);
+      head = (4u - lead) & 3u;
+      head = head < e.total ? head : e.total;
+      mid = ((e.total - head) * 4u) & ~15u;
+    }
     if (lane == 0) {
-      const unsigned rows = rows_of(t);
-      // the DC slice is 4*rows bytes: bulk copies need a multiple of 16, so partial tiles load DC directly
-      const bool dc_bulk = (rows == WTILE);
-      mbar_expect_tx(mb, rows * BLK + (dc_bulk ? WTILE * 4 : 0));
+      mbar_expect_tx(mb, rows * BLK + (dc_bulk ? WTILE * 4 : 0) + mid);
       bulk_g2s(smem_u32(binbuf), bins + (unsigned long long)t * WTILE * BLK, rows * BLK, mb);
       if (dc_bulk) bulk_g2s(smem_u32(dcbuf), dc_in + (unsigned long long)t * WTILE, WTILE * 4, mb);
+      if (mid) bulk_g2s(smem_u32(stage) + 16u, ac_in + e.base + head, mid, mb);
+    }
+    if (PF) {
+      const unsigned tail0 = head + (mid >> 2);
+      if ((unsigned)lane < head) stage[lead + lane] = __ldg(ac_in + e.base + lane);
+      else if (lane >= 8 && tail0 + (unsigned)(lane - 8) < e.total) stage[lead + tail0 + (lane - 8)] = __ldg(ac_in + e.base + tail0 + (lane - 8));
     }
   };
   auto take_ticket = [&]() -> unsigned {
@@ -1008,18 +1045,28 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     return t;
   };
 
-  const unsigned nwarps_grid = gridDim.x * Cfg::WARPS;  // ticket discipline: see k_compress
+  // Tickets run two tiles ahead (there is no ordering between tiles any more): `nxt` is known when an iteration
+  // starts, so its outlier extent can be looked up early and all of its loads issued as soon as the current
+  // tile's inputs are consumed.
+  const unsigned nwarps_grid = gridDim.x * Cfg::WARPS;
   unsigned cur = blockIdx.x * Cfg::WARPS + warp;
-  if (cur < ntiles) issue_tile(cur);
+  Extent ext_cur;
+  ext_cur.base = 0; ext_cur.total = 0;
+  if (cur < ntiles) { ext_cur = extent_of(cur); issue_tile(cur, ext_cur); }
+  unsigned nxt = nwarps_grid + __shfl_sync(FULL, take_ticket(), 0);
   unsigned phase = 0;
 
   while (cur < ntiles) {
     const unsigned pending = take_ticket();
+    Extent ext_nxt;
+    ext_nxt.base = 0; ext_nxt.total = 0;
+    if (nxt < ntiles) ext_nxt = extent_of(nxt);  // loads in flight; consumed after the rebuild below
     const unsigned rows = rows_of(cur);
     const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
     const bool active = (unsigned)lane < rows;
     mbar_wait(mb, phase);
     phase ^= 1u;
+    __syncwarp();  // the ragged outlier elements were stored by other lanes
     unsigned w[16];
     {
       const uint4 *bp = reinterpret_cast<const uint4 *>(binbuf + lane * BLK);
@@ -1034,24 +1081,18 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
 #pragma unroll
       for (int q = 0; q < 16; q++) w[q] = 0;
     }
-    __syncwarp();                        // bin ids and DC are in registers
-    const unsigned nxt = nwarps_grid + __shfl_sync(FULL, pending, 0);
-    if (nxt < ntiles) issue_tile(nxt);   // prefetch the next tile's bin ids
-
     unsigned cnt = 0;
 #pragma unroll
     for (int q = 0; q < 16; q++) cnt += __popc(ff_bytes(q == 0 ? (w[0] & 0xFFFFFF00u) : w[q]));  // position 0 is the DC marker
-    const unsigned incl = warp_inclusive_scan(cnt, lane);
-    const unsigned tile_total = __shfl_sync(FULL, incl, 31);
-    const unsigned my_off = incl - cnt;
-    // offset of the tile's first outlier: scanned group prefix + the counts of the earlier tiles of the group
-    const unsigned long long tile_base = tile_base_of(counts, group_prefix, chunk_prefix, cur, lane);
-    if (lane == 0) bulk_wait_read();  // the previous tile's output has left shared memory (it aliases the stage)
-    __syncwarp();
+    const unsigned my_off = warp_inclusive_scan(cnt, lane) - cnt;
+    const unsigned lead = lead_of(ext_cur);
 
-    // ---- stage this tile's outliers (coalesced) ----
-    for (unsigned i = lane; i < tile_total; i += 32) stage[i] = __ldg(ac_in + tile_base + i);
-    __syncwarp();
+    if (!PF) {  // ---- stage this tile's outliers now (coalesced); the stage aliases the tile buffer ----
+      if (lane == 0) bulk_wait_read();  // the previous tile's output has left shared memory
+      __syncwarp();
+      for (unsigned i = lane; i < ext_cur.total; i += 32) stage[i] = __ldg(ac_in + ext_cur.base + i);
+      __syncwarp();
+    }
 
     // ---- rebuild coefficients (dctz-decomp-lib.c:392-416), already multiplied by sf ----
     T x[BLK];
@@ -1062,7 +1103,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
       x[j] = center[id];  // entry 255 is a dummy, fixed below
     }
     if (cnt != 0) {
-      unsigned p = my_off;
+      unsigned p = lead + my_off;
 #pragma unroll
       for (int q = 0; q < 16; q++) {
         unsigned m = ff_bytes(w[q]);
@@ -1081,12 +1122,17 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
         }
       }
     }
-    __syncwarp();  // every lane is done with the stage before the rows are overwritten
+    __syncwarp();  // bin ids, DC and the stage are consumed by every lane
+    if (nxt < ntiles) issue_tile(nxt, ext_nxt);  // overlaps the inverse transform and the stores
 
     // ---- orthonormal DCT-III (dct.c:115-205) ----
     dct64_inverse<A>(x);
 
     // ---- registers -> own row of the swizzled tile -> TMA tensor stores (rows beyond the field are clipped) ----
+    if (PF) {
+      if (lane == 0) bulk_wait_read();  // the previous tile's output has left shared memory
+      __syncwarp();
+    }
 #pragma unroll
     for (int q = 0; q < L::SLABS; q++) {
 #pragma unroll
@@ -1106,6 +1152,8 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
       bulk_commit();
     }
     cur = nxt;
+    ext_cur = ext_nxt;
+    nxt = nwarps_grid + __shfl_sync(FULL, pending, 0);
   }
   bulk_wait_all();
   __syncthreads();
