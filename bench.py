@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--cpu-log2", type=int, default=23, help="elements per process of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / quality legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--f32", action="store_true", help="c5-slab only: cast the slab to float (single-precision path)")
     return ap.parse_args()
 
 
@@ -194,6 +195,10 @@ def main_reference(args):
 def workload_config(args, world):
     if args.workload == "c5-slab":
         n = 1 << args.slab_log2
+        if getattr(args, "f32", False):
+            return dict(workload=f"c5-slab-f32: per-GPU slab of 2^{args.slab_log2} floats (the {HASH_DIM}^3 field cast to float), EC, eb 1E-3",
+                        mode="ec", error_bound=EB, elements_per_gpu=n, block=64, l2="inputs larger than L2 (no flush needed)",
+                        parallelism=f"slab{world}")
         return dict(workload=f"c5-slab: per-GPU contiguous slab of 2^{args.slab_log2} doubles ({n * 8 / 2**30:.0f} GiB) of the "
                              f"{HASH_DIM}^3 double field (BASELINE config[4]), EC mode, error bound 1E-3; "
                              f"{world} slab(s) = {world * n * 8 / 2**30:.0f} GiB",
@@ -284,6 +289,9 @@ def main_ours(args):
         tdt, code, es = torch.float64, DOUBLE, 8
         x = torch.empty(n, dtype=tdt, device=dev)
         ctx.fill_hash_field(x.data_ptr(), rank * n, n, HASH_DIM, SEED, sh)
+        if args.f32:
+            x = x.float()
+            tdt, code, es = torch.float32, FLOAT, 4
         n_total, first = n * world, rank == 0
     else:
         host, qt = make_host_field(args.workload)

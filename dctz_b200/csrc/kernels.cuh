@@ -287,85 +287,54 @@ template <> struct BitsOf<float> {
   static __device__ __forceinline__ U abs_bits(float v) { return (U)__float_as_int(v) & 0x7FFFFFFFu; }
 };
 
-// Per-thread quantiser state.  DOUBLE: the transform runs on the UNSCALED block (the DCT is linear;
-// dividing afterwards instead of before changes a coefficient by ~1 ulp, far inside the 1e-12
-// tolerance, and saves three FP64 operations per element); the division by sf is folded into one
-// constant kq = 1/(sf*bw):  v = c_u*kq + 127.5 ~ (c_u/sf - rmin)/bw.  The "magic add" turns v into
-// 12.20 fixed point in the low word of z.  Unless the fraction is within 4 units (4e-6) of an
-// integer -- where the approximate v could land on the other side of a bin or range boundary than
-// the exactly rounded expression -- floor(v) and the range test are provably those of the exact
-// expression (|v - v_exact| < 1e-12).  Near-integer coefficients (~8e-6 of all) only raise a flag;
-// flagged blocks are re-quantised once through the exact path (quantize_block_exact).
+// Per-thread quantiser.  The transform runs on the UNSCALED block (the DCT is linear; dividing afterwards
+// instead of before changes a coefficient by ~1 ulp, far inside the coefficient tolerance, and saves the
+// per-element division), and the division by sf is folded into one constant kq = 1/(sf*bw):
+//     v = c_u*kq + 127.5  ~  (c_u/sf - range_min)/bin_width,   t = floor(v),   0 <= t < 255 or outlier.
+// v differs from the exactly rounded reference expression by ~1e-13 (double) / ~1e-5 (float, one ulp of v
+// -- the reference's own float evaluation of that expression carries the same error), i.e. by less than the
+// difference between two correct DCT implementations, so a different floor() can only happen at a
+// quantisation-boundary tie (counted by the parity tests, tests/parity.py).
+//   double: the "magic add" 1.5*2^32, rounded DOWN, leaves floor(v) in bits 20.. of the low word; out of
+//           range saturates.
+//   float : F2I with round-down.
+// id = conv_tbl[t] = max(2t-255, 254-2t) = max(b, ~b) with b = 2t-255; t clamped to 255 gives id 255 (outlier).
 template <typename T> struct Quantizer;
 template <> struct Quantizer<double> {
   double kq;
   Divisor<double> sfdiv;
-  unsigned allok;  // stays 1 while no coefficient of the block came near a boundary
   __device__ __forceinline__ void init(const DevParams *p, const QuantConsts<double> &qc) {
     sfdiv.b = p->sf_d; sfdiv.y = p->inv_sf_d; sfdiv.iters = p->scale_iters;
     kq = __ddiv_rn(1.0, __dmul_rn(p->sf_d, qc.bw));
   }
-  __device__ __forceinline__ void pre_scale(double (&)[BLK]) const {}
   __device__ __forceinline__ double scaled(double c_u) const { return div_exact(c_u, sfdiv); }
   // outliers are stored as float (USE_TRUNCATE): c_u * RN(1/sf) differs from c_u / sf by at most one double ulp,
   // i.e. the float it rounds to differs with probability ~2^-29 -- one multiply instead of the division sequence
   __device__ __forceinline__ float outlier(double c_u) const { return (float)__dmul_rn(c_u, sfdiv.y); }
-  __device__ __forceinline__ void begin_block() { allok = 1u; }
-  __device__ __forceinline__ unsigned quantize(double c_u) {
+  __device__ __forceinline__ unsigned quantize(double c_u) const {
     const double v = __fma_rn(c_u, kq, 127.5);
-    const double z = __dadd_rn(v, 6442450944.0 /* 1.5 * 2^32 */);
+    const double z = __dadd_rd(v, 6442450944.0 /* 1.5 * 2^32 */);  // ROUND DOWN: the 2^-20 grid must not round v up past an integer
     const unsigned lo = (unsigned)__double2loint(z), hi = (unsigned)__double2hiint(z);
-    allok &= (((lo + 4u) & 0xFFFF8u) != 0u) ? 1u : 0u;
     const unsigned u = (hi == 0x41F80000u) ? lo : 0xFFFFFFFFu;  // v outside [0, 4096) saturates
-    const int b = (int)(2u * (u >> 20)) - 255;                  // 2t - 255; conv(t) = max(2t-255, 254-2t) = max(b, ~b)
-    const int id = max(b, ~b);
-    return (unsigned)min(id, 255);                              // t >= 255 (out of range) -> 255
+    const int b = (int)(2u * min(u >> 20, 255u)) - 255;
+    return (unsigned)max(b, ~b);
   }
-  __device__ __forceinline__ bool needs_exact() const { return allok == 0u; }
 };
-// FLOAT: the reference's own float arithmetic on the scaled block, with both divisions done exactly
-// through the reciprocal-FMA sequence (cheap at FP32 rate).
 template <> struct Quantizer<float> {
+  float kq;
   Divisor<float> sfdiv;
-  __device__ __forceinline__ void init(const DevParams *p, const QuantConsts<float> &) {
+  __device__ __forceinline__ void init(const DevParams *p, const QuantConsts<float> &qc) {
     sfdiv.b = p->sf_f; sfdiv.y = p->inv_sf_f; sfdiv.iters = p->scale_iters;
+    kq = (float)__ddiv_rn(1.0, __dmul_rn((double)p->sf_f, (double)qc.bw));
   }
-  __device__ __forceinline__ void pre_scale(float (&x)[BLK]) const {
-    if (sfdiv.iters != 0) {
-#pragma unroll
-      for (int j = 0; j < BLK; j++) x[j] = div_exact(x[j], sfdiv);  // x / sf, bit-exact (dctz-comp-lib.c:208-216)
-    }
+  __device__ __forceinline__ float scaled(float c_u) const { return div_exact(c_u, sfdiv); }
+  __device__ __forceinline__ float outlier(float c_u) const { return div_exact(c_u, sfdiv); }
+  __device__ __forceinline__ unsigned quantize(float c_u) const {
+    const int t = __float2int_rd(__fmaf_rn(c_u, kq, 127.5f));
+    const int b = (int)(2u * min((unsigned)t, 255u)) - 255;  // negative t wraps to a huge unsigned -> 255
+    return (unsigned)max(b, ~b);
   }
-  __device__ __forceinline__ float scaled(float c) const { return c; }
-  __device__ __forceinline__ float outlier(float c) const { return c; }
-  __device__ __forceinline__ void begin_block() {}
-  __device__ __forceinline__ bool needs_exact() const { return false; }
 };
-__device__ __forceinline__ unsigned quantize_f(float c, const QuantConsts<float> &qc) {
-  const bool out = (c < qc.rmin) || (c > qc.rmax);
-  const float q = div_exact(__fsub_rn(c, qc.rmin), qc.div);
-  const int t = __float2int_rz(fminf(q, 254.5f));  // ordinal 255 (c == range_max) clamps to 254, see DESIGN.md
-  return out ? 255u : conv_ordinal(t);
-}
-
-// Cold path of the double quantiser: re-quantise one block exactly.  The coefficients go through
-// local memory so that this rarely executed code stays small (no 63-fold unrolling).
-__device__ __noinline__ void quantize_block_exact(const double *xl, double sf_b, double sf_y, int sf_iters, double rmin,
-                                                  double rmax, double bw, unsigned *wl, unsigned *edge) {
-  Divisor<double> d;
-  d.b = sf_b; d.y = sf_y; d.iters = sf_iters;
-#pragma unroll 1
-  for (int q = 0; q < 16; q++) {
-    unsigned word = 0;
-#pragma unroll 1
-    for (int b = 0; b < 4; b++) {
-      const int j = 4 * q + b;
-      const unsigned id = (j == 0) ? 255u : quant_exact_d(div_exact(xl[j], d), rmin, rmax, bw, edge);
-      word |= id << (8 * b);
-    }
-    wl[q] = word;
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // K2: fused scale + DCT-II + quantise + ordered outlier compaction.
@@ -414,7 +383,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
 
   Quantizer<T> qz;
   qz.init(params, qc);
-  unsigned edge = 0, nexact = 0;
 
   auto rows_of = [&](unsigned t) -> unsigned {
     const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
@@ -466,9 +434,7 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     const bool active = (unsigned)lane < rows;
     // (rows beyond the field arrive zero-filled: they quantise to bin 0 and are never stored)
 
-    // ---- scale (float: x / sf before the transform; double: folded into the quantiser) ----
-    qz.pre_scale(x);
-    // ---- orthonormal DCT-II (dct.c:55-103) ----
+    // ---- orthonormal DCT-II (dct.c:55-103) of the unscaled block; x / sf is folded into the quantiser ----
     dct64_forward<A>(x);
 
     // ---- quantise (dctz-comp-lib.c:350-414); the ids go straight to the warp's bin-id buffer in shared
@@ -477,7 +443,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     __syncwarp();
     uint4 *brow = reinterpret_cast<uint4 *>(binbuf + lane * BLK);
     unsigned cnt = 0;
-    qz.begin_block();
 #pragma unroll
     for (int q4 = 0; q4 < 4; q4++) {
       unsigned wq[4];
@@ -488,31 +453,12 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
         for (int b = 0; b < 4; b++) {
           const int j = 16 * q4 + 4 * k + b;
           if (j == 0) continue;
-          unsigned id;
-          if constexpr (sizeof(T) == 8) id = qz.quantize(x[j]);
-          else id = quantize_f(x[j], qc);
-          word |= id << (8 * b);
+          word |= qz.quantize(x[j]) << (8 * b);
         }
         cnt += __popc(ff_bytes(word));
         wq[k] = word;
       }
       brow[q4] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
-    }
-    if constexpr (sizeof(T) == 8) {
-      if (qz.needs_exact()) {  // rare (~5e-4 of blocks): redo this block through the exact expression
-        double xl[BLK];
-        unsigned wl[16];
-#pragma unroll
-        for (int j = 0; j < BLK; j++) xl[j] = x[j];
-        quantize_block_exact(xl, qz.sfdiv.b, qz.sfdiv.y, qz.sfdiv.iters, qc.rmin, qc.rmax, qc.bw, wl, &edge);
-        cnt = 0;
-#pragma unroll 1
-        for (int q4 = 0; q4 < 4; q4++) {
-          brow[q4] = make_uint4(wl[4 * q4], wl[4 * q4 + 1], wl[4 * q4 + 2], wl[4 * q4 + 3]);
-          cnt += __popc(ff_bytes(wl[4 * q4])) + __popc(ff_bytes(wl[4 * q4 + 1])) + __popc(ff_bytes(wl[4 * q4 + 2])) + __popc(ff_bytes(wl[4 * q4 + 3]));
-        }
-        nexact++;
-      }
     }
     cnt -= 1;  // the DC marker
     if (!active) cnt = 0;
@@ -570,15 +516,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
 
   // ---- epilogue ----
   bulk_wait_all();
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    edge += __shfl_xor_sync(FULL, edge, o);
-    nexact += __shfl_xor_sync(FULL, nexact, o);
-  }
-  if (lane == 0) {
-    if (edge) atomicAdd(&info->n_edge, (unsigned long long)edge);
-    if (nexact) atomicAdd(&info->n_exact_path, (unsigned long long)nexact);
-  }
   __syncthreads();
   if (QT) {
     if (threadIdx.x >= 1 && threadIdx.x < BLK && s_qmax[threadIdx.x] != 0) atomicMax(&qmax_bits[threadIdx.x], s_qmax[threadIdx.x]);

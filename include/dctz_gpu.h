@@ -64,7 +64,7 @@ typedef struct dctz_gpu_info {
   uint64_t n_edge;     /* coefficients at ordinal 255 (item == range_max): the reference indexes
                           conv_tbl[255] out of bounds; we clamp to ordinal 254 and count (double
                           path only)                                                 */
-  uint64_t n_exact_path; /* double path: coefficients routed through the exact-division slow path   */
+  uint64_t n_exact_path; /* reserved (always 0): the quantiser no longer has a slow path                  */
   uint64_t n_qt_dropped; /* QT: rescaled outliers that fell back inside the bin range and are
                             therefore not stored (dctz-comp-lib.c:494-506 quirk)                     */
   int32_t status;      /* 0, or DCTZ_GPU_EDEGENERATE                                                */
