@@ -128,3 +128,26 @@ def test_cesm_config_c2_qt_float(ctx):
     x = fields.cesm_like(dtype=np.float32)
     parity.check_compress(ctx, x, 1e-3, True)
     parity.check_decompress(ctx, x, 1e-3, True)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_coefficients_just_off_bin_boundaries(ctx, dtype):
+    """Blocks built (by an inverse DCT) so that one AC coefficient sits a hair below / above a bin boundary or the
+    outlier range limit -- far enough (>> the coefficient tolerance) that the bin is NOT a tie, close enough
+    that any rounding shortcut in the quantiser (e.g. a round-to-nearest fixed-point conversion) picks the
+    wrong side."""
+    from scipy.fft import idct
+
+    eb = 1e-3
+    rng = np.random.default_rng(17)
+    nblk = 8192
+    c = np.zeros((nblk, 64))
+    c[:, 0] = 40.0  # block values = 5.0 -> max|x| in (1, 10] -> sf == 1: coefficients are used as they are
+    j = rng.integers(1, 64, nblk)
+    t = rng.integers(0, 256, nblk)  # boundary index: range_min + t * bin_width (0 and 255 are the range limits)
+    eps = rng.choice([3e-9, 1e-8, 1e-7, 1e-6, 1e-5] if dtype == np.float64 else [7e-4, 9e-4], nblk) * rng.choice([-1.0, 1.0], nblk)
+    c[np.arange(nblk), j] = -255 * eb + t * 2 * eb + eps
+    x = idct(c, type=2, norm="ortho", axis=-1).reshape(-1).astype(dtype)
+    assert reflib.oracle_stat(x)["sf"] == 1.0
+    rep = parity.check_compress(ctx, x, eb, False)
+    assert rep["ties"] == 0, rep  # none of these is a tie: every bin must be the oracle's
