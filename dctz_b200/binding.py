@@ -19,7 +19,7 @@ EXPORTS = [
     "dctz_gpu_create", "dctz_gpu_destroy", "dctz_gpu_last_error", "dctz_gpu_device_count", "dctz_gpu_sm_count",
     "dctz_gpu_host_alloc", "dctz_gpu_host_free", "dctz_gpu_compress_core", "dctz_gpu_decompress_core", "dctz_gpu_stats",
     "dctz_gpu_stats_dev", "dctz_gpu_compress_dev", "dctz_gpu_qt_finish_dev", "dctz_gpu_compress_field_dev",
-    "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_fill_hash_field",
+    "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_dct64_dev", "dctz_gpu_fill_hash_field",
     "dctz_gpu_sf_from_max", "dctz_gpu_selftest_division", "dctz_gpu_launch_count", "dctz_gpu_set_option",
 ]
 
@@ -70,6 +70,7 @@ def load_library():
         "dctz_gpu_decompress_dev": (i32, [vp, vp, vp, vp, vp, sz, i32, dbl, dbl, i32, vp, vp]),
         "dctz_gpu_scale_dev": (i32, [vp, vp, sz, i32, dbl, i32, vp]),
         "dctz_gpu_dct_blocks": (i32, [vp, vp, vp, sz, i32, i32, i32]),
+        "dctz_gpu_dct64_dev": (i32, [vp, vp, vp, sz, i32, i32, i32, vp]),
         "dctz_gpu_fill_hash_field": (i32, [vp, vp, u64, u64, C.c_uint32, C.c_uint32, vp]),
         "dctz_gpu_sf_from_max": (dbl, [vp, dbl, i32]),
         "dctz_gpu_selftest_division": (i32, [vp, i32, dbl, u64, C.c_uint32, C.POINTER(u64)]),
@@ -259,6 +260,9 @@ class Context:
 
     def scale_dev(self, d_x, n, code, sf, multiply, stream=0):
         self._check(self._lib.dctz_gpu_scale_dev(self._h, d_x, n, code, float(sf), int(bool(multiply)), stream or None))
+
+    def dct64_dev(self, d_in, d_out, nblocks, code, inverse=False, variant=0, stream=0):
+        self._check(self._lib.dctz_gpu_dct64_dev(self._h, d_in, d_out, int(nblocks), code, int(bool(inverse)), int(variant), stream or None))
 
     def fill_hash_field(self, d_out, start, count, dim=2048, seed=20261018, stream=0):
         self._check(self._lib.dctz_gpu_fill_hash_field(self._h, d_out, int(start), int(count), int(dim), int(seed), stream or None))

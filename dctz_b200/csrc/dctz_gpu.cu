@@ -65,6 +65,7 @@ struct dctz_gpu_ctx {
 
   // buffers of the host-buffer API
   DevBuf in, bins, dc, ac, qt, qtraw, out;
+  double *d_dfrag[2] = {nullptr, nullptr};  // DMMA A-fragments of the DCT matrix (forward, inverse)
   int occ[2][2][2] = {};  // resident CTAs/SM per [kernel][datatype][qt]
 };
 
@@ -185,6 +186,7 @@ extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->status, &ctx->slots, &ctx->qt_raw, &ctx->qt_j, &ctx->in, &ctx->bins, &ctx->dc, &ctx->ac,
                     &ctx->qt, &ctx->qtraw, &ctx->out};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+  for (double *p : ctx->d_dfrag) if (p) cudaFree(p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -745,6 +747,57 @@ extern "C" int dctz_gpu_dct_blocks(dctz_gpu_ctx *ctx, const void *in, void *out,
   CU(cudaSetDevice(ctx->device));
   if (datatype == DCTZ_GPU_DOUBLE) return dct_blocks_impl<double>(ctx, (const double *)in, (double *)out, nblocks, dn, inverse);
   return dct_blocks_impl<float>(ctx, (const float *)in, (float *)out, nblocks, dn, inverse);
+}
+
+// Transform-only entry point on device buffers; variant 0 = register butterfly, 1 = FP64 DMMA matrix form.
+static int ensure_dfrag(dctz_gpu_ctx *ctx, int inverse) {
+  if (ctx->d_dfrag[inverse]) return DCTZ_GPU_OK;
+  std::vector<double> f(BLK * BLK);
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int i = 0; i < 8; i++)
+    for (int s = 0; s < 16; s++)
+      for (int lane = 0; lane < 32; lane++) {
+        int row = 8 * i + lane / 4, col = 4 * s + lane % 4;  // entry M[row][col] of the matrix applied to a block
+        int k = inverse ? col : row, n = inverse ? row : col;  // orthonormal DCT-II: C[k][n]; inverse = transpose
+        long double v = sqrtl(2.0L / BLK) * cosl(pi * (long double)(((2 * n + 1) * k) % (4 * BLK)) / (2.0L * BLK));
+        if (k == 0) v /= sqrtl(2.0L);
+        f[(i * 16 + s) * 32 + lane] = (double)v;
+      }
+  CU(cudaMalloc(&ctx->d_dfrag[inverse], f.size() * sizeof(double)));
+  CU(cudaMemcpy(ctx->d_dfrag[inverse], f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_dct64_dev(dctz_gpu_ctx *ctx, const void *d_in, void *d_out, size_t nblocks, int datatype, int inverse, int variant,
+                                  void *stream) {
+  TRY(check_common(ctx, datatype, 1.0));
+  if (!d_in || !d_out || nblocks == 0 || !aligned16(d_in) || !aligned16(d_out)) return fail(ctx, DCTZ_GPU_EINVAL, "dct64_dev: bad pointers");
+  if (variant != 0 && !(variant == 1 && datatype == DCTZ_GPU_DOUBLE)) return fail(ctx, DCTZ_GPU_EINVAL, "dct64_dev: variant %d not available for this type", variant);
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = datatype == DCTZ_GPU_DOUBLE ? 8 : 4;
+  CUtensorMap tin, tout;
+  TRY(make_tile_map(ctx, &tin, d_in, BLK * es, nblocks));
+  TRY(make_tile_map(ctx, &tout, d_out, BLK * es, nblocks));
+  const size_t ntiles = (nblocks + WTILE - 1) / WTILE, ctas = (ntiles + 3) / 4;
+  const size_t resident = (size_t)ctx->sm_count * (datatype == DCTZ_GPU_DOUBLE ? 2 : 3);
+  const int grid = (int)(ctas < resident ? ctas : resident);
+  if (variant == 1) {
+    TRY(ensure_dfrag(ctx, inverse ? 1 : 0));
+    CU(cudaFuncSetAttribute(k_dct64_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, DctOnlyCfg<double>::SMEM));
+    k_dct64_dmma<<<grid, DctOnlyCfg<double>::THREADS, DctOnlyCfg<double>::SMEM, st>>>(tin, tout, nblocks, ctx->d_dfrag[inverse ? 1 : 0]);
+  } else if (datatype == DCTZ_GPU_DOUBLE) {
+    auto k = inverse ? k_dct64_tile<double, true> : k_dct64_tile<double, false>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DctOnlyCfg<double>::SMEM));
+    k<<<grid, DctOnlyCfg<double>::THREADS, DctOnlyCfg<double>::SMEM, st>>>(tin, tout, nblocks);
+  } else {
+    auto k = inverse ? k_dct64_tile<float, true> : k_dct64_tile<float, false>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DctOnlyCfg<float>::SMEM));
+    k<<<grid, DctOnlyCfg<float>::THREADS, DctOnlyCfg<float>::SMEM, st>>>(tin, tout, nblocks);
+  }
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return DCTZ_GPU_OK;
 }
 
 extern "C" int dctz_gpu_fill_hash_field(dctz_gpu_ctx *ctx, double *d_out, uint64_t start, uint64_t count, uint32_t dim, uint32_t seed,

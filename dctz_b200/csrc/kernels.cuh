@@ -1155,6 +1155,150 @@ __global__ void __launch_bounds__(256) k_scale(T *x, size_t n, T sf, int multipl
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Transform-only kernels on device buffers (dctz_gpu_dct64_dev): the butterfly-vs-DMMA comparison
+// of BASELINE config[3].  Both are persistent and warp-autonomous with the same TMA tile movement as
+// K2/K3 (read 8 B + write 8 B per element), so the only difference is the arithmetic:
+//   k_dct64_tile      one block per lane, generated 592-op flow graph on the FP64 vector pipe;
+//   k_dct64_dmma      matrix form Y = D * X on the FP64 tensor pipe: mma.sync.m8n8k4.f64, 8 blocks per
+//                     MMA column tile, 64x64 matrix = 8 m-tiles x 16 k-steps = 128 DMMA per 8 blocks
+//                     (64 FMA per element instead of 9.25 operations).
+// ------------------------------------------------------------------------------------------
+template <typename T> struct DctOnlyCfg {
+  static constexpr int WARPS = 4;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int SMEM = WARPS * WarpTile<T>::BYTES + 1024;
+};
+
+template <typename T, bool INVERSE>
+__global__ void __launch_bounds__(DctOnlyCfg<T>::THREADS, (sizeof(T) == 8 ? 2 : 3))
+k_dct64_tile(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out, unsigned long long nblk) {
+  typedef typename ArithOf<T>::type A;
+  typedef WarpTile<T> L;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_mbar[DctOnlyCfg<T>::WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wsm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) + warp * L::BYTES;
+  const unsigned mb = smem_u32(&s_mbar[warp]);
+  const unsigned ntiles = (unsigned)((nblk + WTILE - 1) / WTILE);
+  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
+  __syncthreads();
+  unsigned phase = 0;
+  for (unsigned t = blockIdx.x * DctOnlyCfg<T>::WARPS + warp; t < ntiles; t += gridDim.x * DctOnlyCfg<T>::WARPS) {
+    if (lane == 0) {
+      bulk_wait_read();  // the previous tile's stores have read the buffer
+      mbar_expect_tx(mb, L::BYTES);
+#pragma unroll
+      for (int q = 0; q < L::SLABS; q++) tma_load_2d(smem_u32(wsm) + q * L::SLAB_BYTES, &tmap_in, q * 128, (int)(t * WTILE), mb);
+    }
+    mbar_wait(mb, phase);
+    phase ^= 1u;
+    T x[BLK];
+#pragma unroll
+    for (int q = 0; q < L::SLABS; q++) {
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(wsm + L::chunk_offset(q, lane, c));
+        const T *e = reinterpret_cast<const T *>(&v);
+#pragma unroll
+        for (int k = 0; k < L::PER_CHUNK; k++) x[(q * 8 + c) * L::PER_CHUNK + k] = e[k];
+      }
+    }
+    if (INVERSE) dct64_inverse<A>(x); else dct64_forward<A>(x);
+#pragma unroll
+    for (int q = 0; q < L::SLABS; q++) {
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        uint4 v;
+        T *e = reinterpret_cast<T *>(&v);
+#pragma unroll
+        for (int k = 0; k < L::PER_CHUNK; k++) e[k] = x[(q * 8 + c) * L::PER_CHUNK + k];
+        *reinterpret_cast<uint4 *>(wsm + L::chunk_offset(q, lane, c)) = v;
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < L::SLABS; q++) tma_store_2d(&tmap_out, q * 128, (int)(t * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES);
+      bulk_commit();
+    }
+  }
+  bulk_wait_all();
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// dfrag: the 64x64 transform matrix pre-arranged as MMA A-fragments, dfrag[(i*16 + s)*32 + lane] =
+// M[8i + lane/4][4s + lane%4], M = orthonormal DCT-II matrix (forward) or its transpose (inverse).
+__global__ void __launch_bounds__(DctOnlyCfg<double>::THREADS, 2)
+k_dct64_dmma(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out, unsigned long long nblk,
+             const double *__restrict__ dfrag) {
+  typedef WarpTile<double> L;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_mbar[DctOnlyCfg<double>::WARPS];
+  __shared__ __align__(16) double s_d[BLK * BLK];  // 32 KB, fragment order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wsm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) + warp * L::BYTES;
+  const unsigned mb = smem_u32(&s_mbar[warp]);
+  const unsigned ntiles = (unsigned)((nblk + WTILE - 1) / WTILE);
+  for (int i = threadIdx.x; i < BLK * BLK; i += blockDim.x) s_d[i] = dfrag[i];
+  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
+  __syncthreads();
+  unsigned phase = 0;
+  const int brow = lane >> 2, kk = lane & 3;  // B fragment: block (column) brow of the group, sample 4s + kk
+  for (unsigned t = blockIdx.x * DctOnlyCfg<double>::WARPS + warp; t < ntiles; t += gridDim.x * DctOnlyCfg<double>::WARPS) {
+    if (lane == 0) {
+      bulk_wait_read();
+      mbar_expect_tx(mb, L::BYTES);
+#pragma unroll
+      for (int q = 0; q < L::SLABS; q++) tma_load_2d(smem_u32(wsm) + q * L::SLAB_BYTES, &tmap_in, q * 128, (int)(t * WTILE), mb);
+    }
+    mbar_wait(mb, phase);
+    phase ^= 1u;
+    double acc[4][8][2];
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[g][i][0] = acc[g][i][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      double bf[4];
+#pragma unroll
+      for (int g = 0; g < 4; g++) {  // element n = 4s + kk of block 8g + brow: chunk (4s+kk)/2 of the row
+        const int n = 4 * s + kk, c = n >> 1, r = 8 * g + brow;
+        bf[g] = *reinterpret_cast<const double *>(wsm + L::chunk_offset(c >> 3, r, c & 7) + (n & 1) * 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const double af = s_d[(i * 16 + s) * 32 + lane];
+#pragma unroll
+        for (int g = 0; g < 4; g++) dmma_m8n8k4(acc[g][i][0], acc[g][i][1], af, bf[g]);
+      }
+    }
+    __syncwarp();  // every lane has consumed the input tile
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {  // C fragment: row k = 8i + lane/4, column (block) 2*(lane%4) + e
+          const int k = 8 * i + brow, c = k >> 1, r = 8 * g + 2 * kk + e;
+          *reinterpret_cast<double *>(wsm + L::chunk_offset(c >> 3, r, c & 7) + (k & 1) * 8) = acc[g][i][e];
+        }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < L::SLABS; q++) tma_store_2d(&tmap_out, q * 128, (int)(t * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES);
+      bulk_commit();
+    }
+  }
+  bulk_wait_all();
+}
+
 // DCT-only kernels behind dctz_gpu_dct_blocks (dct.h:17-27 equivalents)
 constexpr int DCT_ONLY_THREADS = 128;
 template <typename T, bool INVERSE>

@@ -154,6 +154,12 @@ int dctz_gpu_scale_dev(dctz_gpu_ctx *ctx, void *d_x, size_t N, int datatype, dou
 int dctz_gpu_dct_blocks(dctz_gpu_ctx *ctx, const void *in, void *out, size_t nblocks, int dn, int datatype,
                         int inverse);
 
+/* Transform only, device buffers: nblocks blocks of 64 elements, d_in -> d_out (may be the same buffer).
+ * variant 0 = register-resident butterfly (the kernel the codec uses), 1 = matrix form on the FP64 tensor
+ * pipe (mma.sync m8n8k4, double only) -- the comparison BASELINE config[3] asks for.                  */
+int dctz_gpu_dct64_dev(dctz_gpu_ctx *ctx, const void *d_in, void *d_out, size_t nblocks, int datatype, int inverse,
+                       int variant, void *stream);
+
 /* ---- utilities ----------------------------------------------------------------------------- */
 /* Elements [start, start+count) of the exactly reproducible synthetic 3-D field of SURVEY.md §8d
  * (config C5), written as doubles to d_out; host twin: dctz_b200/fields.py:hash_field.          */
@@ -168,8 +174,8 @@ int dctz_gpu_selftest_division(dctz_gpu_ctx *ctx, int datatype, double b, uint64
                                uint64_t *mismatches);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches).                  */
 uint64_t dctz_gpu_launch_count(const dctz_gpu_ctx *ctx);
-/* Kernel variant switches for A/B measurements: name = "dct" -> 0 butterfly (default), 1 FP64 DMMA
- * matrix form (double only).  Returns the previous value or a negative error.                   */
+/* Reserved for kernel variant switches; no option is defined in this build (the DMMA comparison is
+ * dctz_gpu_dct64_dev's `variant`).  Returns the previous value or a negative error.             */
 int dctz_gpu_set_option(dctz_gpu_ctx *ctx, const char *name, int value);
 
 #ifdef __cplusplus

@@ -153,3 +153,34 @@ def test_full_size_properties_nyx_like(ctx):
         assert np.all(dist <= 1e-12 * np.maximum(parity.block_max(o["coef"])[diff], 1e-300))
     assert np.array_equal(d0[w0 // 64:(w0 + (1 << 20)) // 64].cpu().numpy(), o["dc"]) or np.allclose(
         d0[w0 // 64:(w0 + (1 << 20)) // 64].cpu().numpy(), o["dc"], rtol=2e-7)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_transform_only_kernels_butterfly_and_dmma(ctx, variant, inverse):
+    """dctz_gpu_dct64_dev: the register butterfly (variant 0) and the FP64-DMMA matrix form (variant 1) compute the
+    same orthonormal DCT-II / DCT-III as the oracle (dct.c:55-103 / 115-205) to 1e-12."""
+    rng = np.random.default_rng(4)
+    nblk = 32 * 50 + 7  # a partial last tile
+    x = rng.standard_normal(nblk * 64) * rng.choice([1e-3, 1.0, 30.0], nblk * 64)
+    d = _dev(x)
+    out = torch.empty_like(d)
+    ctx.dct64_dev(d.data_ptr(), out.data_ptr(), nblk, DOUBLE, inverse=inverse, variant=variant, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(-1, 64)
+    pick = list(range(0, nblk, 37)) + [nblk - 1]
+    want = np.stack([reflib.oracle_dct(x.reshape(-1, 64)[i], inverse=inverse) for i in pick])
+    scale = np.max(np.abs(want), axis=1, keepdims=True)
+    assert np.max(np.abs(got[pick] - want) / scale) <= 1e-12
+
+
+def test_transform_only_float(ctx):
+    rng = np.random.default_rng(5)
+    nblk = 32 * 20 + 3
+    x = rng.standard_normal(nblk * 64).astype(np.float32)
+    d = _dev(x)
+    ctx.dct64_dev(d.data_ptr(), d.data_ptr(), nblk, FLOAT, inverse=False, variant=0, stream=torch.cuda.current_stream().cuda_stream)  # in place
+    torch.cuda.synchronize()
+    got = d.cpu().numpy().reshape(-1, 64).astype(np.float64)
+    want = np.stack([reflib.oracle_dct(b) for b in x.reshape(-1, 64)[:64]]).astype(np.float64)
+    assert np.max(np.abs(got[:64] - want) / np.max(np.abs(want), axis=1, keepdims=True)) <= 1e-5
