@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdctz_gpu
 EXPORTS = [
     "dctz_gpu_create", "dctz_gpu_destroy", "dctz_gpu_last_error", "dctz_gpu_device_count", "dctz_gpu_sm_count",
     "dctz_gpu_host_alloc", "dctz_gpu_host_free", "dctz_gpu_compress_core", "dctz_gpu_decompress_core", "dctz_gpu_stats",
+    "dctz_gpu_compress_core_with_stats", "dctz_gpu_quality", "dctz_gpu_quality_dev",
     "dctz_gpu_stats_dev", "dctz_gpu_compress_dev", "dctz_gpu_qt_finish_dev", "dctz_gpu_compress_field_dev",
     "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_dct64_dev", "dctz_gpu_fill_hash_field",
     "dctz_gpu_sf_from_max", "dctz_gpu_selftest_division", "dctz_gpu_launch_count", "dctz_gpu_set_option",
@@ -63,6 +64,9 @@ def load_library():
         "dctz_gpu_compress_core": (i32, [vp, vp, sz, i32, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(GpuInfo)]),
         "dctz_gpu_decompress_core": (i32, [vp, vp, vp, vp, u64, vp, sz, i32, dbl, dbl, i32, vp]),
         "dctz_gpu_stats": (i32, [vp, vp, sz, i32, C.POINTER(GpuInfo)]),
+        "dctz_gpu_compress_core_with_stats": (i32, [vp, vp, sz, sz, C.POINTER(dbl), i32, i32, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(GpuInfo)]),
+        "dctz_gpu_quality": (i32, [vp, vp, vp, sz, i32, C.POINTER(dbl)]),
+        "dctz_gpu_quality_dev": (i32, [vp, vp, vp, sz, i32, vp, vp]),
         "dctz_gpu_stats_dev": (i32, [vp, vp, sz, i32, vp, vp]),
         "dctz_gpu_compress_dev": (i32, [vp, vp, sz, sz, i32, dbl, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "dctz_gpu_qt_finish_dev": (i32, [vp, i32, dbl, vp, vp, vp, vp, vp]),
@@ -203,6 +207,29 @@ class Context:
         if want_scaled:
             res["scaled"] = scaled
         return res
+
+    def compress_core_with_stats(self, x, n_total, stats3, first_piece, eb, qt=False):
+        """one block-aligned piece of a larger data set, scaled by the caller's global statistics"""
+        x = np.ascontiguousarray(x)
+        n = x.size
+        bins, dc, ac = np.empty(n, np.uint8), np.empty((n + BLK - 1) // BLK, np.float32), np.empty(max(n, 1), np.float32)
+        qtable = np.zeros(BLK, x.dtype) if qt else None
+        info = GpuInfo()
+        st = (C.c_double * 3)(*[float(v) for v in stats3])
+        self._check(self._lib.dctz_gpu_compress_core_with_stats(self._h, _p(x), n, int(n_total), st, int(bool(first_piece)), _code(x.dtype),
+                                                                float(eb), int(bool(qt)), None, _p(bins), _p(dc), _p(ac), _p(qtable), None,
+                                                                C.byref(info)))
+        res = dict(bin_index=bins, dc=dc, ac=ac[: info.n_outliers], info=info.as_dict(), sf=info.sf, mean=info.mean)
+        if qt:
+            res["qtable"] = qtable
+        return res
+
+    def quality(self, a, b):
+        """{min(a), max(a), max|a-b|, sum (a-b)^2}: the core of calc_psnr (util.c:54-104)"""
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b, dtype=a.dtype)
+        out = (C.c_double * 4)()
+        self._check(self._lib.dctz_gpu_quality(self._h, _p(a), _p(b), a.size, _code(a.dtype), out))
+        return dict(min=out[0], max=out[1], maxdiff=out[2], sumsq=out[3])
 
     def stats(self, x):
         x = np.ascontiguousarray(x)

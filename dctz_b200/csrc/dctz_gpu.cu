@@ -51,6 +51,8 @@ struct dctz_gpu_ctx {
   TileControl *d_ctl = nullptr;
   unsigned long long *d_nconsumed = nullptr;
   unsigned long long *d_mismatch = nullptr;
+  QualityPartial *d_qpartials = nullptr;  // [stat_grid] + 1 result slot
+  double *d_stats_host3 = nullptr;        // 3 doubles for compress_core_with_stats
   DevBuf status;        // [group_prefix: u64 per 32 tiles][counts: u32 per warp tile]
   DevBuf slots;         // EC: tile-strided outlier scratch (TILE_SLOT floats per warp tile)
   DevBuf qt_raw, qt_j;  // QT: tile-strided un-rescaled outliers + their coefficient position
@@ -180,7 +182,7 @@ extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void *small[] = {ctx->d_partials, ctx->d_done, ctx->d_stats3, ctx->d_params, ctx->d_info, ctx->d_ctl,
-                   ctx->d_nconsumed, ctx->d_mismatch, (void *)ctx->tb.thr_d, (void *)ctx->tb.sf_d,
+                   ctx->d_nconsumed, ctx->d_mismatch, ctx->d_qpartials, ctx->d_stats_host3, (void *)ctx->tb.thr_d, (void *)ctx->tb.sf_d,
                    (void *)ctx->tb.thr_f, (void *)ctx->tb.sf_f};
   for (void *p : small) if (p) cudaFree(p);
   DevBuf *bufs[] = {&ctx->status, &ctx->slots, &ctx->qt_raw, &ctx->qt_j, &ctx->in, &ctx->bins, &ctx->dc, &ctx->ac,
@@ -216,8 +218,8 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->stat_grid = ctx->sm_count * 8;
   CU(cudaMalloc(&ctx->d_partials, sizeof(StatPartial) * ctx->stat_grid));
-  CU(cudaMalloc(&ctx->d_done, 2 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups
-  CU(cudaMemset(ctx->d_done, 0, 2 * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->d_done, 4 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups, [2] k_quality
+  CU(cudaMemset(ctx->d_done, 0, 4 * sizeof(unsigned)));
   CU(cudaMalloc(&ctx->d_stats3, 3 * sizeof(double)));
   CU(cudaMalloc(&ctx->d_params, sizeof(DevParams)));
   CU(cudaMalloc(&ctx->d_info, sizeof(Info)));
@@ -225,6 +227,8 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   CU(cudaMemset(ctx->d_ctl, 0, 2 * sizeof(TileControl)));
   CU(cudaMalloc(&ctx->d_nconsumed, sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_mismatch, sizeof(unsigned long long)));
+  CU(cudaMalloc(&ctx->d_qpartials, sizeof(QualityPartial) * (ctx->stat_grid + 1)));
+  CU(cudaMalloc(&ctx->d_stats_host3, 3 * sizeof(double)));
   build_sf_tables(ctx);
   TRY(upload(ctx, ctx->thr_d, &ctx->tb.thr_d));
   TRY(upload(ctx, ctx->sfv_d, &ctx->tb.sf_d));
@@ -632,9 +636,9 @@ extern "C" int dctz_gpu_scale_dev(dctz_gpu_ctx *ctx, void *d_x, size_t N, int da
 // ------------------------------------------------------------------------------------------
 // host-buffer API (the drop-in seam)
 // ------------------------------------------------------------------------------------------
-extern "C" int dctz_gpu_compress_core(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, double eb, int mode_qt,
-                                      void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact, void *qtable,
-                                      void *qtable_raw, dctz_gpu_info *info) {
+static int compress_core_impl(dctz_gpu_ctx *ctx, const void *in, size_t N, size_t N_total, const double *stats3, int first_piece,
+                              int datatype, double eb, int mode_qt, void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact,
+                              void *qtable, void *qtable_raw, dctz_gpu_info *info) {
   TRY(check_common(ctx, datatype, eb));
   if (!in || !bin_index || !DC || !AC_exact || !info || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "compress_core: NULL pointer or N == 0");
   if (mode_qt && !qtable) return fail(ctx, DCTZ_GPU_EINVAL, "compress_core: QT mode needs a qtable output");
@@ -649,8 +653,15 @@ extern "C" int dctz_gpu_compress_core(dctz_gpu_ctx *ctx, const void *in, size_t 
   TRY(grow(ctx, ctx->qt, BLK * 8));
   TRY(grow(ctx, ctx->qtraw, BLK * 8));
   CU(cudaMemcpyAsync(ctx->in.p, in, N * es, cudaMemcpyHostToDevice, st));
-  TRY(dctz_gpu_compress_field_dev(ctx, ctx->in.p, N, datatype, eb, mode_qt, (uint8_t *)ctx->bins.p, (float *)ctx->dc.p,
-                                  (float *)ctx->ac.p, ctx->qt.p, ctx->qtraw.p, (dctz_gpu_info *)ctx->d_info, st));
+  if (stats3) {  // the caller's global statistics decide the scaling factor
+    CU(cudaMemcpyAsync(ctx->d_stats_host3, stats3, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    TRY(dctz_gpu_compress_dev(ctx, ctx->in.p, N, N_total, datatype, eb, mode_qt, ctx->d_stats_host3, 1, first_piece, (uint8_t *)ctx->bins.p,
+                              (float *)ctx->dc.p, (float *)ctx->ac.p, ctx->qtraw.p, (dctz_gpu_info *)ctx->d_info, st));
+    if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, ctx->qtraw.p, ctx->qt.p, (float *)ctx->ac.p, (dctz_gpu_info *)ctx->d_info, st));
+  } else {
+    TRY(dctz_gpu_compress_field_dev(ctx, ctx->in.p, N, datatype, eb, mode_qt, (uint8_t *)ctx->bins.p, (float *)ctx->dc.p,
+                                    (float *)ctx->ac.p, ctx->qt.p, ctx->qtraw.p, (dctz_gpu_info *)ctx->d_info, st));
+  }
   CU(cudaMemcpyAsync(info, ctx->d_info, sizeof(Info), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(bin_index, ctx->bins.p, N, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(DC, ctx->dc.p, nblk * 4, cudaMemcpyDeviceToHost, st));
@@ -670,6 +681,56 @@ extern "C" int dctz_gpu_compress_core(dctz_gpu_ctx *ctx, const void *in, size_t 
       memcpy(scaled_out, in, N * es);
     }
   }
+  CU(cudaStreamSynchronize(st));
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_compress_core(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, double eb, int mode_qt,
+                                      void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact, void *qtable,
+                                      void *qtable_raw, dctz_gpu_info *info) {
+  return compress_core_impl(ctx, in, N, N, nullptr, 1, datatype, eb, mode_qt, scaled_out, bin_index, DC, AC_exact, qtable, qtable_raw, info);
+}
+
+extern "C" int dctz_gpu_compress_core_with_stats(dctz_gpu_ctx *ctx, const void *in, size_t N, size_t N_total, const double stats3[3],
+                                                 int first_piece, int datatype, double eb, int mode_qt, void *scaled_out,
+                                                 uint8_t *bin_index, float *DC, float *AC_exact, void *qtable, void *qtable_raw,
+                                                 dctz_gpu_info *info) {
+  if (!stats3 || N_total < N) return fail(ctx, DCTZ_GPU_EINVAL, "compress_core_with_stats: bad statistics arguments");
+  return compress_core_impl(ctx, in, N, N_total, stats3, first_piece, datatype, eb, mode_qt, scaled_out, bin_index, DC, AC_exact, qtable,
+                            qtable_raw, info);
+}
+
+template <typename T>
+static int launch_quality(dctz_gpu_ctx *ctx, const T *a, const T *b, size_t N, double *d_out4, cudaStream_t st) {
+  size_t want = (N + 255) / 256 / 8 + 1;
+  const int grid = (int)(want < (size_t)ctx->stat_grid ? want : (size_t)ctx->stat_grid);
+  k_quality<T><<<grid, 256, 0, st>>>(a, b, N, ctx->d_qpartials, ctx->d_done + 2, (QualityPartial *)d_out4);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_quality_dev(dctz_gpu_ctx *ctx, const void *d_a, const void *d_b, size_t N, int datatype, double *d_out4, void *stream) {
+  TRY(check_common(ctx, datatype, 1.0));
+  if (!d_a || !d_b || !d_out4 || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "quality: NULL pointer or N == 0");
+  CU(cudaSetDevice(ctx->device));
+  if (datatype == DCTZ_GPU_DOUBLE) return launch_quality<double>(ctx, (const double *)d_a, (const double *)d_b, N, d_out4, (cudaStream_t)stream);
+  return launch_quality<float>(ctx, (const float *)d_a, (const float *)d_b, N, d_out4, (cudaStream_t)stream);
+}
+
+extern "C" int dctz_gpu_quality(dctz_gpu_ctx *ctx, const void *a, const void *b, size_t N, int datatype, double out4[4]) {
+  TRY(check_common(ctx, datatype, 1.0));
+  if (!a || !b || !out4 || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "quality: NULL pointer or N == 0");
+  CU(cudaSetDevice(ctx->device));
+  const size_t es = datatype == DCTZ_GPU_DOUBLE ? 8 : 4;
+  cudaStream_t st = ctx->stream;
+  TRY(grow(ctx, ctx->in, N * es));
+  TRY(grow(ctx, ctx->out, N * es));
+  CU(cudaMemcpyAsync(ctx->in.p, a, N * es, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->out.p, b, N * es, cudaMemcpyHostToDevice, st));
+  double *d_res = (double *)(ctx->d_qpartials + ctx->stat_grid);
+  TRY(dctz_gpu_quality_dev(ctx, ctx->in.p, ctx->out.p, N, datatype, d_res, st));
+  CU(cudaMemcpyAsync(out4, d_res, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return DCTZ_GPU_OK;
 }

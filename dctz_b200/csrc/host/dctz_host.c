@@ -289,19 +289,62 @@ size_t dctz_host_deflate(const void *src, size_t n, void *dst, size_t cap) {
   return out;
 }
 
+/* ---- stream assembly (dctz-comp-lib.c:583-846): side files, three deflates, header, concatenation ---- */
+static size_t assemble_stream(t_datatype dt, size_t n, double error_bound, const dctz_gpu_info *info, const t_bin_id *bin_index,
+                              const float *DC, const float *AC_exact, const void *qtable, const void *qtable_raw, unsigned char *out,
+                              int write_dumps) {
+  const int is_double = (dt == DOUBLE);
+  const size_t es = is_double ? sizeof(double) : sizeof(float);
+  const size_t nblk = (n + DCTZ_BLK_SZ - 1) / DCTZ_BLK_SZ, qbytes = MODE_QT ? DCTZ_BLK_SZ * es : 0;
+  zjob jobs[3];
+  struct header h;
+  size_t total;
+  int i;
+  if (info->n_outliers > 0xFFFFFFFFull) die("too many outliers for the stream header", NULL);
+  if (write_dumps && dumps_enabled()) { /* dctz-comp-lib.c:443-448, 583-595: side files the reference's scripts rename */
+    if (MODE_QT) dump("qtable.bin", qtable_raw, qbytes);
+    dump("bin_index.bin", bin_index, n);
+    dump("AC_exact.bin", AC_exact, (size_t)info->n_outliers * sizeof(float));
+  }
+  memset(jobs, 0, sizeof jobs);
+  jobs[0].src = bin_index; jobs[0].n_src = n;
+  jobs[1].src = DC;        jobs[1].n_src = nblk * sizeof(float);
+  jobs[2].src = AC_exact;  jobs[2].n_src = (size_t)info->n_outliers * sizeof(float);
+  deflate_sections(jobs, 3);
+
+  memset(&h, 0, sizeof h); /* the reference leaves padding uninitialised; zero is as valid and reproducible */
+  h.datatype = dt;
+  h.num_elements = (unsigned int)n;
+  h.error_bound = error_bound;
+  h.tot_AC_exact_count = (unsigned int)info->n_outliers;
+  if (is_double) { h.scaling_factor.d = info->sf; h.mean.d = info->mean; }
+  else { h.scaling_factor.f = (float)info->sf; h.mean.f = (float)info->mean; }
+  h.bindex_sz_compressed = (unsigned int)jobs[0].n_dst;
+  h.DC_sz_compressed = (unsigned int)jobs[1].n_dst;
+  h.AC_exact_sz_compressed = (unsigned int)jobs[2].n_dst;
+#ifdef USE_QTABLE
+  h.bindex_count = (unsigned int)n;
+#endif
+  total = sizeof h + jobs[0].n_dst + jobs[1].n_dst + jobs[2].n_dst + qbytes;
+  memcpy(out, &h, sizeof h);
+  out += sizeof h;
+  for (i = 0; i < 3; i++) {
+    memcpy(out, jobs[i].dst, jobs[i].n_dst);
+    out += jobs[i].n_dst;
+    free(jobs[i].dst);
+  }
+  if (MODE_QT) memcpy(out, qtable, qbytes);
+  return total;
+}
+
 /* ---- dctz_compress (dctz.h:126) ------------------------------------------------------------------ */
 int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error_bound) {
   const int is_double = (var->datatype == DOUBLE);
-  const size_t es = is_double ? sizeof(double) : sizeof(float);
-  size_t n, nblk, qbytes;
+  size_t n, nblk;
   t_bin_id *bin_index;
   float *DC, *AC_exact;
   unsigned char qtable[DCTZ_BLK_SZ * sizeof(double)], qtable_raw[DCTZ_BLK_SZ * sizeof(double)];
   dctz_gpu_info info;
-  zjob jobs[3];
-  struct header h;
-  unsigned char *out;
-  int i;
 
   if (error_bound < 1E-6) { /* dctz-comp-lib.c:135-138 */
     fprintf(stderr, "ERROR: error bound should be no less than 1E-6.\n");
@@ -310,7 +353,6 @@ int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error
   if (N <= 0) die("nothing to compress", "N <= 0");
   n = (size_t)N;
   nblk = (n + DCTZ_BLK_SZ - 1) / DCTZ_BLK_SZ;
-  qbytes = MODE_QT ? DCTZ_BLK_SZ * es : 0;
   bin_index = (t_bin_id *)xmalloc(n, "bin_index");
   DC = (float *)xmalloc(nblk * sizeof(float), "DC");
   AC_exact = (float *)xmalloc(n * sizeof(float), "AC_exact");
@@ -321,45 +363,8 @@ int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error
                              error_bound, MODE_QT, is_double ? (void *)var->buf.d : (void *)var->buf.f, bin_index, DC, AC_exact,
                              MODE_QT ? qtable : NULL, MODE_QT ? qtable_raw : NULL, &info) != DCTZ_GPU_OK)
     die("GPU compress failed", dctz_gpu_last_error(g_ctx));
-  if (info.n_outliers > 0xFFFFFFFFull) die("too many outliers for the stream header", NULL);
-
-  if (dumps_enabled()) { /* dctz-comp-lib.c:443-448, 583-595: side files the reference's scripts rename */
-    if (MODE_QT) dump("qtable.bin", qtable_raw, qbytes);
-    dump("bin_index.bin", bin_index, n);
-    dump("AC_exact.bin", AC_exact, (size_t)info.n_outliers * sizeof(float));
-  }
-
-  memset(jobs, 0, sizeof jobs);
-  jobs[0].src = bin_index; jobs[0].n_src = n;
-  jobs[1].src = DC;        jobs[1].n_src = nblk * sizeof(float);
-  jobs[2].src = AC_exact;  jobs[2].n_src = (size_t)info.n_outliers * sizeof(float);
-  deflate_sections(jobs, 3);
-
-  memset(&h, 0, sizeof h); /* the reference leaves padding uninitialised; zero is as valid and reproducible */
-  h.datatype = var->datatype;
-  h.num_elements = (unsigned int)N;
-  h.error_bound = error_bound;
-  h.tot_AC_exact_count = (unsigned int)info.n_outliers;
-  if (is_double) { h.scaling_factor.d = info.sf; h.mean.d = info.mean; }
-  else { h.scaling_factor.f = (float)info.sf; h.mean.f = (float)info.mean; }
-  h.bindex_sz_compressed = (unsigned int)jobs[0].n_dst;
-  h.DC_sz_compressed = (unsigned int)jobs[1].n_dst;
-  h.AC_exact_sz_compressed = (unsigned int)jobs[2].n_dst;
-#ifdef USE_QTABLE
-  h.bindex_count = (unsigned int)N;
-#endif
-
-  out = is_double ? (unsigned char *)var_z->buf.d : (unsigned char *)var_z->buf.f;
-  memcpy(out, &h, sizeof h);
-  out += sizeof h;
-  for (i = 0; i < 3; i++) {
-    memcpy(out, jobs[i].dst, jobs[i].n_dst);
-    out += jobs[i].n_dst;
-    free(jobs[i].dst);
-  }
-  if (MODE_QT) memcpy(out, qtable, qbytes);
-  *outSize = sizeof h + jobs[0].n_dst + jobs[1].n_dst + jobs[2].n_dst + qbytes;
-
+  *outSize = assemble_stream(var->datatype, n, error_bound, &info, bin_index, DC, AC_exact, qtable, qtable_raw,
+                             is_double ? (unsigned char *)var_z->buf.d : (unsigned char *)var_z->buf.f, 1);
   free(bin_index);
   free(DC);
   free(AC_exact);
@@ -368,10 +373,10 @@ int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error
 }
 
 /* ---- dctz_decompress (dctz.h:127) ---------------------------------------------------------------- */
-int dctz_decompress(t_var *var_z, t_var *var_r) {
-  const int is_double = (var_z->datatype == DOUBLE);
+/* decode one standard stream at `p` into `out` (room for its num_elements); returns the stream's element count */
+static size_t decode_stream(dctz_gpu_ctx *ctx, t_datatype dt, const unsigned char *p, void *out, int chatty) {
+  const int is_double = (dt == DOUBLE);
   const size_t es = is_double ? sizeof(double) : sizeof(float);
-  const unsigned char *p = is_double ? (const unsigned char *)var_z->buf.d : (const unsigned char *)var_z->buf.f;
   struct header h;
   size_t n, nblk, n_out;
   t_bin_id *bin_index;
@@ -399,19 +404,200 @@ int dctz_decompress(t_var *var_z, t_var *var_r) {
   run_zjobs(jobs, 3);
   if (jobs[0].n_dst != n || jobs[1].n_dst != nblk * sizeof(float) || jobs[2].n_dst != n_out * sizeof(float))
     die("corrupt stream", "section sizes do not match the header");
-  printf("uncompressed bin_index size is: %lu\n", (unsigned long)jobs[0].n_dst);
+  if (chatty) printf("uncompressed bin_index size is: %lu\n", (unsigned long)jobs[0].n_dst);
   if (MODE_QT) memcpy(qtable, (const unsigned char *)jobs[2].src + h.AC_exact_sz_compressed, DCTZ_BLK_SZ * es);
 
   sf = is_double ? h.scaling_factor.d : (double)h.scaling_factor.f;
   /* dequantise + inverse DCT + de-scale: dctz-decomp-lib.c:358-511 */
-  if (dctz_gpu_decompress_core(gpu(), bin_index, DC, AC_exact, n_out, MODE_QT ? qtable : NULL, n,
-                               is_double ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT, h.error_bound, sf, MODE_QT,
-                               is_double ? (void *)var_r->buf.d : (void *)var_r->buf.f) != DCTZ_GPU_OK)
-    die("GPU decompress failed", dctz_gpu_last_error(g_ctx));
+  if (dctz_gpu_decompress_core(ctx, bin_index, DC, AC_exact, n_out, MODE_QT ? qtable : NULL, n,
+                               is_double ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT, h.error_bound, sf, MODE_QT, out) != DCTZ_GPU_OK)
+    die("GPU decompress failed", dctz_gpu_last_error(ctx));
   free(bin_index);
   free(DC);
   free(AC_exact);
+  return n;
+}
+
+int dctz_decompress(t_var *var_z, t_var *var_r) {
+  const int is_double = (var_z->datatype == DOUBLE);
+  decode_stream(gpu(), var_z->datatype, is_double ? (const unsigned char *)var_z->buf.d : (const unsigned char *)var_z->buf.f,
+                is_double ? (void *)var_r->buf.d : (void *)var_r->buf.f, 1);
   return 1;
+}
+
+/* ---- large fields: several standard streams sharing ONE global scaling factor -----------
+ * `dctz_compress` takes `int N` and the header stores 32-bit counts (dctz.h:99-114), so a 2048^3 field (2^33
+ * elements) cannot be one stream.  The container below frames it as block-aligned pieces of at most
+ * `g_piece` elements; every piece is a complete, standard DCTZ stream whose header carries the GLOBAL scaling
+ * factor (the reference's dctz_decompress decodes each of them), compressed by one of DCTZ_GPUS devices:
+ *     "DCTZMS01" | u64 N_total | u32 datatype | u32 n_streams | u64 size[n_streams] | stream 0 | stream 1 | ...
+ */
+static size_t g_piece = (size_t)1 << 30;
+void dctz_large_set_piece(size_t elements) { g_piece = elements < 64 ? 64 : (elements / 64) * 64; }
+
+typedef struct {
+  int device, ndev, failed;
+  t_datatype dt;
+  const unsigned char *data;
+  size_t N, npieces;
+  double eb;
+  /* pass 1 */
+  double *pmax, *pmin, *psum;
+  /* pass 2 */
+  const double *stats3;
+  unsigned char **streams;
+  size_t *sizes;
+  /* decode */
+  const unsigned char *in;
+  const size_t *offs;
+  unsigned char *out;
+} large_job;
+
+static size_t piece_len(const large_job *j, size_t i) {
+  const size_t start = i * g_piece;
+  return j->N - start < g_piece ? j->N - start : g_piece;
+}
+
+static void *large_stats_worker(void *arg) {
+  large_job *j = (large_job *)arg;
+  const size_t es = j->dt == DOUBLE ? 8 : 4;
+  dctz_gpu_ctx *ctx = NULL;
+  size_t i;
+  if (dctz_gpu_create(&ctx, j->device) != DCTZ_GPU_OK) { j->failed = 1; return NULL; }
+  for (i = (size_t)j->device; i < j->npieces; i += (size_t)j->ndev) {
+    const unsigned char *p = j->data + i * g_piece * es;
+    dctz_gpu_info info;
+    if (dctz_gpu_stats(ctx, p, piece_len(j, i), j->dt == DOUBLE ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT, &info) != DCTZ_GPU_OK) { j->failed = 1; break; }
+    j->pmax[i] = info.max_abs;
+    j->pmin[i] = info.min_abs;
+    j->psum[i] = info.sum + (j->dt == DOUBLE ? *(const double *)p : (double)*(const float *)p); /* the kernel skipped the piece's element 0 */
+  }
+  dctz_gpu_destroy(ctx);
+  return NULL;
+}
+
+static void *large_compress_worker(void *arg) {
+  large_job *j = (large_job *)arg;
+  const size_t es = j->dt == DOUBLE ? 8 : 4;
+  dctz_gpu_ctx *ctx = NULL;
+  size_t i;
+  if (dctz_gpu_create(&ctx, j->device) != DCTZ_GPU_OK) { j->failed = 1; return NULL; }
+  for (i = (size_t)j->device; i < j->npieces; i += (size_t)j->ndev) {
+    const size_t n = piece_len(j, i), nblk = (n + DCTZ_BLK_SZ - 1) / DCTZ_BLK_SZ;
+    t_bin_id *bin_index = (t_bin_id *)xmalloc(n, "bin_index");
+    float *DC = (float *)xmalloc(nblk * sizeof(float), "DC"), *AC_exact = (float *)xmalloc(n * sizeof(float), "AC_exact");
+    unsigned char qtable[DCTZ_BLK_SZ * sizeof(double)], qtable_raw[DCTZ_BLK_SZ * sizeof(double)];
+    dctz_gpu_info info;
+    if (dctz_gpu_compress_core_with_stats(ctx, j->data + i * g_piece * es, n, j->N, j->stats3, i == 0, j->dt == DOUBLE ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT,
+                                          j->eb, MODE_QT, NULL, bin_index, DC, AC_exact, MODE_QT ? qtable : NULL, MODE_QT ? qtable_raw : NULL,
+                                          &info) != DCTZ_GPU_OK) {
+      fprintf(stderr, "dctz: %s\n", dctz_gpu_last_error(ctx));
+      j->failed = 1;
+    } else {
+      j->streams[i] = (unsigned char *)xmalloc(64 + n + n / 8 + nblk * 4 + (size_t)info.n_outliers * 4 + 4096, "stream");
+      j->sizes[i] = assemble_stream(j->dt, n, j->eb, &info, bin_index, DC, AC_exact, qtable, qtable_raw, j->streams[i], 0);
+    }
+    free(bin_index); free(DC); free(AC_exact);
+    if (j->failed) break;
+  }
+  dctz_gpu_destroy(ctx);
+  return NULL;
+}
+
+static void *large_decode_worker(void *arg) {
+  large_job *j = (large_job *)arg;
+  const size_t es = j->dt == DOUBLE ? 8 : 4;
+  dctz_gpu_ctx *ctx = NULL;
+  size_t i;
+  if (dctz_gpu_create(&ctx, j->device) != DCTZ_GPU_OK) { j->failed = 1; return NULL; }
+  for (i = (size_t)j->device; i < j->npieces; i += (size_t)j->ndev) decode_stream(ctx, j->dt, j->in + j->offs[i], j->out + i * g_piece * es, 0);
+  dctz_gpu_destroy(ctx);
+  return NULL;
+}
+
+static int large_devices(void) {
+  const char *e = getenv("DCTZ_GPUS");
+  int n = e ? atoi(e) : 1, have = dctz_gpu_device_count();
+  if (have < 1) die("cannot open the GPU", "no CUDA device");
+  if (n < 1) n = 1;
+  return n > have ? have : n;
+}
+
+static void run_large(large_job *proto, void *(*fn)(void *)) {
+  const int ndev = large_devices();
+  large_job jobs[16];
+  pthread_t th[16];
+  int t, n = ndev > 16 ? 16 : ndev;
+  for (t = 0; t < n; t++) {
+    jobs[t] = *proto;
+    jobs[t].device = t;
+    jobs[t].ndev = n;
+    jobs[t].failed = 0;
+    if (pthread_create(&th[t], NULL, fn, &jobs[t])) die("Error creating thread", NULL);
+  }
+  for (t = 0; t < n; t++) pthread_join(th[t], NULL);
+  for (t = 0; t < n; t++) if (jobs[t].failed) die("GPU worker failed", dctz_gpu_last_error(NULL));
+}
+
+size_t dctz_large_bound(size_t N, t_datatype dt) {
+  const size_t es = dt == DOUBLE ? 8 : 4, np = (N + g_piece - 1) / g_piece;
+  return 24 + 8 * np + N * (1 + es) + N / 8 + np * 8192; /* every coefficient an outlier + zlib slack */
+}
+
+size_t dctz_compress_large(const void *data, size_t N, t_datatype dt, double error_bound, void *out, size_t out_cap) {
+  large_job j;
+  double stats3[3];
+  size_t i, total, np;
+  unsigned char *o = (unsigned char *)out;
+  if (error_bound < 1E-6) { fprintf(stderr, "ERROR: error bound should be no less than 1E-6.\n"); exit(1); }
+  if (!data || N == 0) die("nothing to compress", "N == 0");
+  memset(&j, 0, sizeof j);
+  np = (N + g_piece - 1) / g_piece;
+  j.dt = dt; j.data = (const unsigned char *)data; j.N = N; j.npieces = np; j.eb = error_bound;
+  j.pmax = (double *)xmalloc(3 * np * sizeof(double), "stats");
+  j.pmin = j.pmax + np; j.psum = j.pmin + np;
+  run_large(&j, large_stats_worker); /* pass 1: statistics of every piece */
+  stats3[0] = j.pmax[0]; stats3[1] = j.pmin[0]; stats3[2] = 0.0;
+  for (i = 0; i < np; i++) { /* piece order: deterministic */
+    if (j.pmax[i] > stats3[0]) stats3[0] = j.pmax[i];
+    if (j.pmin[i] < stats3[1]) stats3[1] = j.pmin[i];
+    stats3[2] += j.psum[i];
+  }
+  j.stats3 = stats3;
+  j.streams = (unsigned char **)xmalloc(np * sizeof(unsigned char *), "streams");
+  j.sizes = (size_t *)xmalloc(np * sizeof(size_t), "sizes");
+  memset(j.streams, 0, np * sizeof(unsigned char *));
+  run_large(&j, large_compress_worker); /* pass 2: every piece with the global scaling factor */
+  total = 24 + 8 * np;
+  for (i = 0; i < np; i++) total += j.sizes[i];
+  if (total > out_cap) die("output buffer too small", "dctz_compress_large");
+  memcpy(o, "DCTZMS01", 8);
+  { const unsigned long long nt = N; const unsigned int d = (unsigned int)dt, ns = (unsigned int)np; memcpy(o + 8, &nt, 8); memcpy(o + 16, &d, 4); memcpy(o + 20, &ns, 4); }
+  o += 24;
+  for (i = 0; i < np; i++) { const unsigned long long sz = j.sizes[i]; memcpy(o, &sz, 8); o += 8; }
+  for (i = 0; i < np; i++) { memcpy(o, j.streams[i], j.sizes[i]); o += j.sizes[i]; free(j.streams[i]); }
+  free(j.streams); free(j.sizes); free(j.pmax);
+  return total;
+}
+
+size_t dctz_decompress_large(const void *in, size_t in_size, void *out, size_t out_elements) {
+  const unsigned char *p = (const unsigned char *)in;
+  unsigned long long nt;
+  unsigned int d, ns;
+  size_t *offs, off, i;
+  large_job j;
+  if (in_size < 24 || memcmp(p, "DCTZMS01", 8)) die("corrupt stream", "not a DCTZ multi-stream container");
+  memcpy(&nt, p + 8, 8); memcpy(&d, p + 16, 4); memcpy(&ns, p + 20, 4);
+  if (nt > out_elements) die("output buffer too small", "dctz_decompress_large");
+  offs = (size_t *)xmalloc(ns * sizeof(size_t), "offsets");
+  off = 24 + 8 * (size_t)ns;
+  for (i = 0; i < ns; i++) { unsigned long long sz; memcpy(&sz, p + 24 + 8 * i, 8); offs[i] = off; off += (size_t)sz; }
+  if (off > in_size) die("corrupt stream", "container sizes exceed the buffer");
+  memset(&j, 0, sizeof j);
+  j.dt = (t_datatype)d; j.N = (size_t)nt; j.npieces = ns; j.in = p; j.offs = offs; j.out = (unsigned char *)out;
+  run_large(&j, large_decode_worker);
+  free(offs);
+  return (size_t)nt;
 }
 
 /* ---- the fine-grained legacy symbols (dctz.h:121-124, dct.h:17-27) ----------------------------------- */
@@ -460,22 +646,15 @@ void dct_fftw_f(float *a, float *b, int dn, int nblk) { (void)nblk; dct_one(a, b
 void ifft_idct(int dn, double *a, double *data) { dct_one(a, data, dn, DCTZ_GPU_DOUBLE, 1); }
 void ifft_idct_f(int dn, float *a, float *data) { dct_one(a, data, dn, DCTZ_GPU_FLOAT, 1); }
 
-/* util.c:54-104: verification utility of the test driver (host loop; not part of the codec) */
+/* util.c:54-104: the driver's quality metric; the reductions run on the GPU */
 double calc_psnr(t_var *var, t_var *var_r, int N, double error_bound) {
   const int is_double = (var->datatype == DOUBLE);
-  double lo = 0, hi = 0, worst = 0, ss = 0, range;
-  int i;
+  double q[4], range;
   (void)error_bound;
-  for (i = 0; i < N; i++) {
-    double v, e;
-    if (is_double) { v = var->buf.d[i]; e = v - var_r->buf.d[i]; }
-    else { v = var->buf.f[i]; e = (double)(float)(var->buf.f[i] - var_r->buf.f[i]); }
-    if (i == 0 || v > hi) hi = v;
-    if (i == 0 || v < lo) lo = v;
-    if (fabs(e) > worst) worst = fabs(e);
-    ss += e * e;
-  }
-  range = hi - lo;
-  printf("Max relative error = %.6f\n", worst / range);
-  return 20 * log10(range / sqrt(ss / N));
+  if (dctz_gpu_quality(gpu(), is_double ? (void *)var->buf.d : (void *)var->buf.f, is_double ? (void *)var_r->buf.d : (void *)var_r->buf.f,
+                       (size_t)N, is_double ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT, q) != DCTZ_GPU_OK)
+    die("GPU quality metrics failed", dctz_gpu_last_error(g_ctx));
+  range = q[1] - q[0];
+  printf("Max relative error = %.6f\n", q[2] / range);
+  return 20 * log10(range / sqrt(q[3] / N));
 }

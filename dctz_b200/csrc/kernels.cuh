@@ -1325,6 +1325,53 @@ __global__ void __launch_bounds__(32) k_dct_generic_blocks(const T *__restrict__
   for (int h = 0; h < 2; h++) if (lane + 32 * h < dn) out[b * dn + lane + 32 * h] = (T)r[h];
 }
 
+// Quality metrics of a reconstruction against the original (util.c:54-104 calc_psnr): min, max of the
+// original, max |a-b| and sum (a-b)^2 (float data: the difference is formed in float like util.c:88).
+struct QualityPartial { double vmin, vmax, maxdiff, sumsq; };
+template <typename T>
+__global__ void __launch_bounds__(256) k_quality(const T *__restrict__ a, const T *__restrict__ b, size_t n, QualityPartial *partials,
+                                                 unsigned *done_counter, QualityPartial *out) {
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  double vmin = inf, vmax = -inf, md = 0.0, ss = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const T va = a[i];
+    const double e = (double)(T)(va - b[i]);
+    vmin = fmin(vmin, (double)va);
+    vmax = fmax(vmax, (double)va);
+    md = fmax(md, fabs(e));
+    ss = __fma_rn(e, e, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fmin(vmin, __shfl_xor_sync(0xFFFFFFFFu, vmin, o));
+    vmax = fmax(vmax, __shfl_xor_sync(0xFFFFFFFFu, vmax, o));
+    md = fmax(md, __shfl_xor_sync(0xFFFFFFFFu, md, o));
+    ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+  }
+  __shared__ QualityPartial sp[8];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sp[warp].vmin = vmin; sp[warp].vmax = vmax; sp[warp].maxdiff = md; sp[warp].sumsq = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    QualityPartial r = sp[0];
+    for (int w = 1; w < 8; w++) { r.vmin = fmin(r.vmin, sp[w].vmin); r.vmax = fmax(r.vmax, sp[w].vmax); r.maxdiff = fmax(r.maxdiff, sp[w].maxdiff); r.sumsq += sp[w].sumsq; }
+    partials[blockIdx.x] = r;
+    __threadfence();
+    is_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  QualityPartial r = partials[0];  // index order: deterministic
+  for (unsigned k = 1; k < gridDim.x; k++) {
+    const QualityPartial q = partials[k];
+    r.vmin = fmin(r.vmin, q.vmin); r.vmax = fmax(r.vmax, q.vmax); r.maxdiff = fmax(r.maxdiff, q.maxdiff); r.sumsq += q.sumsq;
+  }
+  *out = r;
+  *done_counter = 0u;
+}
+
 // Exactly reproducible synthetic field (config C5); host twin in dctz_b200/fields.py.
 __device__ __forceinline__ unsigned hash32(unsigned h) {
   h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;

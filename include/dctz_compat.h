@@ -72,6 +72,14 @@ void idct_finish_f(void);
  * DCTZ_GPU_DEVICE environment variable).  */
 int dctz_build_is_qt(void);
 void dctz_set_device(int device);
+/* Large fields (beyond the `int N` / 32-bit header of one stream): a container of block-aligned pieces, each a
+ * complete standard DCTZ stream compressed with the GLOBAL scaling factor; DCTZ_GPUS=<n> spreads the pieces over
+ * n devices.  dctz_compress_large returns the container size (out must hold dctz_large_bound bytes);
+ * dctz_decompress_large returns the element count.  dctz_large_set_piece changes the piece length (tests). */
+size_t dctz_large_bound(size_t N, t_datatype dt);
+size_t dctz_compress_large(const void *data, size_t N, t_datatype dt, double error_bound, void *out, size_t out_cap);
+size_t dctz_decompress_large(const void *in, size_t in_size, void *out, size_t out_elements);
+void dctz_large_set_piece(size_t elements);
 /* deflate one stream section the way dctz_compress does (chunk-parallel above 2 MiB); returns the size or 0 */
 size_t dctz_host_deflate(const void *src, size_t n, void *dst, size_t cap);
 

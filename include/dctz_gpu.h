@@ -103,6 +103,21 @@ int dctz_gpu_decompress_core(dctz_gpu_ctx *ctx, const uint8_t *bin_index, const 
  * info->max_abs / min_abs / sum / mean / sf (the other fields are zero).                        */
 int dctz_gpu_stats(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, dctz_gpu_info *info);
 
+/* compress_core_with_stats: like compress_core, but the scaling factor comes from the caller's statistics
+ * {max|x|, min|x|, sum} of the WHOLE data set this buffer is a block-aligned piece of (N_total elements;
+ * `first_piece` != 0 for the piece holding element 0).  This is what frames a field beyond the reference's
+ * `int N` limit as several standard DCTZ streams that share one global scaling factor. */
+int dctz_gpu_compress_core_with_stats(dctz_gpu_ctx *ctx, const void *in, size_t N, size_t N_total, const double stats3[3],
+                                      int first_piece, int datatype, double error_bound, int mode_qt, void *scaled_out,
+                                      uint8_t *bin_index, float *DC, float *AC_exact, void *qtable, void *qtable_raw,
+                                      dctz_gpu_info *info);
+
+/* quality: the GPU-backed core of calc_psnr() (util.c:54-104) on host buffers: out4 = {min(a), max(a),
+ * max|a-b|, sum (a-b)^2}.                                                                          */
+int dctz_gpu_quality(dctz_gpu_ctx *ctx, const void *a, const void *b, size_t N, int datatype, double out4[4]);
+/* same on device buffers (d_out4: 4 doubles on the device), asynchronous on `stream`                */
+int dctz_gpu_quality_dev(dctz_gpu_ctx *ctx, const void *d_a, const void *d_b, size_t N, int datatype, double *d_out4, void *stream);
+
 /* ---- device-resident API (benchmarks, multi-GPU slabs, pipelines) ---------------------------
  * All pointers are device pointers on ctx's device; `stream` is a cudaStream_t passed as void*
  * (NULL = default stream).  Input/outputs must be 16-byte aligned.

@@ -155,3 +155,75 @@ def test_cli_round_trip(tmp_path, flavour, flag, dtype):
     o = reflib.oracle_compress(x, 1e-3, flavour == "qt")
     want = reflib.oracle_decompress(o["bin_index"], o["dc"], o["ac"], o["qtable"], x.size, 1e-3, o["stat"]["sf"], flavour == "qt", dtype)
     assert np.max(np.abs(r.astype(np.float64) - want.astype(np.float64))) <= parity.RTOL[np.dtype(dtype)] * 8 * np.max(np.abs(x))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_large_container_pieces_share_the_global_scaling_factor(dtype, tmp_path):
+    """dctz_compress_large: block-aligned pieces, each a standard stream with the GLOBAL sf.
+    With the piece length forced small: the concatenated bin indices equal the single-stream result, every
+    piece decodes with the unmodified reference, and the dump tool walks the container."""
+    lib = hostlib(False)
+    lib.dctz_compress_large.restype = C.c_size_t
+    lib.dctz_decompress_large.restype = C.c_size_t
+    lib.dctz_large_bound.restype = C.c_size_t
+    lib.dctz_compress_large.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_void_p, C.c_size_t]
+    lib.dctz_decompress_large.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    lib.dctz_large_bound.argtypes = [C.c_size_t, C.c_int]
+    lib.dctz_large_set_piece.argtypes = [C.c_size_t]
+    x = np.concatenate([fields.small_cases(dtype)["smooth"] * 0.3 + 1.0, fields.small_cases(dtype)["tail32"]]).astype(dtype)  # max in the LAST piece
+    n, eb, code = x.size, 1e-3, (1 if dtype == np.float64 else 0)
+    piece = 64 * 300
+    lib.dctz_large_set_piece(piece)
+    try:
+        cap = lib.dctz_large_bound(n, code)
+        out = np.zeros(cap, np.uint8)
+        size = lib.dctz_compress_large(x.ctypes.data, n, code, eb, out.ctypes.data, cap)
+        assert 0 < size <= cap and bytes(out[:8]) == b"DCTZMS01"
+        ns = int(np.frombuffer(out[20:24].tobytes(), "<u4")[0])
+        assert ns == (n + piece - 1) // piece and int(np.frombuffer(out[8:16].tobytes(), "<u8")[0]) == n
+        sizes = np.frombuffer(out[24:24 + 8 * ns].tobytes(), "<u8")
+        whole, _, _ = our_compress(x, eb, False)
+        hw, bins_w, dc_w, ac_w, _ = split_stream(whole, dtype, False)
+        sf_w = np.frombuffer(hw["scaling_factor"].tobytes(), dtype=dtype)[0]
+        off, bins, dcs, acs, recon_ref = 24 + 8 * ns, [], [], [], []
+        for i in range(ns):
+            s = out[off:off + int(sizes[i])]
+            h, b, d, a, _ = split_stream(s, dtype, False)
+            assert np.frombuffer(h["scaling_factor"].tobytes(), dtype=dtype)[0] == sf_w  # the GLOBAL scaling factor
+            bins.append(b); dcs.append(d); acs.append(a)
+            if reflib.have_ref():
+                recon_ref.append(ref_decompress(s, int(h["num_elements"]), dtype, False))
+            off += int(sizes[i])
+        assert off == size
+        assert np.array_equal(np.concatenate(bins), bins_w) and np.array_equal(np.concatenate(dcs), dc_w) and np.array_equal(np.concatenate(acs), ac_w)
+        rec = np.zeros(n, dtype)
+        assert lib.dctz_decompress_large(out.ctypes.data, size, rec.ctypes.data, n) == n
+        want = our_decompress(whole, n, dtype, False)
+        assert np.array_equal(rec, want)
+        if recon_ref:
+            tol = parity.RTOL[np.dtype(dtype)] * 8 * float(np.max(np.abs(x)))
+            assert np.max(np.abs(np.concatenate(recon_ref).astype(np.float64) - rec.astype(np.float64))) <= tol
+        f = tmp_path / "big.zms"
+        out[:size].tofile(f)
+        p = subprocess.run([os.path.join(ROOT, "dctz_b200", "bin", "dctz-dump"), str(f)], capture_output=True, text=True)
+        assert p.returncode == 0 and f"streams={ns}" in p.stdout and p.stdout.count("SF=") == ns
+    finally:
+        lib.dctz_large_set_piece(1 << 30)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_quality_metrics_on_the_gpu(ctx, dtype):
+    """dctz_gpu_quality = the reductions of calc_psnr (util.c:54-104)."""
+    rng = np.random.default_rng(2)
+    a = (rng.standard_normal(100003) * 3 + 1).astype(dtype)
+    b = (a + rng.standard_normal(a.size).astype(dtype) * dtype(1e-3)).astype(dtype)
+    q = ctx.quality(a, b)
+    e = (a - b).astype(dtype).astype(np.float64)
+    assert q["min"] == float(a.min()) and q["max"] == float(a.max()) and q["maxdiff"] == float(np.abs(e).max())
+    assert abs(q["sumsq"] - float(np.sum(e * e))) <= 1e-9 * float(np.sum(e * e))
+    lib = hostlib(False)
+    va = reflib.TVar(1 if dtype == np.float64 else 0, 0.0, b"v", a.ctypes.data)
+    vb = reflib.TVar(1 if dtype == np.float64 else 0, 0.0, b"v", b.ctypes.data)
+    psnr = lib.calc_psnr(C.byref(va), C.byref(vb), C.c_int(a.size), C.c_double(1e-3))
+    want = 20 * np.log10((float(a.max()) - float(a.min())) / np.sqrt(float(np.sum(e * e)) / a.size))
+    assert abs(psnr - want) < 1e-9 * abs(want)
