@@ -26,6 +26,47 @@ static void usage(const char *me) {
   printf("Example: %s -d 1E-3 sedov testdata/x86/testfloat_8_8_128.dat 8 8 128 \n", me);
 }
 
+/* Fields beyond one stream's `int N` (dctz.h:126): the multi-stream container of dctz_compress_large, written
+ * to <src>.<ec|qt>.<bound>.zms; DCTZ_GPUS=<n> spreads its pieces over n devices. */
+static int run_large_field(char *argv[], t_datatype dt, size_t n, double eb, const char *mode) {
+  const size_t esize = dt == DOUBLE ? sizeof(double) : sizeof(float);
+  const size_t cap = dctz_large_bound(n, dt);
+  void *data = malloc(n * esize), *rec = malloc(n * esize), *z = malloc(cap);
+  char path[1024];
+  size_t zsize;
+  double t0, t1, t2;
+  t_var va, vr;
+  FILE *f;
+  if (!data || !rec || !z) { fprintf(stderr, "Out of memory\n"); return 1; }
+  f = fopen(argv[4], "rb");
+  if (!f) { printf("File Not Found\n"); return 1; }
+  if (fread(data, esize, n, f) != n) { fprintf(stderr, "short read from %s\n", argv[4]); return 1; }
+  fclose(f);
+  t0 = now();
+  zsize = dctz_compress_large(data, n, dt, eb, z, cap);
+  t1 = now();
+  snprintf(path, sizeof path, "%s.%s.%s.zms", argv[4], mode, argv[2]);
+  f = fopen(path, "wb");
+  if (!f || fwrite(z, zsize, 1, f) != 1) { printf("Write zms file failed\n"); return 1; }
+  fclose(f);
+  printf("outsize = %zu\n", zsize);
+  dctz_decompress_large(z, zsize, rec, n);
+  t2 = now();
+  snprintf(path, sizeof path, "%s.%s.%s.zms.r", argv[4], mode, argv[2]);
+  f = fopen(path, "wb");
+  if (!f || fwrite(rec, n * esize, 1, f) != 1) { printf("Write zms.r file failed\n"); return 1; }
+  fclose(f);
+  if (getenv("TIME")) printf("comp_time = %f (s), decomp_time = %f (s) [wall clock]\n", t1 - t0, t2 - t1);
+  memset(&va, 0, sizeof va);
+  va.datatype = dt; vr = va;
+  va.buf.d = (double *)data; vr.buf.d = (double *)rec;
+  if (n <= 0x7FFFFFFFu) printf("CR = %.2f, PSNR = %.2f\n", (double)(n * esize) / (double)zsize, calc_psnr(&va, &vr, (int)n, eb));
+  else printf("CR = %.2f\n", (double)(n * esize) / (double)zsize);
+  free(data); free(rec); free(z);
+  printf("done\n");
+  return 0;
+}
+
 int main(int argc, char *argv[]) {
   const char *mode = dctz_build_is_qt() ? "qt" : "ec";
   size_t dims[4] = {0, 0, 0, 0}, n = 1, esize, out_size = 0;
@@ -42,8 +83,9 @@ int main(int argc, char *argv[]) {
   eb = atof(argv[2]);
   ndims = argc - 5;
   for (i = 0; i < ndims; i++) { dims[i] = (size_t)atoll(argv[5 + i]); n *= dims[i]; }
-  if (n == 0 || n > 0x7FFFFFFFu) { fprintf(stderr, "element count %zu does not fit the int N of dctz_compress\n", n); return 1; }
+  if (n == 0) { usage(argv[0]); return 1; }
   printf("total number of elements = %zu\n", n);
+  if (n > ((size_t)1 << 30) || getenv("DCTZ_FORCE_LARGE")) return run_large_field(argv, dt, n, eb, mode);
 
   memset(&var, 0, sizeof var);
   var.datatype = dt; var.err_bound = eb; var.var_name = argv[3];

@@ -184,3 +184,42 @@ def test_transform_only_float(ctx):
     got = d.cpu().numpy().reshape(-1, 64).astype(np.float64)
     want = np.stack([reflib.oracle_dct(b) for b in x.reshape(-1, 64)[:64]]).astype(np.float64)
     assert np.max(np.abs(got[:64] - want) / np.max(np.abs(want), axis=1, keepdims=True)) <= 1e-5
+
+
+def test_more_elements_than_int32(ctx):
+    """The C-ABI takes size_t counts: a slab of 2^31 + 64*5 + 3 doubles (16 GiB; beyond the reference's `int N`)
+    goes through compress and decompress on the device; every index computation must be 64-bit clean.
+    Checked by properties: block markers, outlier count consistency, the error bound, and an oracle
+    comparison of the LAST 2^16 elements (the partial tail block included)."""
+    n = (1 << 31) + 64 * 5 + 3
+    s = torch.cuda.current_stream().cuda_stream
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    ctx.fill_hash_field(x.data_ptr(), 0, n, 2048, fields.SEED, s)
+    x[n - 40000] = -39.0  # an isolated spike far inside the last tiles: outliers with a 64-bit offset
+    eb = 1e-3
+    bins = torch.empty(n, dtype=torch.uint8, device="cuda")
+    dc = torch.empty((n + 63) // 64, dtype=torch.float32, device="cuda")
+    ac = torch.empty(1 << 24, dtype=torch.float32, device="cuda")  # this field has few outliers (checked below)
+    info = torch.zeros(binding.INFO_BYTES, dtype=torch.uint8, device="cuda")
+    # statistics first, to size AC_exact honestly: the API contract is "room for N floats", here we verify the count
+    ctx.compress_field_dev(x.data_ptr(), n, DOUBLE, eb, False, bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), 0, 0, info.data_ptr(), s)
+    torch.cuda.synchronize()
+    i = _info(info)
+    assert i["status"] == 0 and i["sf"] == 10.0 and 0 < i["n_outliers"] < (1 << 24)
+    assert bool(torch.all(bins[::64] == 255))
+    start = ((n - (1 << 16)) // 64) * 64
+    pos = (torch.arange(start, n, device="cuda") % 64)
+    k_tail = int(((bins[start:] == 255) & (pos != 0)).sum())
+    assert k_tail > 0
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    ctx.decompress_dev(bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), 0, n, DOUBLE, eb, i["sf"], False, out.data_ptr(), s)
+    torch.cuda.synchronize()
+    err = float(((out - x).abs().max() / i["sf"]).item())
+    assert err <= eb * (1 + 63 * np.sqrt(2)) / 8 * 1.01
+    # oracle on the last 2^16 elements, compressed as their own field with the same sf (max of the window is the spike)
+    xw = x[start:].cpu().numpy()
+    o = reflib.oracle_compress(xw, eb, False)
+    assert o["stat"]["sf"] == i["sf"]
+    assert np.array_equal(bins[start:].cpu().numpy(), o["bin_index"])
+    assert np.allclose(dc[start // 64:].cpu().numpy(), o["dc"], rtol=2e-7, atol=0)
+    assert np.allclose(ac[i["n_outliers"] - k_tail: i["n_outliers"]].cpu().numpy(), o["ac"], rtol=2e-7, atol=0)
