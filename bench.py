@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / quality legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--f32", action="store_true", help="c5-slab only: cast the slab to float (single-precision path)")
+    ap.add_argument("--noise", type=float, default=0.0, help="c5-slab only: add Gaussian noise of this std (raw units) to study the outlier path")
     return ap.parse_args()
 
 
@@ -289,6 +290,9 @@ def main_ours(args):
         tdt, code, es = torch.float64, DOUBLE, 8
         x = torch.empty(n, dtype=tdt, device=dev)
         ctx.fill_hash_field(x.data_ptr(), rank * n, n, HASH_DIM, SEED, sh)
+        if args.noise > 0:
+            gen = torch.Generator(device=dev).manual_seed(SEED + rank)
+            x += args.noise * torch.randn(n, generator=gen, device=dev, dtype=torch.float64)
         if args.f32:
             x = x.float()
             tdt, code, es = torch.float32, FLOAT, 4

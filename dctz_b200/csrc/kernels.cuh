@@ -338,13 +338,15 @@ template <> struct Quantizer<float> {
 
 // ------------------------------------------------------------------------------------------
 // K2: fused scale + DCT-II + quantise + ordered outlier compaction.
-// Shared memory per warp: [ tile: 4 (2) swizzled slabs ][ bin ids 2 KB ]
+// Shared memory per warp: [ tile: 4 (2) swizzled slabs ][ EC: outlier candidates 63 x 32 floats ][ bin ids 2 KB ]
 // ------------------------------------------------------------------------------------------
 template <typename T, bool QT> struct CompressCfg {
   static constexpr int WARPS = 4;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int CTAS_PER_SM = (sizeof(T) == 8) ? 2 : 3;
-  static constexpr int OFF_BINS = WarpTile<T>::BYTES;
+  // EC: outlier candidates [63 coefficient positions][32 lanes] as float, written only by tiles that have outliers
+  static constexpr int OFF_CAND = WarpTile<T>::BYTES;
+  static constexpr int OFF_BINS = OFF_CAND + (QT ? 0 : 63 * WTILE * 4);
   static constexpr int WARP_BYTES = ((OFF_BINS + WTILE * BLK + 1023) / 1024) * 1024;  // tiles need 1 KB alignment (swizzle atom)
   static constexpr int SMEM = WARPS * WARP_BYTES + 1024;                             // + slack to align the base
 };
@@ -483,30 +485,52 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     }
 
     // ---- outliers (dctz-comp-lib.c:478-544): each lane appends its block's outliers, in ascending j, to the
-    //      block's own run of the tile slot, straight from registers; k_gather_* puts the runs in order ----
+    //      block's own run of the tile slot; k_gather_* puts the runs in order ----
     if (tile_total != 0) {
       const unsigned long long run = (unsigned long long)cur * TILE_SLOT + (unsigned)lane * LANE_SLOT;
       const unsigned *wrow = reinterpret_cast<const unsigned *>(binbuf + lane * BLK);
-      unsigned pos = 0;
+      if constexpr (QT) {  // raw coefficient + position, rescaled by K2b once the global qtable is known
+        unsigned pos = 0;
 #pragma unroll
-      for (int q = 0; q < 16; q++) {
-        unsigned m = ff_bytes(wrow[q]);
-        if (q == 0) m &= ~1u;  // the DC marker is not an outlier
-        if (m) {
+        for (int q = 0; q < 16; q++) {
+          unsigned m = ff_bytes(wrow[q]);
+          if (q == 0) m &= ~1u;  // the DC marker is not an outlier
+          if (m) {
 #pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const int j = 4 * q + b;
-            if (j >= 1 && (m & (1u << (8 * b)))) {
-              if (QT) {  // raw coefficient + position, rescaled by K2b once the global qtable is known
+            for (int b = 0; b < 4; b++) {
+              const int j = 4 * q + b;
+              if (j >= 1 && (m & (1u << (8 * b)))) {
                 const T c = qz.scaled(x[j]);
                 raw_slots[run + pos] = c;
                 j_slots[run + pos] = (uint8_t)j;
                 atomicMax(&s_qmax[j], BitsOf<T>::abs_bits(c));  // :371-372, 396-397
-              } else {
-                ac_slots[run + pos] = qz.outlier(x[j]);  // :537 (USE_TRUNCATE)
+                pos++;
               }
-              pos++;
             }
+          }
+        }
+      } else {
+        // Uniform, branch-free part: every lane parks all 63 scaled AC coefficients as float (:537, USE_TRUNCATE) in
+        // its own column of the candidate array (conflict-free; register indices stay compile-time), and packs
+        // the outlier flags of its 64 bin ids into a bit mask.  Then a short loop over the set bits -- its trip
+        // count is the largest per-block count of the warp -- copies the outliers to the block's run.
+        float *cand = reinterpret_cast<float *>(wsm + Cfg::OFF_CAND) + lane;
+#pragma unroll
+        for (int j = 1; j < BLK; j++) cand[(j - 1) * WTILE] = qz.outlier(x[j]);
+        unsigned mlo = 0, mhi = 0;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          const unsigned nib = (ff_bytes(wrow[q]) * 0x01020408u) >> 24;  // flag of byte k -> bit k
+          if (q < 8) mlo |= nib << (4 * q); else mhi |= nib << (4 * (q - 8));
+        }
+        mlo &= ~1u;  // the DC marker is not an outlier
+        const unsigned trips = __reduce_max_sync(FULL, cnt);
+        float *dst = ac_slots + run;
+        for (unsigned it = 0; it < trips; it++) {
+          if (mlo | mhi) {
+            const int j = mlo ? (__ffs(mlo) - 1) : (31 + __ffs(mhi));
+            *dst++ = cand[(j - 1) * WTILE];
+            if (mlo) mlo &= mlo - 1u; else mhi &= mhi - 1u;
           }
         }
       }
