@@ -977,7 +977,10 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     const unsigned long long a = (unsigned long long)(uintptr_t)(ac_in + e.base);
     return 4u - (unsigned)(((16u - (unsigned)(a & 15u)) & 15u) >> 2);
   };
-  auto issue_tile = [&](unsigned t, const Extent &e) {  // bin ids (2 KB) + DC (128 B) [+ outliers] of tile t
+  // The ragged head / tail elements are LOADED when the tile's copies are issued and STORED to the stage only at
+  // the end of the iteration (park_ragged), so the global-load latency hides behind the inverse transform.
+  struct Ragged { float v; int idx; };
+  auto issue_tile = [&](unsigned t, const Extent &e) -> Ragged {  // bin ids (2 KB) + DC (128 B) [+ outliers] of tile t
     const unsigned rows = rows_of(t);
     // the DC slice is 4*rows bytes: bulk copies need a multiple of 16, so partial tiles load DC directly
     const bool dc_bulk = (rows == WTILE);
@@ -994,12 +997,16 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
       if (dc_bulk) bulk_g2s(smem_u32(dcbuf), dc_in + (unsigned long long)t * WTILE, WTILE * 4, mb);
       if (mid) bulk_g2s(smem_u32(stage) + 16u, ac_in + e.base + head, mid, mb);
     }
+    Ragged r;
+    r.v = 0.f; r.idx = -1;
     if (PF) {
       const unsigned tail0 = head + (mid >> 2);
-      if ((unsigned)lane < head) stage[lead + lane] = __ldg(ac_in + e.base + lane);
-      else if (lane >= 8 && tail0 + (unsigned)(lane - 8) < e.total) stage[lead + tail0 + (lane - 8)] = __ldg(ac_in + e.base + tail0 + (lane - 8));
+      if ((unsigned)lane < head) { r.idx = (int)(lead + lane); r.v = __ldg(ac_in + e.base + lane); }
+      else if (lane >= 8 && tail0 + (unsigned)(lane - 8) < e.total) { r.idx = (int)(lead + tail0 + (lane - 8)); r.v = __ldg(ac_in + e.base + tail0 + (lane - 8)); }
     }
+    return r;
   };
+  auto park_ragged = [&](const Ragged &r) { if (PF && r.idx >= 0) stage[r.idx] = r.v; };
   auto take_ticket = [&]() -> unsigned {
     unsigned t = 0;
     if (lane == 0) t = atomicAdd(&ctl->ticket, 1u);
@@ -1013,7 +1020,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   unsigned cur = blockIdx.x * Cfg::WARPS + warp;
   Extent ext_cur;
   ext_cur.base = 0; ext_cur.total = 0;
-  if (cur < ntiles) { ext_cur = extent_of(cur); issue_tile(cur, ext_cur); }
+  if (cur < ntiles) { ext_cur = extent_of(cur); park_ragged(issue_tile(cur, ext_cur)); }
   unsigned nxt = nwarps_grid + __shfl_sync(FULL, take_ticket(), 0);
   unsigned phase = 0;
 
@@ -1084,7 +1091,9 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
       }
     }
     __syncwarp();  // bin ids, DC and the stage are consumed by every lane
-    if (nxt < ntiles) issue_tile(nxt, ext_nxt);  // overlaps the inverse transform and the stores
+    Ragged rag;
+    rag.v = 0.f; rag.idx = -1;
+    if (nxt < ntiles) rag = issue_tile(nxt, ext_nxt);  // overlaps the inverse transform and the stores
 
     // ---- orthonormal DCT-III (dct.c:115-205) ----
     dct64_inverse<A>(x);
@@ -1112,6 +1121,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
       for (int q = 0; q < L::SLABS; q++) tma_store_2d(&tmap_out, q * 128, (int)(cur * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES);
       bulk_commit();
     }
+    park_ragged(rag);
     cur = nxt;
     ext_cur = ext_nxt;
     nxt = nwarps_grid + __shfl_sync(FULL, pending, 0);
