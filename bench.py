@@ -216,13 +216,16 @@ def workload_config(args, world):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 20 ms from before the warm-up (its first line takes ~0.2 s to appear); stop() keeps
+    the samples whose timestamp falls inside the timed region."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -233,33 +236,44 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
+
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         with open(self.path) as fh:
             for ln in fh:
-                p = [s.strip() for s in ln.split(",")]
-                if len(p) < 9:
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 10:
                     continue
                 try:
-                    sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(p[2]), float(p[3]), float(p[4]), [nm for nm, v in zip(names, p[6:10]) if v.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for nm, v in zip(names, p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
         os.unlink(self.path)
-        if not sm:
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        use = inside if inside else rows[-3:]
+        if not use:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        sm.sort()
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm), reasons=sorted(reasons))
+        sm = sorted(r[1] for r in use)
+        reasons = sorted({x for r in use for x in r[4]})
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in use), power_w_max=max(r[3] for r in use), samples=len(use),
+                    samples_in_timed_region=len(inside), reasons=reasons)
 
 
 def main_ours(args):
@@ -277,6 +291,13 @@ def main_ours(args):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:  # run (and allocate pinned host memory) on the CPU cores / NUMA node next to this rank's GPU
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = dctz_b200.Context(local)
@@ -342,6 +363,9 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     compress()
     torch.cuda.synchronize()
     info = read_info()
@@ -360,10 +384,8 @@ def main_ours(args):
     E = lambda: torch.cuda.Event(enable_timing=True)
     evs = [[E() for _ in range(5)] for _ in range(args.steps)]
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
+    sampler.mark_begin()
     for k in range(args.steps):
         if flush is not None:
             flush.zero_()
@@ -374,6 +396,7 @@ def main_ours(args):
         decompress(sf)
         e[4].record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count - launches0
     t_c = sum(e[0].elapsed_time(e[3]) for e in evs) / 1e3
@@ -443,9 +466,11 @@ def main_ours(args):
     bpe_c = 2 * es + 1 + 4 / 64 + 4 * p_out              # + statistics read (SURVEY.md §8d B_c)
     bpe_d = es + 1 + 4 / 64 + 4 * p_out                  # SURVEY.md §8d B_d
     ach = bpe_k2 * n * args.steps / t_k2 / 1e9
-    traffic = None
+    traffic = None  # dram__bytes_read+write of k_compress per launch, from the committed ncu capture, scaled to this slab
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("k_compress")
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("k_compress")
+        if tr and es == 8 and not qt:
+            traffic = tr["bytes_per_element"] * n
     except Exception:
         pass
     roofline = dict(bound="hbm", kernel="k_compress<%s,%s>" % ("double" if es == 8 else "float", "QT" if qt else "EC"),
