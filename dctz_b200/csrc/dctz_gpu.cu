@@ -398,14 +398,15 @@ template <typename T> static QtConsts<T> make_qt(double eb) {
 template <typename T>
 static int launch_stats(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double *d_stats3, int finalize_inline, size_t n_total,
                         void *d_qtable_raw, Info *d_info, cudaStream_t st) {
-  constexpr int VEC = 16 / (int)sizeof(T);
-  size_t want = (N / VEC + 255) / 256 / 4 + 1;
-  int grid = (int)(want < (size_t)ctx->stat_grid ? want : (size_t)ctx->stat_grid);
+  const size_t nchunks = (N * sizeof(T) + STAT_CHUNK - 1) / STAT_CHUNK;
+  const size_t resident = (size_t)ctx->sm_count * 3;  // 3 CTAs x 64 KB of staging per SM
+  int grid = (int)(nchunks < resident ? (nchunks ? nchunks : 1) : resident);
   SfTables tb = ctx->tb;
   tb.qmax_words = (int)(BLK * sizeof(T) / 8);
-  k_stats<T><<<grid, 256, 0, st>>>(d_in, N, ctx->d_partials, ctx->d_done, d_stats3, finalize_inline,
-                                   (unsigned long long)n_total, 1, tb, ctx->d_params, d_info,
-                                   (unsigned long long *)d_qtable_raw);
+  CU(cudaFuncSetAttribute(k_stats<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAT_SMEM));
+  k_stats<T><<<grid, 256, STAT_SMEM, st>>>(d_in, N, ctx->d_partials, ctx->d_done, d_stats3, finalize_inline,
+                                           (unsigned long long)n_total, 1, tb, ctx->d_params, d_info,
+                                           (unsigned long long *)d_qtable_raw);
   ctx->launches++;
   CU(cudaGetLastError());
   return DCTZ_GPU_OK;

@@ -58,10 +58,13 @@ struct Info {             // mirrors dctz_gpu_info (include/dctz_gpu.h)
 };
 
 // ------------------------------------------------------------------------------------------
-// K1: statistics.  Grid-stride over 16-byte vectors; |x| compared as unsigned bit patterns
-// (monotonic for non-negative IEEE values), sum accumulated in double.
+// K1: statistics.  Persistent CTAs stream 16 KB chunks through shared memory (TMA bulk copies); |x| compared
+// as unsigned bit patterns (monotonic for non-negative IEEE values), sum accumulated in double.
 // ------------------------------------------------------------------------------------------
 struct StatPartial { unsigned long long umax, umin; double sum; };
+constexpr int STAT_CHUNK = 16384;   // bytes per TMA bulk copy
+constexpr int STAT_STAGES = 4;      // chunks in flight per CTA
+constexpr int STAT_SMEM = STAT_CHUNK * STAT_STAGES;
 
 template <typename T> struct AbsBits;
 template <> struct AbsBits<double> {
@@ -88,35 +91,57 @@ __global__ void __launch_bounds__(256) k_stats(const T *__restrict__ in, size_t 
   unsigned long long umax = 0ull, umin = ~0ull;
   double s0 = 0.0, s1 = 0.0;
   const size_t nvec = n / VEC;
-  const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // 4 independent 128-bit loads in flight per thread
-  for (; i + 3 * stride < nvec; i += 4 * stride) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) v[u] = __ldg(in4 + i + u * stride);
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const T *e = reinterpret_cast<const T *>(&v[u]);
-#pragma unroll
-      for (int k = 0; k < VEC; k++) {
-        const unsigned long long a = AbsBits<T>::get(e[k]);
-        umax = a > umax ? a : umax;
-        umin = a < umin ? a : umin;
-        if (k & 1) s1 += (double)e[k]; else s0 += (double)e[k];
+  // The slab streams through shared memory in 16 KB chunks fetched by TMA bulk copies (one thread issues, a
+  // STAT_STAGES-deep ring of mbarriers tracks them): the load path costs the SM one instruction per 16 KB
+  // instead of 1024 LDG.128, and reaches the bandwidth the TMA-fed transform kernels reach.
+  extern __shared__ __align__(128) unsigned char stat_smem[];
+  __shared__ __align__(8) unsigned long long s_full[STAT_STAGES];
+  const size_t nchunks = (nvec * 16 + STAT_CHUNK - 1) / STAT_CHUNK;
+  const unsigned char *src = reinterpret_cast<const unsigned char *>(in);
+  auto chunk_bytes = [&](size_t c) -> unsigned {
+    const size_t left = nvec * 16 - c * STAT_CHUNK;
+    return (unsigned)(left < (size_t)STAT_CHUNK ? left : (size_t)STAT_CHUNK);
+  };
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < STAT_STAGES; st++) mbar_init(smem_u32(&s_full[st]), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < STAT_STAGES; st++) {
+      const size_t c = (size_t)blockIdx.x + (size_t)st * gridDim.x;
+      if (c < nchunks) {
+        mbar_expect_tx(smem_u32(&s_full[st]), chunk_bytes(c));
+        bulk_g2s(smem_u32(stat_smem + st * STAT_CHUNK), src + c * STAT_CHUNK, chunk_bytes(c), smem_u32(&s_full[st]));
       }
     }
   }
-  for (; i < nvec; i += stride) {
-    const uint4 v = __ldg(in4 + i);
-    const T *e = reinterpret_cast<const T *>(&v);
+  unsigned k = 0;
+  for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, k++) {
+    const int st = (int)(k % STAT_STAGES);
+    mbar_wait(smem_u32(&s_full[st]), (k / STAT_STAGES) & 1u);
+    const uint4 *buf = reinterpret_cast<const uint4 *>(stat_smem + st * STAT_CHUNK);
+    const unsigned nv = chunk_bytes(c) / 16;
 #pragma unroll
-    for (int k = 0; k < VEC; k++) {
-      const unsigned long long a = AbsBits<T>::get(e[k]);
-      umax = a > umax ? a : umax;
-      umin = a < umin ? a : umin;
-      s0 += (double)e[k];
+    for (int u = 0; u < STAT_CHUNK / 16 / 256; u++) {
+      const unsigned idx = u * 256 + threadIdx.x;
+      if (idx < nv) {
+        const uint4 v = buf[idx];
+        const T *e = reinterpret_cast<const T *>(&v);
+#pragma unroll
+        for (int q = 0; q < VEC; q++) {
+          const unsigned long long a = AbsBits<T>::get(e[q]);
+          umax = a > umax ? a : umax;
+          umin = a < umin ? a : umin;
+          if (q & 1) s1 += (double)e[q]; else s0 += (double)e[q];
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with this stage: refill it
+    const size_t cn = c + (size_t)STAT_STAGES * gridDim.x;
+    if (threadIdx.x == 0 && cn < nchunks) {
+      mbar_expect_tx(smem_u32(&s_full[st]), chunk_bytes(cn));
+      bulk_g2s(smem_u32(stat_smem + st * STAT_CHUNK), src + cn * STAT_CHUNK, chunk_bytes(cn), smem_u32(&s_full[st]));
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
