@@ -218,7 +218,7 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->stat_grid = ctx->sm_count * 8;
   CU(cudaMalloc(&ctx->d_partials, sizeof(StatPartial) * ctx->stat_grid));
-  CU(cudaMalloc(&ctx->d_done, 4 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups, [2] k_quality
+  CU(cudaMalloc(&ctx->d_done, 4 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups, [2] k_quality, [3] k_count_bins
   CU(cudaMemset(ctx->d_done, 0, 4 * sizeof(unsigned)));
   CU(cudaMalloc(&ctx->d_stats3, 3 * sizeof(double)));
   CU(cudaMalloc(&ctx->d_params, sizeof(DevParams)));
@@ -441,6 +441,8 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
   float *ac_slots = nullptr;
   T *raw = nullptr;
   uint8_t *jpos = nullptr;
+  FusedScan fused;
+  fused.n_entries = 0;
   if (QT) {
     TRY(grow(ctx, ctx->qt_raw, n_entries * TILE_SLOT * sizeof(T)));
     TRY(grow(ctx, ctx->qt_j, n_entries * TILE_SLOT));
@@ -457,8 +459,11 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     const int grid = (int)(ctas < resident ? ctas : resident);
     CUtensorMap tmap;
     TRY(make_tile_map(ctx, &tmap, d_in, BLK * sizeof(T), nblk_full));
+    fused.out = sb.out;
+    fused.total = &d_info->n_outliers;
+    fused.n_entries = (rem == 0 && (n_entries + 31) / 32 <= 1024) ? (unsigned)n_entries : 0u;  // small field: the last CTA scans
     k_compress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts, sb.blk_counts, ac_slots,
-                                                             raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0], d_info);
+                                                             raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0], d_info, fused);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -468,8 +473,10 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     ctx->launches++;
     CU(cudaGetLastError());
   }
-  k_scan_groups<<<sb.nchunks, 1024, 0, st>>>(sb.counts, (unsigned)n_entries, sb.out, &d_info->n_outliers);
-  ctx->launches++;
+  if (!fused.n_entries) {
+    k_scan_groups<<<sb.nchunks, 1024, 0, st>>>(sb.counts, (unsigned)n_entries, sb.out, &d_info->n_outliers);
+    ctx->launches++;
+  }
   if (!QT) {
     const size_t want = (n_entries + 7) / 8;
     const int grid = (int)(want < (size_t)ctx->sm_count * 16 ? want : (size_t)ctx->sm_count * 16);
@@ -579,9 +586,16 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
     {
       const size_t want = (ntiles + 7) / 8;
       const int grid = (int)(want < (size_t)ctx->sm_count * 16 ? want : (size_t)ctx->sm_count * 16);
-      k_count_bins<<<grid, 256, 0, st>>>(d_bins, nblk_full, sb.counts);
-      k_scan_groups<<<sb.nchunks, 1024, 0, st>>>(sb.counts, (unsigned)ntiles, sb.out, ctx->d_nconsumed);
-      ctx->launches += 2;
+      FusedScan fused;
+      fused.out = sb.out;
+      fused.total = ctx->d_nconsumed;
+      fused.n_entries = ((ntiles + 31) / 32 <= 1024) ? (unsigned)ntiles : 0u;  // small field: the last CTA scans
+      k_count_bins<<<grid, 256, 0, st>>>(d_bins, nblk_full, sb.counts, ctx->d_done + 3, fused);
+      ctx->launches++;
+      if (!fused.n_entries) {
+        k_scan_groups<<<sb.nchunks, 1024, 0, st>>>(sb.counts, (unsigned)ntiles, sb.out, ctx->d_nconsumed);
+        ctx->launches++;
+      }
     }
     const size_t resident = (size_t)ctx->sm_count * ctx->occ[1][sizeof(T) == 8][QT];
     const size_t ctas = (ntiles + Cfg::WARPS - 1) / Cfg::WARPS;

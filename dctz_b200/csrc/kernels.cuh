@@ -362,6 +362,84 @@ template <> struct Quantizer<float> {
 };
 
 // ------------------------------------------------------------------------------------------
+// Scan of the per-tile outlier counts (shared by K2 / the gather kernels / K3)
+// ------------------------------------------------------------------------------------------
+// Chunk c = 1024 consecutive groups, one per thread of CTA c.  group_prefix[g] = outliers in the earlier
+// groups of the same chunk; the last CTA to finish turns the chunk totals into chunk_prefix[c] and
+// writes the grand total to *total.  Consumers add the two: prefix_of_group().
+struct ScanOut {
+  unsigned long long *group_prefix;  // one per group
+  unsigned long long *chunk_prefix;  // one per chunk (first used as chunk totals)
+  unsigned *done;                    // CTAs finished; reset by the last one
+};
+__device__ __forceinline__ unsigned long long prefix_of_group(const unsigned long long *__restrict__ group_prefix,
+                                                              const unsigned long long *__restrict__ chunk_prefix, unsigned g) {
+  return __ldg(chunk_prefix + (g >> 10)) + __ldg(group_prefix + g);
+}
+__device__ __forceinline__ unsigned long long block_exclusive_scan_1024(unsigned long long v, unsigned long long *s_warp,
+                                                                        unsigned long long *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0ull;  // CTAs smaller than 1024 threads
+    unsigned long long wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+      if (lane >= o) wi += n;
+    }
+    s_warp[lane] = wi - w;
+    if (lane == 31) s_warp[32] = wi;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[warp] + incl - v;
+}
+// For small fields the producer kernel's LAST CTA runs the scan itself (one launch less): ngroups <= 1024, i.e. one
+// chunk, so group_prefix holds global prefixes and chunk_prefix[0] = 0.  Executed by every thread of the CTA.
+struct FusedScan {
+  ScanOut out;
+  unsigned long long *total;
+  unsigned n_entries;  // 0 = the caller launches k_scan_groups instead
+};
+__device__ __forceinline__ void cta_scan_small(const unsigned *counts, const FusedScan &f) {
+  __shared__ unsigned long long s_w[33];
+  __shared__ unsigned long long s_carry;
+  const unsigned ngroups = (f.n_entries + 31u) / 32u;
+  if (threadIdx.x == 0) s_carry = 0ull;
+  __syncthreads();
+  for (unsigned base = 0; base < ngroups; base += blockDim.x) {
+    const unsigned g = base + threadIdx.x;
+    unsigned long long sum = 0;
+    if (g < ngroups) {
+      const unsigned first = g * 32u;
+      if (first + 32u <= f.n_entries) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(counts + first);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const uint4 v = __ldcg(p + k); sum += (unsigned long long)v.x + v.y + v.z + v.w; }
+      } else {
+        for (unsigned t = first; t < f.n_entries; t++) sum += __ldcg(counts + t);
+      }
+    }
+    unsigned long long tot;
+    const unsigned long long excl = block_exclusive_scan_1024(sum, s_w, &tot);
+    const unsigned long long carry = s_carry;
+    if (g < ngroups) f.out.group_prefix[g] = carry + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { f.out.chunk_prefix[0] = 0ull; *f.total = s_carry; }
+}
+
+// ------------------------------------------------------------------------------------------
 // K2: fused scale + DCT-II + quantise + ordered outlier compaction.
 // Shared memory per warp: [ tile: 4 (2) swizzled slabs ][ EC: outlier candidates 63 x 32 floats ][ bin ids 2 KB ]
 // ------------------------------------------------------------------------------------------
@@ -386,7 +464,7 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
            T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
            typename BitsOf<T>::U *__restrict__ qmax_bits,     // QT: 64 per-position maxima (bit patterns)
            T *__restrict__ qtable0,                           // QT: receives the last full block's DC
-           TileControl *ctl, Info *info) {
+           TileControl *ctl, Info *info, FusedScan fused) {
   typedef typename ArithOf<T>::type A;
   typedef CompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -569,10 +647,18 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
   if (QT) {
     if (threadIdx.x >= 1 && threadIdx.x < BLK && s_qmax[threadIdx.x] != 0) atomicMax(&qmax_bits[threadIdx.x], s_qmax[threadIdx.x]);
   }
+  __shared__ bool s_last;
+  __threadfence();  // this thread's counts are visible device-wide before the CTA signs off
+  __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
     const unsigned prev = atomicAdd(&ctl->done, 1u);
-    if (prev == gridDim.x - 1) { ctl->ticket = 0u; ctl->done = 0u; }
+    s_last = (prev == gridDim.x - 1);
+    if (s_last) { ctl->ticket = 0u; ctl->done = 0u; }
+  }
+  __syncthreads();
+  if (s_last && fused.n_entries) {
+    __threadfence();
+    cta_scan_small(counts, fused);
   }
 }
 
@@ -680,44 +766,6 @@ __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /
 // ------------------------------------------------------------------------------------------
 // Scan + gather: per-tile counts -> exclusive prefix per group of 32 tiles -> final AC_exact order.
 // ------------------------------------------------------------------------------------------
-// Chunk c = 1024 consecutive groups, one per thread of CTA c.  group_prefix[g] = outliers in the earlier
-// groups of the same chunk; the last CTA to finish turns the chunk totals into chunk_prefix[c] and
-// writes the grand total to *total.  Consumers add the two: prefix_of_group().
-struct ScanOut {
-  unsigned long long *group_prefix;  // one per group
-  unsigned long long *chunk_prefix;  // one per chunk (first used as chunk totals)
-  unsigned *done;                    // CTAs finished; reset by the last one
-};
-__device__ __forceinline__ unsigned long long prefix_of_group(const unsigned long long *__restrict__ group_prefix,
-                                                              const unsigned long long *__restrict__ chunk_prefix, unsigned g) {
-  return __ldg(chunk_prefix + (g >> 10)) + __ldg(group_prefix + g);
-}
-__device__ __forceinline__ unsigned long long block_exclusive_scan_1024(unsigned long long v, unsigned long long *s_warp,
-                                                                        unsigned long long *total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += n;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    const unsigned long long w = s_warp[lane];
-    unsigned long long wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-      if (lane >= o) wi += n;
-    }
-    s_warp[lane] = wi - w;
-    if (lane == 31) s_warp[32] = wi;
-  }
-  __syncthreads();
-  *total = s_warp[32];
-  return s_warp[warp] + incl - v;
-}
 __global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *__restrict__ counts, unsigned ntiles, ScanOut out,
                                                      unsigned long long *total) {
   __shared__ unsigned long long s_warp[33];
@@ -885,7 +933,7 @@ __global__ void __launch_bounds__(32) k_qt_compact(const uint8_t *__restrict__ b
 
 // Decompress pre-pass: number of 255 markers at positions j >= 1 per warp tile (32 blocks = 2 KB of bin ids).
 __global__ void __launch_bounds__(256) k_count_bins(const uint8_t *__restrict__ bins, unsigned long long nblk_full,
-                                                    unsigned *__restrict__ counts) {
+                                                    unsigned *__restrict__ counts, unsigned *done_counter, FusedScan fused) {
   const int lane = threadIdx.x & 31;
   const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
   const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
@@ -906,6 +954,19 @@ __global__ void __launch_bounds__(256) k_count_bins(const uint8_t *__restrict__ 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
     if (lane == 0) counts[t] = cnt;
+  }
+  if (!fused.n_entries) return;
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+    if (s_last) *done_counter = 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    cta_scan_small(counts, fused);
   }
 }
 
