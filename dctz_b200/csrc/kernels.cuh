@@ -462,8 +462,8 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
            uint8_t *__restrict__ blk_counts,                  // outliers per block (32 per tile slot)
            float *__restrict__ ac_slots,                      // EC: outlier scratch, TILE_SLOT per tile, LANE_SLOT per block
            T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
-           typename BitsOf<T>::U *__restrict__ qmax_bits,     // QT: 64 per-position maxima (bit patterns)
-           T *__restrict__ qtable0,                           // QT: receives the last full block's DC
+           typename BitsOf<T>::U *qmax_bits,                  // QT: 64 per-position maxima (bit patterns), entries 1..63
+           T *qtable0,                                        // QT: entry 0 of the same table: the last full block's DC
            TileControl *ctl, Info *info, FusedScan fused) {
   typedef typename ArithOf<T>::type A;
   typedef CompressCfg<T, QT> Cfg;

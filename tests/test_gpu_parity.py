@@ -151,3 +151,39 @@ def test_coefficients_just_off_bin_boundaries(ctx, dtype):
     assert reflib.oracle_stat(x)["sf"] == 1.0
     rep = parity.check_compress(ctx, x, eb, False)
     assert rep["ties"] == 0, rep  # none of these is a tie: every bin must be the oracle's
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("qt", [False, True])
+def test_randomised_sweep(ctx, dtype, qt):
+    """Sizes around every structural boundary (block 64, warp tile 2048, group 65536, vector width), error bounds
+    from 1E-6 (every coefficient an outlier: 63 per block, full slots) to 1 (nothing is), magnitudes from 1e-30
+    to 1e30, both signs -- all against the oracle."""
+    rng = np.random.default_rng(2026 + (1 if qt else 0) + (2 if dtype == np.float32 else 0))
+    sizes = [1, 2, 63, 64, 65, 127, 128, 2047, 2048, 2049, 4096 + 17, 65536, 65536 + 64 + 5, 3 * 65536 + 1000]
+    kinds = ["smooth", "noise", "const", "step", "spiky"]
+    for n in sizes:
+        for _ in range(2):
+            kind = kinds[int(rng.integers(len(kinds)))]
+            eb = float(rng.choice([1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1.0]))
+            scale = float(10.0 ** rng.integers(-30 if dtype == np.float64 else -20, 31 if dtype == np.float64 else 21))
+            t = np.arange(n)
+            if kind == "smooth":
+                x = np.sin(t / 17.0) + 0.3 * np.cos(t / 5.0) + 2.0
+            elif kind == "noise":
+                x = rng.standard_normal(n)
+            elif kind == "const":
+                x = np.full(n, -3.0)
+            elif kind == "step":
+                x = np.where((t // 50) % 2 == 0, 1.0, -7.5)
+            else:
+                x = 0.01 * rng.standard_normal(n)
+                x[rng.integers(0, n, max(1, n // 97))] += 9.0
+            x = (x * scale).astype(dtype)
+            if not np.any(x) or not np.all(np.isfinite(x)):
+                continue
+            try:
+                parity.check_compress(ctx, x, eb, qt)
+                parity.check_decompress(ctx, x, eb, qt)
+            except AssertionError as e:  # pragma: no cover
+                raise AssertionError(f"n={n} kind={kind} eb={eb} scale={scale}: {e}") from e
