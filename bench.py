@@ -190,7 +190,7 @@ def main_reference(args):
                 dtype="f64" if sample.dtype.itemsize == 8 else "f32", data="synthetic",
                 config=workload_config(args, args.gpus), cpu_baseline=base,
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -548,12 +548,23 @@ def main_ours(args):
                 compress_gbs=gb_all / t_c, decompress_gbs=gb_all / t_d, ms_compress=1e3 * t_c / args.steps,
                 ms_decompress=1e3 * t_d / args.steps, roofline=roofline, cpu_baseline=cpu, e2e=e2e, quality=quality, outlier_leg=outlier_leg,
                 gpu_launches=int(launches), clocks=clocks, impl="ours")
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def _emit(line):
+    """The contract is ONE JSON line on stdout: everything else any library prints goes to stderr (see __main__)."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 if __name__ == "__main__":
     a = parse_args()
+    # keep stdout clean: NCCL, torchrun and friends print banners on fd 1; route fd 1 to stderr and keep a private
+    # handle on the real stdout for the JSON line
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
