@@ -19,7 +19,7 @@ EXPORTS = [
     "dctz_gpu_create", "dctz_gpu_destroy", "dctz_gpu_last_error", "dctz_gpu_device_count", "dctz_gpu_sm_count",
     "dctz_gpu_host_alloc", "dctz_gpu_host_free", "dctz_gpu_compress_core", "dctz_gpu_decompress_core", "dctz_gpu_stats",
     "dctz_gpu_compress_core_with_stats", "dctz_gpu_quality", "dctz_gpu_quality_dev",
-    "dctz_gpu_stats_dev", "dctz_gpu_compress_dev", "dctz_gpu_qt_finish_dev", "dctz_gpu_compress_field_dev",
+    "dctz_gpu_stats_dev", "dctz_gpu_compress_dev", "dctz_gpu_compress_known_stats_dev", "dctz_gpu_qt_finish_dev", "dctz_gpu_compress_field_dev",
     "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_dct64_dev", "dctz_gpu_fill_hash_field",
     "dctz_gpu_sf_from_max", "dctz_gpu_selftest_division", "dctz_gpu_launch_count", "dctz_gpu_set_option",
 ]
@@ -69,6 +69,7 @@ def load_library():
         "dctz_gpu_quality_dev": (i32, [vp, vp, vp, sz, i32, vp, vp]),
         "dctz_gpu_stats_dev": (i32, [vp, vp, sz, i32, vp, vp]),
         "dctz_gpu_compress_dev": (i32, [vp, vp, sz, sz, i32, dbl, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
+        "dctz_gpu_compress_known_stats_dev": (i32, [vp, vp, sz, sz, i32, dbl, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "dctz_gpu_qt_finish_dev": (i32, [vp, i32, dbl, vp, vp, vp, vp, vp]),
         "dctz_gpu_compress_field_dev": (i32, [vp, vp, sz, i32, dbl, i32, vp, vp, vp, vp, vp, vp, vp]),
         "dctz_gpu_decompress_dev": (i32, [vp, vp, vp, vp, vp, sz, i32, dbl, dbl, i32, vp, vp]),
@@ -273,6 +274,13 @@ class Context:
         self._check(self._lib.dctz_gpu_compress_dev(self._h, d_in, n, n_total, code, float(eb), int(bool(qt)), d_stats_all,
                                                     int(nranks), int(bool(first_slab)), d_bins, d_dc, d_ac,
                                                     d_qtable_raw or None, d_info, stream or None))
+
+    def compress_known_stats_dev(self, d_in, n, n_total, code, eb, qt, d_stats_all, nranks, first_slab, d_bins, d_dc, d_ac,
+                                 d_qtable_raw, d_info, stream=0):
+        """compress_dev with caller-supplied statistics that the kernel verifies (info.status = -6 if stale)"""
+        self._check(self._lib.dctz_gpu_compress_known_stats_dev(self._h, d_in, n, n_total, code, float(eb), int(bool(qt)), d_stats_all,
+                                                                int(nranks), int(bool(first_slab)), d_bins, d_dc, d_ac,
+                                                                d_qtable_raw or None, d_info, stream or None))
 
     def qt_finish_dev(self, code, eb, d_qtable_raw, d_qtable, d_ac, d_info, stream=0):
         self._check(self._lib.dctz_gpu_qt_finish_dev(self._h, code, float(eb), d_qtable_raw, d_qtable, d_ac, d_info, stream or None))

@@ -225,7 +225,8 @@ constexpr int LANE_SLOT = 64;    // LANE_SLOT entries each (a block has at most 
 // Control block shared by all CTAs of a persistent kernel.
 struct TileControl {
   unsigned ticket;   // next tile index (dynamic scheduling)
-  unsigned done;     // CTAs that have exited; the last one resets both fields for the next launch
+  unsigned done;     // CTAs that have exited; the last one resets the fields for the next launch
+  unsigned long long max_bits;  // VERIFY variant of K2: largest |x| bit pattern seen so far
 };
 
 // inclusive warp scan of one small count per lane

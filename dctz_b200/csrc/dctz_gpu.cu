@@ -241,10 +241,16 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   ctx->tb.min_d = ctx->min_d;
   ctx->tb.min_f = ctx->min_f;
   // kernel attributes + residency (persistent grids are sized from these)
-  ctx->occ[0][1][0] = kernel_occupancy(k_compress<double, false>, CompressCfg<double, false>::THREADS, CompressCfg<double, false>::SMEM);
-  ctx->occ[0][1][1] = kernel_occupancy(k_compress<double, true>, CompressCfg<double, true>::THREADS, CompressCfg<double, true>::SMEM);
-  ctx->occ[0][0][0] = kernel_occupancy(k_compress<float, false>, CompressCfg<float, false>::THREADS, CompressCfg<float, false>::SMEM);
-  ctx->occ[0][0][1] = kernel_occupancy(k_compress<float, true>, CompressCfg<float, true>::THREADS, CompressCfg<float, true>::SMEM);
+  ctx->occ[0][1][0] = kernel_occupancy(k_compress<double, false, false>, CompressCfg<double, false>::THREADS, CompressCfg<double, false>::SMEM);
+  ctx->occ[0][1][1] = kernel_occupancy(k_compress<double, true, false>, CompressCfg<double, true>::THREADS, CompressCfg<double, true>::SMEM);
+  ctx->occ[0][0][0] = kernel_occupancy(k_compress<float, false, false>, CompressCfg<float, false>::THREADS, CompressCfg<float, false>::SMEM);
+  ctx->occ[0][0][1] = kernel_occupancy(k_compress<float, true, false>, CompressCfg<float, true>::THREADS, CompressCfg<float, true>::SMEM);
+  // the VERIFY instantiations (caller-supplied statistics) need the same shared-memory opt-in
+  if (kernel_occupancy(k_compress<double, false, true>, CompressCfg<double, false>::THREADS, CompressCfg<double, false>::SMEM) < 1 ||
+      kernel_occupancy(k_compress<double, true, true>, CompressCfg<double, true>::THREADS, CompressCfg<double, true>::SMEM) < 1 ||
+      kernel_occupancy(k_compress<float, false, true>, CompressCfg<float, false>::THREADS, CompressCfg<float, false>::SMEM) < 1 ||
+      kernel_occupancy(k_compress<float, true, true>, CompressCfg<float, true>::THREADS, CompressCfg<float, true>::SMEM) < 1)
+    return fail(ctx, DCTZ_GPU_ECUDA, "k_compress<VERIFY> cannot be made resident");
   ctx->occ[1][1][0] = kernel_occupancy(k_decompress<double, false>, DecompressCfg<double, false>::THREADS, DecompressCfg<double, false>::SMEM);
   ctx->occ[1][1][1] = kernel_occupancy(k_decompress<double, true>, DecompressCfg<double, true>::THREADS, DecompressCfg<double, true>::SMEM);
   ctx->occ[1][0][0] = kernel_occupancy(k_decompress<float, false>, DecompressCfg<float, false>::THREADS, DecompressCfg<float, false>::SMEM);
@@ -427,7 +433,7 @@ extern "C" int dctz_gpu_stats_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N,
 // ------------------------------------------------------------------------------------------
 template <typename T, bool QT>
 static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb, uint8_t *d_bins, float *d_dc, float *d_ac,
-                           void *d_qtable_raw, Info *d_info, cudaStream_t st) {
+                           void *d_qtable_raw, Info *d_info, cudaStream_t st, int verify = 0, int verify_lower = 0) {
   typedef CompressCfg<T, QT> Cfg;
   typedef typename BitsOf<T>::U U;
   const unsigned long long nblk_full = N / BLK;
@@ -462,14 +468,20 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     fused.out = sb.out;
     fused.total = &d_info->n_outliers;
     fused.n_entries = (rem == 0 && (n_entries + 31) / 32 <= 1024) ? (unsigned)n_entries : 0u;  // small field: the last CTA scans
-    k_compress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts, sb.blk_counts, ac_slots,
-                                                             raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0], d_info, fused);
+    if (verify)
+      k_compress<T, QT, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts, sb.blk_counts,
+                                                                     ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0],
+                                                                     d_info, fused, verify_lower);
+    else
+      k_compress<T, QT, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts, sb.blk_counts,
+                                                                      ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0],
+                                                                      d_info, fused, 0);
     ctx->launches++;
     CU(cudaGetLastError());
   }
   if (rem) {
     k_tail_compress<T, QT><<<1, 32, 0, st>>>(d_in + nblk_full * BLK, rem, nblk_full, (unsigned)ntiles, ctx->d_params, qc, d_bins, d_dc,
-                                             sb.counts, sb.blk_counts, ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, d_info);
+                                             sb.counts, sb.blk_counts, ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, d_info, verify, verify_lower);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -488,13 +500,14 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
 }
 
 static int compress_dispatch(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt, uint8_t *d_bins,
-                             float *d_dc, float *d_ac, void *d_qtable_raw, Info *d_info, cudaStream_t st) {
+                             float *d_dc, float *d_ac, void *d_qtable_raw, Info *d_info, cudaStream_t st, int verify = 0,
+                             int verify_lower = 0) {
   if (datatype == DCTZ_GPU_DOUBLE) {
-    if (mode_qt) return launch_compress<double, true>(ctx, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
-    return launch_compress<double, false>(ctx, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
+    if (mode_qt) return launch_compress<double, true>(ctx, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st, verify, verify_lower);
+    return launch_compress<double, false>(ctx, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st, verify, verify_lower);
   }
-  if (mode_qt) return launch_compress<float, true>(ctx, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
-  return launch_compress<float, false>(ctx, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
+  if (mode_qt) return launch_compress<float, true>(ctx, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st, verify, verify_lower);
+  return launch_compress<float, false>(ctx, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st, verify, verify_lower);
 }
 
 static int check_compress_args(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt,
@@ -507,9 +520,9 @@ static int check_compress_args(dctz_gpu_ctx *ctx, const void *d_in, size_t N, in
   return DCTZ_GPU_OK;
 }
 
-extern "C" int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb,
-                                     int mode_qt, const double *d_stats_all, int nranks, int first_slab, uint8_t *d_bins,
-                                     float *d_dc, float *d_ac, void *d_qtable_raw, dctz_gpu_info *d_info, void *stream) {
+static int compress_dev_impl(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb, int mode_qt,
+                             const double *d_stats_all, int nranks, int first_slab, uint8_t *d_bins, float *d_dc, float *d_ac,
+                             void *d_qtable_raw, dctz_gpu_info *d_info, void *stream, int verify) {
   TRY(check_compress_args(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, d_info));
   if (!d_stats_all || nranks < 1 || N_total < N) return fail(ctx, DCTZ_GPU_EINVAL, "compress: bad statistics arguments");
   CU(cudaSetDevice(ctx->device));
@@ -520,7 +533,23 @@ extern "C" int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t
                                ctx->d_params, (Info *)d_info, mode_qt ? (unsigned long long *)d_qtable_raw : nullptr);
   ctx->launches++;
   CU(cudaGetLastError());
-  return compress_dispatch(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, (Info *)d_info, st);
+  // a slab of a larger field need not hold the global maximum: only a single-slab call can check the lower limit
+  return compress_dispatch(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, (Info *)d_info, st, verify,
+                           verify && N_total == N);
+}
+
+extern "C" int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb,
+                                     int mode_qt, const double *d_stats_all, int nranks, int first_slab, uint8_t *d_bins,
+                                     float *d_dc, float *d_ac, void *d_qtable_raw, dctz_gpu_info *d_info, void *stream) {
+  return compress_dev_impl(ctx, d_in, N, N_total, datatype, eb, mode_qt, d_stats_all, nranks, first_slab, d_bins, d_dc, d_ac, d_qtable_raw,
+                           d_info, stream, 0);
+}
+
+extern "C" int dctz_gpu_compress_known_stats_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb,
+                                                 int mode_qt, const double *d_stats_all, int nranks, int first_slab, uint8_t *d_bins,
+                                                 float *d_dc, float *d_ac, void *d_qtable_raw, dctz_gpu_info *d_info, void *stream) {
+  return compress_dev_impl(ctx, d_in, N, N_total, datatype, eb, mode_qt, d_stats_all, nranks, first_slab, d_bins, d_dc, d_ac, d_qtable_raw,
+                           d_info, stream, 1);
 }
 
 template <typename T>

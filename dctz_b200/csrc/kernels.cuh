@@ -33,6 +33,7 @@ struct DevParams {        // written on the device by finalize_params(), read by
   float sf_f, inv_sf_f;   // float path divisor
   int scale_iters;        // Divisor::iters for x / sf
   int status;
+  double decade_lo, decade_hi;  // sf is right for this data iff decade_lo <= max|x| < decade_hi (util.c:28/42)
 };
 
 template <typename T> struct QuantConsts;  // host-computed from the error bound only
@@ -244,15 +245,27 @@ __device__ __forceinline__ void finalize_params(const double *stats_all, int nra
   if (!(mx > 0.0) || !(mx < __longlong_as_double(0x7FF0000000000000ll))) status = -5;  // DCTZ_GPU_EDEGENERATE
   double sf = 1.0, mean;
   if (!status && (is_double ? !(mx >= tb.min_d) : !((float)mx >= tb.min_f))) status = -5;  // sf would be subnormal
+  p->decade_lo = 0.0;
+  p->decade_hi = __longlong_as_double(0x7FF0000000000000ll);
   if (is_double) {
-    if (!status) sf = sf_lookup_d(mx, tb);
+    if (!status) {
+      const int idx = sf_index<double>(mx, tb.thr_d, tb.n_d, tb.kmin_d, ilogb(mx));
+      sf = tb.sf_d[idx];
+      p->decade_lo = idx > 0 ? tb.thr_d[idx - 1] : tb.min_d;
+      if (idx < tb.n_d) p->decade_hi = tb.thr_d[idx];
+    }
     mean = sum / (double)(long long)n_total;
     const Divisor<double> d = make_divisor(sf);
     p->sf_d = d.b; p->inv_sf_d = d.y; p->scale_iters = d.iters;
     p->sf_f = (float)sf; p->inv_sf_f = 0.f;
   } else {
     float sff = 1.0f;
-    if (!status) sff = sf_lookup_f((float)mx, tb);
+    if (!status) {
+      const int idx = sf_index<float>((float)mx, tb.thr_f, tb.n_f, tb.kmin_f, ilogbf((float)mx));
+      sff = tb.sf_f[idx];
+      p->decade_lo = (double)(idx > 0 ? tb.thr_f[idx - 1] : tb.min_f);
+      if (idx < tb.n_f) p->decade_hi = (double)tb.thr_f[idx];
+    }
     sf = (double)sff;
     mean = (double)((float)sum / (float)(long long)n_total);
     const Divisor<float> d = make_divisor(sff);
@@ -454,7 +467,12 @@ template <typename T, bool QT> struct CompressCfg {
   static constexpr int SMEM = WARPS * WARP_BYTES + 1024;                             // + slack to align the base
 };
 
-template <typename T, bool QT>
+// VERIFY: the statistics behind `params` are the caller's belief (a previous time step, a sample, a bound), not
+// a pass over this data.  The kernel then also tracks the true max|x| (exact 64-bit bit-pattern maximum) and
+// its last CTA checks that it lies in the decade the scaling factor was derived from; if not, info->status =
+// DCTZ_GPU_ESTALE and the outputs are to be discarded.  `verify_lower` = 0 leaves the lower limit to the caller
+// (a slab of a larger field need not contain the global maximum).
+template <typename T, bool QT, bool VERIFY>
 __global__ void __launch_bounds__(CompressCfg<T, QT>::THREADS, CompressCfg<T, QT>::CTAS_PER_SM)
 k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_full, const DevParams *__restrict__ params,
            QuantConsts<T> qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
@@ -464,7 +482,7 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
            T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
            typename BitsOf<T>::U *qmax_bits,                  // QT: 64 per-position maxima (bit patterns), entries 1..63
            T *qtable0,                                        // QT: entry 0 of the same table: the last full block's DC
-           TileControl *ctl, Info *info, FusedScan fused) {
+           TileControl *ctl, Info *info, FusedScan fused, int verify_lower) {
   typedef typename ArithOf<T>::type A;
   typedef CompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -488,6 +506,7 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
 
   Quantizer<T> qz;
   qz.init(params, qc);
+  U seen_max = 0;  // VERIFY: largest |x| bit pattern of this thread's blocks
 
   auto rows_of = [&](unsigned t) -> unsigned {
     const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
@@ -538,6 +557,10 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
     const bool active = (unsigned)lane < rows;
     // (rows beyond the field arrive zero-filled: they quantise to bin 0 and are never stored)
+    if constexpr (VERIFY) {
+#pragma unroll
+      for (int j = 0; j < BLK; j++) { const U a = BitsOf<T>::abs_bits(x[j]); seen_max = a > seen_max ? a : seen_max; }
+    }
 
     // ---- orthonormal DCT-II (dct.c:55-103) of the unscaled block; x / sf is folded into the quantiser ----
     dct64_forward<A>(x);
@@ -648,12 +671,30 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     if (threadIdx.x >= 1 && threadIdx.x < BLK && s_qmax[threadIdx.x] != 0) atomicMax(&qmax_bits[threadIdx.x], s_qmax[threadIdx.x]);
   }
   __shared__ bool s_last;
+  if constexpr (VERIFY) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const U m = __shfl_xor_sync(FULL, seen_max, o); seen_max = m > seen_max ? m : seen_max; }
+    if (lane == 0) atomicMax(&ctl->max_bits, (unsigned long long)seen_max);
+  }
   __threadfence();  // this thread's counts are visible device-wide before the CTA signs off
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned prev = atomicAdd(&ctl->done, 1u);
     s_last = (prev == gridDim.x - 1);
-    if (s_last) { ctl->ticket = 0u; ctl->done = 0u; }
+    if (s_last) {
+      ctl->ticket = 0u;
+      ctl->done = 0u;
+      if constexpr (VERIFY) {
+        __threadfence();
+        const unsigned long long mb = atomicExch(&ctl->max_bits, 0ull);
+        const double mx = sizeof(T) == 8 ? __longlong_as_double((long long)mb) : (double)__int_as_float((int)(unsigned)mb);
+        info->max_abs = mx;  // the true maximum of this slab
+        if (!(mx < params->decade_hi) || (verify_lower && !(mx >= params->decade_lo))) {
+          info->status = -6;  // DCTZ_GPU_ESTALE
+          info->n_exact_path = 1;
+        }
+      }
+    }
   }
   __syncthreads();
   if (s_last && fused.n_entries) {
@@ -715,10 +756,22 @@ __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /
                                                       const DevParams *params, QuantConsts<T> qc, uint8_t *bins,
                                                       float *dc_out, unsigned *counts, uint8_t *blk_counts, float *ac_slots,
                                                       T *raw_slots, uint8_t *j_slots, typename BitsOf<T>::U *qmax_bits,
-                                                      T *qtable0, Info *info) {
+                                                      T *qtable0, Info *info, int verify, int verify_lower) {
   __shared__ double xs[BLK];
   const int lane = threadIdx.x;
   const T sf = (sizeof(T) == 8) ? (T)params->sf_d : (T)params->sf_f;
+  if (verify) {  // the caller's statistics are a belief: the tail's values count towards the true maximum too
+    double m = 0.0;
+    for (int n = lane; n < rem; n += 32) m = fmax(m, fabs((double)in[n]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if (lane == 0) {
+      const double mx = fmax(m, info->max_abs);  // the main kernel stored the maximum of the full blocks (none: the caller's)
+      if (blk_index != 0) info->max_abs = mx; else info->max_abs = m;
+      const double t = blk_index != 0 ? mx : m;
+      if (!(t < params->decade_hi) || (verify_lower && !(t >= params->decade_lo))) { info->status = -6; info->n_exact_path = 1; }
+    }
+  }
   for (int n = lane; n < rem; n += 32) {
     T v = in[n];
     if (sf != (T)1) v = v / sf;  // IEEE division (no fast-math)

@@ -47,6 +47,7 @@ extern "C" {
 #define DCTZ_GPU_EINVAL (-3)    /* bad argument (eb < 1e-6 like dctz-comp-lib.c:135, alignment, ...) */
 #define DCTZ_GPU_ENOMEM (-4)
 #define DCTZ_GPU_EDEGENERATE (-5) /* max|x| is 0, inf or NaN: the reference computes sf = 0/NaN (util.c:28) */
+#define DCTZ_GPU_ESTALE (-6)      /* compress_known_stats: the data's true max|x| gives another scaling factor */
 
 #define DCTZ_GPU_BLK 64    /* BLK_SZ, dctz.h:28 */
 #define DCTZ_GPU_NBINS 255 /* NBINS,  dctz.h:66 */
@@ -64,7 +65,7 @@ typedef struct dctz_gpu_info {
   uint64_t n_edge;     /* coefficients at ordinal 255 (item == range_max): the reference indexes
                           conv_tbl[255] out of bounds; we clamp to ordinal 254 and count (double
                           path only)                                                 */
-  uint64_t n_exact_path; /* reserved (always 0): the quantiser no longer has a slow path                  */
+  uint64_t n_exact_path; /* 1 if compress_known_stats found the statistics stale (status ESTALE), else 0     */
   uint64_t n_qt_dropped; /* QT: rescaled outliers that fell back inside the bin range and are
                             therefore not stored (dctz-comp-lib.c:494-506 quirk)                     */
   int32_t status;      /* 0, or DCTZ_GPU_EDEGENERATE                                                */
@@ -140,6 +141,20 @@ int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t 
                           double error_bound, int mode_qt, const double *d_stats_all, int nranks,
                           int first_slab, uint8_t *d_bin_index, float *d_DC, float *d_AC_exact,
                           void *d_qtable_raw, dctz_gpu_info *d_info, void *stream);
+
+/* Phase 2 WITHOUT phase 1: the statistics in d_stats_all are the caller's belief -- the previous time step of a
+ * simulation, a sample, an analytic bound -- not a pass over this data.  Same arguments and outputs as
+ * dctz_gpu_compress_dev, one read of the input instead of two.  While compressing, the kernel tracks the true
+ * max|x| of the slab and verifies that it lies in the decade the scaling factor was derived from
+ * (sf = 10^(ceil(log10 max)-1), util.c:28): on success d_info->max_abs is the slab's true maximum and the result is
+ * exactly what phases 1+2 would have produced (d_info->sum / mean are the caller's); otherwise d_info->status =
+ * DCTZ_GPU_ESTALE, the outputs are to be discarded and the caller runs dctz_gpu_stats_dev + dctz_gpu_compress_dev.
+ * With several ranks only "max < upper limit" is checked per slab; that the GLOBAL maximum reaches the decade's
+ * lower limit is the caller's check on the exchanged d_info->max_abs values.                            */
+int dctz_gpu_compress_known_stats_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype,
+                                      double error_bound, int mode_qt, const double *d_stats_all, int nranks,
+                                      int first_slab, uint8_t *d_bin_index, float *d_DC, float *d_AC_exact,
+                                      void *d_qtable_raw, dctz_gpu_info *d_info, void *stream);
 
 /* Phase 3 (QT only): d_qtable_raw now holds the GLOBAL maxima (after the caller's all-reduce;
  * entry 0 = DC of the field's last block).  Writes the clamped table to d_qtable, rescales the

@@ -223,3 +223,46 @@ def test_more_elements_than_int32(ctx):
     assert np.array_equal(bins[start:].cpu().numpy(), o["bin_index"])
     assert np.allclose(dc[start // 64:].cpu().numpy(), o["dc"], rtol=2e-7, atol=0)
     assert np.allclose(ac[i["n_outliers"] - k_tail: i["n_outliers"]].cpu().numpy(), o["ac"], rtol=2e-7, atol=0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_compress_with_known_statistics_is_verified(ctx, dtype):
+    """dctz_gpu_compress_known_stats_dev: one read of the input, scaling factor from the caller's statistics (here:
+    the previous 'time step'), verified against the true max|x| while compressing."""
+    code = DOUBLE if dtype == np.float64 else FLOAT
+    s = torch.cuda.current_stream().cuda_stream
+    x_prev = (fields.small_cases(dtype)["tail32"]).astype(dtype)            # max ~ 7.03 -> sf = 1
+    n = x_prev.size
+    d_prev = _dev(x_prev)
+    stats = torch.zeros(3, dtype=torch.float64, device="cuda")
+    ctx.stats_dev(d_prev.data_ptr(), n, code, stats.data_ptr(), s)
+
+    def run(x, n_total=None):
+        d = _dev(x)
+        o = dict(bins=torch.empty(n, dtype=torch.uint8, device="cuda"), dc=torch.empty((n + 63) // 64, dtype=torch.float32, device="cuda"),
+                 ac=torch.empty(n, dtype=torch.float32, device="cuda"), info=torch.zeros(binding.INFO_BYTES, dtype=torch.uint8, device="cuda"))
+        ctx.compress_known_stats_dev(d.data_ptr(), n, n_total or n, code, 1e-3, False, stats.data_ptr(), 1, True, o["bins"].data_ptr(),
+                                     o["dc"].data_ptr(), o["ac"].data_ptr(), 0, o["info"].data_ptr(), s)
+        torch.cuda.synchronize()
+        o["i"] = _info(o["info"])
+        return o
+
+    # (a) the next time step stays in the same decade: verified, and bit-identical to the two-pass result
+    x_next = (x_prev * dtype(1.01)).astype(dtype)
+    o = run(x_next)
+    want = ctx.compress_core(x_next, 1e-3)
+    assert o["i"]["status"] == 0 and o["i"]["n_exact_path"] == 0 and o["i"]["sf"] == want["sf"]
+    assert o["i"]["max_abs"] == float(np.max(np.abs(x_next)))  # the TRUE maximum, not the caller's
+    k = o["i"]["n_outliers"]
+    assert np.array_equal(o["bins"].cpu().numpy(), want["bin_index"]) and np.array_equal(o["dc"].cpu().numpy(), want["dc"])
+    assert k == want["ac"].size and np.array_equal(o["ac"][:k].cpu().numpy(), want["ac"])
+    # (b) the field grew into the next decade: flagged
+    assert run((x_prev * dtype(20.0)).astype(dtype))["i"]["status"] == -6
+    # (c) it shrank below the decade: flagged for a whole field, left to the caller for a slab of a larger field
+    small = (x_prev * dtype(0.05)).astype(dtype)
+    assert run(small)["i"]["status"] == -6
+    assert run(small, n_total=4 * n)["i"]["status"] == 0
+    # (d) the maximum sits in the partial tail block only
+    spike = x_next.copy()
+    spike[-3] = dtype(55.0)
+    assert run(spike)["i"]["status"] == -6
