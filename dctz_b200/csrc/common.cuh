@@ -211,16 +211,15 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // rejected: every warp tile has to wait for all earlier tiles to be counted, which turns the
 // persistent kernel into an in-order pipeline that runs at the pace of its slowest warp (2.5-6x
 // slower than the same kernel without the chain; profiles/README.md).  Instead:
-//   compress:   K2 writes each block's outliers, straight from registers, to the block's run of a
-//               tile-strided scratch slot (TILE_SLOT floats per tile) plus the block / tile counts; k_scan_groups turns the counts into
+//   compress:   K2 writes each tile's outliers, packed in their final order, to a tile-strided scratch
+//               slot (TILE_SLOT floats per tile) plus the tile's count; k_scan_groups turns the counts into
 //               exclusive prefixes per group of 32 tiles; k_gather moves the runs to their final
 //               place (8 bytes of traffic per outlier -- nothing when there are none);
 //   decompress: k_count_bins counts the 255 markers per tile (1 byte/element of extra reads), the
 //               same scan follows, and K3 starts every tile with its offset already known.
 // No kernel ever waits for another warp.
 // ------------------------------------------------------------------------------------------
-constexpr int TILE_SLOT = 2048;  // scratch entries per warp tile: 32 runs (one per block) of
-constexpr int LANE_SLOT = 64;    // LANE_SLOT entries each (a block has at most 63 outliers)
+constexpr int TILE_SLOT = 2048;  // scratch entries per warp tile (>= 63 * 32 = 2016 outliers worst case), packed in final order
 
 // Control block shared by all CTAs of a persistent kernel.
 struct TileControl {

@@ -352,17 +352,16 @@ static int check_common(dctz_gpu_ctx *ctx, int datatype, double eb) {
 }
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
-struct ScanBufs { unsigned *counts; uint8_t *blk_counts; ScanOut out; unsigned nchunks; };
+struct ScanBufs { unsigned *counts; ScanOut out; unsigned nchunks; };
 static size_t up128(size_t v) { return (v + 127) / 128 * 128; }
 static int scan_bufs(dctz_gpu_ctx *ctx, size_t n_entries, ScanBufs *sb) {
   const size_t ngroups = (n_entries + 31) / 32, nchunks = (ngroups + 1023) / 1024;
-  TRY(grow(ctx, ctx->status, up128(ngroups * 8) + up128(nchunks * 8) + up128(n_entries * 4) + n_entries * WTILE));
+  TRY(grow(ctx, ctx->status, up128(ngroups * 8) + up128(nchunks * 8) + up128(n_entries * 4)));
   char *p = (char *)ctx->status.p;
   sb->out.group_prefix = (unsigned long long *)p;
   sb->out.chunk_prefix = (unsigned long long *)(p + up128(ngroups * 8));
   sb->out.done = ctx->d_done + 1;
   sb->counts = (unsigned *)(p + up128(ngroups * 8) + up128(nchunks * 8));  // 16-byte aligned for the uint4 loads
-  sb->blk_counts = (uint8_t *)((char *)sb->counts + up128(n_entries * 4));
   sb->nchunks = (unsigned)nchunks;
   return DCTZ_GPU_OK;
 }
@@ -469,11 +468,11 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     fused.total = &d_info->n_outliers;
     fused.n_entries = (rem == 0 && (n_entries + 31) / 32 <= 1024) ? (unsigned)n_entries : 0u;  // small field: the last CTA scans
     if (verify)
-      k_compress<T, QT, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts, sb.blk_counts,
+      k_compress<T, QT, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts,
                                                                      ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0],
                                                                      d_info, fused, verify_lower);
     else
-      k_compress<T, QT, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts, sb.blk_counts,
+      k_compress<T, QT, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts,
                                                                       ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0],
                                                                       d_info, fused, 0);
     ctx->launches++;
@@ -481,7 +480,7 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
   }
   if (rem) {
     k_tail_compress<T, QT><<<1, 32, 0, st>>>(d_in + nblk_full * BLK, rem, nblk_full, (unsigned)ntiles, ctx->d_params, qc, d_bins, d_dc,
-                                             sb.counts, sb.blk_counts, ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, d_info, verify, verify_lower);
+                                             sb.counts, ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, d_info, verify, verify_lower);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -492,7 +491,7 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
   if (!QT) {
     const size_t want = (n_entries + 7) / 8;
     const int grid = (int)(want < (size_t)ctx->sm_count * 16 ? want : (size_t)ctx->sm_count * 16);
-    k_gather_ec<<<grid, 256, 0, st>>>(sb.counts, sb.blk_counts, sb.out.group_prefix, sb.out.chunk_prefix, (unsigned)n_entries, ac_slots, d_ac);
+    k_gather_ec<<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, (unsigned)n_entries, ac_slots, d_ac);
     ctx->launches++;
   }
   CU(cudaGetLastError());
@@ -560,9 +559,9 @@ static int launch_qt_finish(dctz_gpu_ctx *ctx, double eb, const T *d_qraw, T *d_
   TRY(scan_bufs(ctx, n_entries, &sb));  // same layout as in the compress call: nothing is reallocated
   const size_t want = ((size_t)n_entries + 7) / 8;
   const int grid = (int)(want < (size_t)ctx->sm_count * 16 ? (want ? want : 1) : (size_t)ctx->sm_count * 16);
-  k_qt_gather<T><<<grid, 256, 0, st>>>(sb.counts, sb.blk_counts, sb.out.group_prefix, sb.out.chunk_prefix, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p,
+  k_qt_gather<T><<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p,
                                        d_qraw, d_qtable, k, d_ac, d_info);
-  k_qt_compact<T><<<1, 32, 0, st>>>(sb.blk_counts, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, k, d_ac, d_info);
+  k_qt_compact<T><<<1, 32, 0, st>>>(sb.counts, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, k, d_ac, d_info);
   ctx->launches += 2;
   CU(cudaGetLastError());
   return DCTZ_GPU_OK;

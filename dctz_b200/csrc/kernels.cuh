@@ -477,8 +477,7 @@ __global__ void __launch_bounds__(CompressCfg<T, QT>::THREADS, CompressCfg<T, QT
 k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_full, const DevParams *__restrict__ params,
            QuantConsts<T> qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
            unsigned *__restrict__ counts,                     // outliers per warp tile
-           uint8_t *__restrict__ blk_counts,                  // outliers per block (32 per tile slot)
-           float *__restrict__ ac_slots,                      // EC: outlier scratch, TILE_SLOT per tile, LANE_SLOT per block
+           float *__restrict__ ac_slots,                      // EC: outlier scratch, TILE_SLOT entries per tile, packed
            T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
            typename BitsOf<T>::U *qmax_bits,                  // QT: 64 per-position maxima (bit patterns), entries 1..63
            T *qtable0,                                        // QT: entry 0 of the same table: the last full block's DC
@@ -591,11 +590,10 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     cnt -= 1;  // the DC marker
     if (!active) cnt = 0;
 
-    unsigned tile_total = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tile_total += __shfl_xor_sync(FULL, tile_total, o);
+    const unsigned incl = warp_inclusive_scan(cnt, lane);
+    const unsigned tile_total = __shfl_sync(FULL, incl, 31);
+    const unsigned my_off = incl - cnt;  // this block's first outlier inside the tile's run
     if (lane == 0) counts[cur] = tile_total;
-    blk_counts[(unsigned long long)cur * WTILE + lane] = (uint8_t)cnt;
 
     // ---- bin ids: one bulk store per tile; DC ----
     fence_async_smem();
@@ -610,11 +608,15 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
       if (QT && blk == nblk_full - 1) *qtable0 = dcs;  // :357/:359 (a later tail block overwrites it)
     }
 
-    // ---- outliers (dctz-comp-lib.c:478-544): each lane appends its block's outliers, in ascending j, to the
-    //      block's own run of the tile slot; k_gather_* puts the runs in order ----
+    // ---- outliers (dctz-comp-lib.c:478-544): each lane writes its block's outliers, in ascending j, at the block's
+    //      offset inside the tile's slot, so the slot holds the tile's outliers packed in their final order;
+    //      k_gather_* only has to move whole tile runs ----
     if (tile_total != 0) {
-      const unsigned long long run = (unsigned long long)cur * TILE_SLOT + (unsigned)lane * LANE_SLOT;
-      const unsigned *wrow = reinterpret_cast<const unsigned *>(binbuf + lane * BLK);
+      const unsigned long long run = (unsigned long long)cur * TILE_SLOT + my_off;
+      uint4 wv[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; q4++) wv[q4] = brow[q4];  // the block's 64 bin ids back from shared memory (4 x 128-bit)
+      const unsigned *wrow = reinterpret_cast<const unsigned *>(wv);
       if constexpr (QT) {  // raw coefficient + position, rescaled by K2b once the global qtable is known
         unsigned pos = 0;
 #pragma unroll
@@ -754,7 +756,7 @@ template <typename T, bool QT>
 __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /* start of the tail block */, int rem,
                                                       unsigned long long blk_index, unsigned slot_tile,
                                                       const DevParams *params, QuantConsts<T> qc, uint8_t *bins,
-                                                      float *dc_out, unsigned *counts, uint8_t *blk_counts, float *ac_slots,
+                                                      float *dc_out, unsigned *counts, float *ac_slots,
                                                       T *raw_slots, uint8_t *j_slots, typename BitsOf<T>::U *qmax_bits,
                                                       T *qtable0, Info *info, int verify, int verify_lower) {
   __shared__ double xs[BLK];
@@ -813,7 +815,6 @@ __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /
   }
   edge = (unsigned)warp_sum((double)edge);
   if (lane == 0) { counts[slot_tile] = base; if (edge) info->n_edge += edge; }
-  blk_counts[(unsigned long long)slot_tile * WTILE + lane] = (uint8_t)(lane == 0 ? base : 0u);  // the block is run 0 of its slot
 }
 
 // ------------------------------------------------------------------------------------------
@@ -864,8 +865,7 @@ __global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *__restrict
   if (threadIdx.x == 0) { *total = carry; *out.done = 0u; }
 }
 
-// Gather: one warp per tile.  Lane l holds the count of block l of the tile; run l of the slot holds that
-// block's outliers.  The runs are copied, in block order, to the tile's final position
+// Gather: one warp per tile copies the tile's packed run to its final position
 // prefix_of_group + (totals of the earlier tiles of the group).
 __device__ __forceinline__ unsigned long long tile_base_of(const unsigned *__restrict__ counts,
                                                            const unsigned long long *__restrict__ group_prefix,
@@ -876,24 +876,18 @@ __device__ __forceinline__ unsigned long long tile_base_of(const unsigned *__res
   return prefix_of_group(group_prefix, chunk_prefix, tile >> 5) + e;
 }
 
-__global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ counts, const uint8_t *__restrict__ blk_counts,
-                                                   const unsigned long long *__restrict__ group_prefix,
+__global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
                                                    const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles,
                                                    const float *__restrict__ ac_slots, float *__restrict__ ac_out) {
   const int lane = threadIdx.x & 31;
   const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
   for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += wpg) {
-    if (__ldg(counts + t) == 0) continue;
-    const unsigned c = __ldg(blk_counts + (unsigned long long)t * WTILE + lane);
-    const unsigned excl = warp_inclusive_scan(c, lane) - c;
+    const unsigned n = __ldg(counts + t);
+    if (n == 0) continue;
     float *dst = ac_out + tile_base_of(counts, group_prefix, chunk_prefix, t, lane);
     const float *src = ac_slots + (unsigned long long)t * TILE_SLOT;
-#pragma unroll 8
-    for (int s = 0; s < WTILE; s++) {
-      const unsigned n = __shfl_sync(0xFFFFFFFFu, c, s), off = __shfl_sync(0xFFFFFFFFu, excl, s);
-      if ((unsigned)lane < n) dst[off + lane] = __ldg(src + s * LANE_SLOT + lane);
-      if ((unsigned)lane + 32u < n) dst[off + lane + 32] = __ldg(src + s * LANE_SLOT + lane + 32);
-    }
+#pragma unroll 4
+    for (unsigned i = lane; i < n; i += 32) dst[i] = __ldg(src + i);
   }
 }
 
@@ -926,8 +920,7 @@ __device__ __forceinline__ bool qt_rescale_one(float item, float q, const QtCons
 
 // QT gather: rescale while moving to the final place.
 template <typename T>
-__global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ counts, const uint8_t *__restrict__ blk_counts,
-                                                   const unsigned long long *__restrict__ group_prefix,
+__global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
                                                    const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles,
                                                    const T *__restrict__ raw_slots, const uint8_t *__restrict__ j_slots,
                                                    const T *__restrict__ qraw /* global maxima, [0] = last DC */,
@@ -944,19 +937,14 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
   const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
   unsigned dropped = 0;
   for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += wpg) {
-    if (__ldg(counts + t) == 0) continue;
-    const unsigned c = __ldg(blk_counts + (unsigned long long)t * WTILE + lane);
-    const unsigned excl = warp_inclusive_scan(c, lane) - c;
+    const unsigned n = __ldg(counts + t);
+    if (n == 0) continue;
     float *dst = ac_out + tile_base_of(counts, group_prefix, chunk_prefix, t, lane);
     const unsigned long long src = (unsigned long long)t * TILE_SLOT;
-    for (int s = 0; s < WTILE; s++) {
-      const unsigned n = __shfl_sync(0xFFFFFFFFu, c, s), off = __shfl_sync(0xFFFFFFFFu, excl, s);
-      for (unsigned i = lane; i < n; i += 32) {
-        const unsigned long long e = src + s * LANE_SLOT + i;
-        float o;
-        if (!qt_rescale_one(raw_slots[e], qt[j_slots[e]], k, &o)) dropped++;
-        dst[off + i] = o;
-      }
+    for (unsigned i = lane; i < n; i += 32) {
+      float o;
+      if (!qt_rescale_one(raw_slots[src + i], qt[j_slots[src + i]], k, &o)) dropped++;
+      dst[i] = o;
     }
   }
   if (dropped) atomicAdd(&info->n_qt_dropped, (unsigned long long)dropped);
@@ -966,19 +954,19 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
 // (dctz-comp-lib.c:494-506: such a value is not stored although its bin index stays 255).  It is a
 // no-op unless that ever happens (it cannot for realistic data).
 template <typename T>
-__global__ void __launch_bounds__(32) k_qt_compact(const uint8_t *__restrict__ blk_counts, unsigned ntiles, const T *__restrict__ raw_slots,
+__global__ void __launch_bounds__(32) k_qt_compact(const unsigned *__restrict__ counts, unsigned ntiles, const T *__restrict__ raw_slots,
                                                    const uint8_t *__restrict__ j_slots, const T *__restrict__ qraw, QtConsts<T> k,
                                                    float *ac_out, Info *info) {
   if (info->n_qt_dropped == 0) return;  // the only path ever taken in practice
   if (threadIdx.x != 0) return;
   unsigned long long w = 0;
-  for (unsigned long long b = 0; b < (unsigned long long)ntiles * WTILE; b++) {
-    const unsigned long long run = (b / WTILE) * TILE_SLOT + (b % WTILE) * LANE_SLOT;
-    for (unsigned i = 0; i < blk_counts[b]; i++) {
-      T q = qraw[j_slots[run + i]];
-      if (j_slots[run + i] >= 1 && q < (T)1.0) q = (T)1.0;
+  for (unsigned t = 0; t < ntiles; t++) {
+    const unsigned long long slot = (unsigned long long)t * TILE_SLOT;
+    for (unsigned i = 0; i < counts[t]; i++) {
+      T q = qraw[j_slots[slot + i]];
+      if (j_slots[slot + i] >= 1 && q < (T)1.0) q = (T)1.0;
       float o;
-      if (qt_rescale_one(raw_slots[run + i], q, k, &o)) ac_out[w++] = o;
+      if (qt_rescale_one(raw_slots[slot + i], q, k, &o)) ac_out[w++] = o;
     }
   }
   info->n_outliers = w;
