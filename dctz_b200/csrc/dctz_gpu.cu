@@ -631,7 +631,7 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
     CUtensorMap tmap;
     TRY(make_tile_map(ctx, &tmap, d_out, BLK * sizeof(T), nblk_full));
     k_decompress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, tmap, sb.counts,
-                                                               sb.out.group_prefix, sb.out.chunk_prefix, &ctx->d_ctl[1]);
+                                                               sb.out.group_prefix, sb.out.chunk_prefix, ctx->d_nconsumed, &ctx->d_ctl[1]);
     ctx->launches++;
     CU(cudaGetLastError());
   }

@@ -1055,7 +1055,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
              const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
              const __grid_constant__ CUtensorMap tmap_out, const unsigned *__restrict__ counts,
              const unsigned long long *__restrict__ group_prefix, const unsigned long long *__restrict__ chunk_prefix,
-             TileControl *ctl) {
+             const unsigned long long *__restrict__ n_outliers_total, TileControl *ctl) {
   typedef typename ArithOf<T>::type A;
   typedef DecompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -1088,48 +1088,66 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     return left < (unsigned long long)WTILE ? (unsigned)left : (unsigned)WTILE;
   };
   // Outlier extent of a tile (warp-uniform): offset of its first outlier = scanned group prefix + the counts of
-  // the earlier tiles of its group; its size is the tile's count from k_count_bins.
+  // the earlier tiles of its group; its size is the tile's count from k_count_bins.  The loads (extent_load) and the
+  // warp reduction that consumes them (extent_finish) are a whole iteration apart, so their latency is never waited for.
   struct Extent { unsigned long long base; unsigned total; };
-  auto extent_of = [&](unsigned t) -> Extent {
+  struct ExtentRaw { unsigned long long gp; unsigned c; unsigned k; };
+  auto extent_load = [&](unsigned t) -> ExtentRaw {
+    ExtentRaw r;
+    r.k = t & 31u;
+    r.c = ((unsigned)lane <= r.k) ? __ldg(counts + (t & ~31u) + lane) : 0u;  // lanes < k: earlier tiles of the group; lane k: the tile
+    r.gp = prefix_of_group(group_prefix, chunk_prefix, t >> 5);
+    return r;
+  };
+  auto extent_finish = [&](const ExtentRaw &r) -> Extent {
     Extent e;
-    e.base = tile_base_of(counts, group_prefix, chunk_prefix, t, lane);
-    e.total = __ldg(counts + t);
+    e.total = __shfl_sync(FULL, r.c, (int)r.k);
+    unsigned before = ((unsigned)lane < r.k) ? r.c : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(FULL, before, o);
+    e.base = r.gp + before;
     return e;
   };
-  // Stage layout (PF): outlier i of the tile lives at stage[lead + i], lead = 4 - (elements up to the next 16-byte
-  // boundary of its global address), so that the 16-byte aligned middle of the run can be fetched by ONE bulk copy to
-  // stage + 16 bytes; the ragged head and tail (at most 3 elements each) are fetched by plain loads.
+  // Stage layout (PF): the stage mirrors the 16-byte granules of AC_exact that hold the tile's run: outlier i lives at
+  // stage[lead + i], lead = (elements between the previous 16-byte boundary and the run's first element), so ONE bulk
+  // copy of the aligned superset of the run fetches everything (up to 3 foreign floats on either side are copied and
+  // ignored).  Only where the superset would leave the array -- before AC_exact[0] when the array itself is not
+  // 16-byte aligned, or past the last outlier of the field -- the copy is clipped to whole granules inside the array
+  // and the at most 3 + 3 ragged elements are fetched by plain loads.
+  const unsigned long long n_ac = PF ? __ldg(n_outliers_total) : 0ull;
   auto lead_of = [&](const Extent &e) -> unsigned {
     if (!PF) return 0u;
-    const unsigned long long a = (unsigned long long)(uintptr_t)(ac_in + e.base);
-    return 4u - (unsigned)(((16u - (unsigned)(a & 15u)) & 15u) >> 2);
+    return (unsigned)(((unsigned long long)(uintptr_t)(ac_in + e.base) & 15ull) >> 2);
   };
-  // The ragged head / tail elements are LOADED when the tile's copies are issued and STORED to the stage only at
-  // the end of the iteration (park_ragged), so the global-load latency hides behind the inverse transform.
+  // The ragged elements are LOADED when the tile's copies are issued and STORED to the stage only at the end of the
+  // iteration (park_ragged), so the global-load latency hides behind the inverse transform.
   struct Ragged { float v; int idx; };
   auto issue_tile = [&](unsigned t, const Extent &e) -> Ragged {  // bin ids (2 KB) + DC (128 B) [+ outliers] of tile t
     const unsigned rows = rows_of(t);
     // the DC slice is 4*rows bytes: bulk copies need a multiple of 16, so partial tiles load DC directly
     const bool dc_bulk = (rows == WTILE);
-    unsigned head = 0, mid = 0, lead = 0;
-    if (PF) {
+    unsigned lead = 0, k0 = 0, k1 = 0, kend = 0;  // stage indices: bulk copy covers [k0, k1), the run is [lead, kend)
+    if (PF && e.total) {
       lead = lead_of(e);
-      head = (4u - lead) & 3u;
-      head = head < e.total ? head : e.total;
-      mid = ((e.total - head) * 4u) & ~15u;
+      kend = lead + e.total;
+      k0 = (e.base < (unsigned long long)lead) ? 4u : 0u;                                 // would start before AC_exact[0]
+      k1 = (kend + 3u) & ~3u;
+      if (e.base + (unsigned long long)(k1 - lead) > n_ac) k1 = kend & ~3u;               // would end past the last outlier
+      if (k1 < k0) k1 = k0;
     }
     if (lane == 0) {
-      mbar_expect_tx(mb, rows * BLK + (dc_bulk ? WTILE * 4 : 0) + mid);
+      mbar_expect_tx(mb, rows * BLK + (dc_bulk ? WTILE * 4 : 0) + (k1 - k0) * 4u);
       bulk_g2s(smem_u32(binbuf), bins + (unsigned long long)t * WTILE * BLK, rows * BLK, mb);
       if (dc_bulk) bulk_g2s(smem_u32(dcbuf), dc_in + (unsigned long long)t * WTILE, WTILE * 4, mb);
-      if (mid) bulk_g2s(smem_u32(stage) + 16u, ac_in + e.base + head, mid, mb);
+      if (k1 > k0) bulk_g2s(smem_u32(stage) + k0 * 4u, ac_in + e.base + k0 - lead, (k1 - k0) * 4u, mb);
     }
     Ragged r;
     r.v = 0.f; r.idx = -1;
-    if (PF) {
-      const unsigned tail0 = head + (mid >> 2);
-      if ((unsigned)lane < head) { r.idx = (int)(lead + lane); r.v = __ldg(ac_in + e.base + lane); }
-      else if (lane >= 8 && tail0 + (unsigned)(lane - 8) < e.total) { r.idx = (int)(lead + tail0 + (lane - 8)); r.v = __ldg(ac_in + e.base + tail0 + (lane - 8)); }
+    if (PF && e.total) {
+      const unsigned kh = lead + (unsigned)lane;         // head: stage indices lead .. k0-1 (k0 = 4 only)
+      const unsigned kt = k1 + (unsigned)(lane - 8);     // tail: stage indices k1 .. kend-1 (at most 3), lanes 8..10
+      if (kh < k0 && kh < kend) { r.idx = (int)kh; r.v = __ldg(ac_in + e.base + lane); }
+      else if (lane >= 8 && lane < 12 && kt < kend) { r.idx = (int)kt; r.v = __ldg(ac_in + e.base + (kt - lead)); }
     }
     return r;
   };
@@ -1140,22 +1158,30 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     return t;
   };
 
-  // Tickets run two tiles ahead (there is no ordering between tiles any more): `nxt` is known when an iteration
-  // starts, so its outlier extent can be looked up early and all of its loads issued as soon as the current
-  // tile's inputs are consumed.
+  // Tickets run three tiles ahead (there is no ordering between tiles): `nxt` and its outlier extent are known when an
+  // iteration starts, so all of its loads are issued as soon as the current tile's inputs are consumed; the counts
+  // behind the extent of the tile after it (`nn`) are loaded at the top of the iteration and reduced at its end.
   const unsigned nwarps_grid = gridDim.x * Cfg::WARPS;
   unsigned cur = blockIdx.x * Cfg::WARPS + warp;
-  Extent ext_cur;
+  unsigned nxt, nn;
+  {
+    unsigned t2 = 0;
+    if (lane == 0) t2 = atomicAdd(&ctl->ticket, 2u);
+    nxt = nwarps_grid + __shfl_sync(FULL, t2, 0);
+    nn = nxt + 1u;
+  }
+  Extent ext_cur, ext_nxt;
   ext_cur.base = 0; ext_cur.total = 0;
-  if (cur < ntiles) { ext_cur = extent_of(cur); park_ragged(issue_tile(cur, ext_cur)); }
-  unsigned nxt = nwarps_grid + __shfl_sync(FULL, take_ticket(), 0);
+  ext_nxt = ext_cur;
+  if (cur < ntiles) { ext_cur = extent_finish(extent_load(cur)); park_ragged(issue_tile(cur, ext_cur)); }
+  if (nxt < ntiles) ext_nxt = extent_finish(extent_load(nxt));
   unsigned phase = 0;
 
   while (cur < ntiles) {
     const unsigned pending = take_ticket();
-    Extent ext_nxt;
-    ext_nxt.base = 0; ext_nxt.total = 0;
-    if (nxt < ntiles) ext_nxt = extent_of(nxt);  // loads in flight; consumed after the rebuild below
+    ExtentRaw raw_nn;
+    raw_nn.gp = 0; raw_nn.c = 0; raw_nn.k = 0;
+    if (nn < ntiles) raw_nn = extent_load(nn);  // loads in flight for the whole iteration
     const unsigned rows = rows_of(cur);
     const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
     const bool active = (unsigned)lane < rows;
@@ -1198,19 +1224,29 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
       x[j] = center[id];  // entry 255 is a dummy, fixed below
     }
     if (cnt != 0) {
+      // eight coefficients at a time: the (predicated) stage loads first, the conversions after them, so the
+      // shared-memory latency is paid once per group and not once per outlier
       unsigned p = lead + my_off;
 #pragma unroll
-      for (int q = 0; q < 16; q++) {
-        unsigned m = ff_bytes(w[q]);
-        if (q == 0) m &= ~1u;
-        if (m) {
+      for (int g = 0; g < 8; g++) {
+        unsigned m0 = ff_bytes(w[2 * g]);
+        const unsigned m1 = ff_bytes(w[2 * g + 1]);
+        if (g == 0) m0 &= ~1u;  // the DC marker
+        if (m0 | m1) {
+          float a[8];
 #pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const int j = 4 * q + b;
-            if (j >= 1 && (m & (1u << (8 * b)))) {
-              const float a = stage[p++];  // :402-403
+          for (int b = 0; b < 8; b++) {
+            const bool hit = ((b < 4 ? m0 >> (8 * b) : m1 >> (8 * (b - 4))) & 1u) != 0u;
+            a[b] = 0.f;
+            if (hit) a[b] = stage[p++];  // :402-403
+          }
+#pragma unroll
+          for (int b = 0; b < 8; b++) {
+            const int j = 8 * g + b;
+            const bool hit = ((b < 4 ? m0 >> (8 * b) : m1 >> (8 * (b - 4))) & 1u) != 0u;
+            if (hit) {
               T v;
-              if (QT) v = qt_unscale_one(a, s_qt[j], qk); else v = (T)a;
+              if (QT) v = qt_unscale_one(a[b], s_qt[j], qk); else v = (T)a[b];
               x[j] = mul_rn<T>(v, sf);
             }
           }
@@ -1251,7 +1287,9 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     park_ragged(rag);
     cur = nxt;
     ext_cur = ext_nxt;
-    nxt = nwarps_grid + __shfl_sync(FULL, pending, 0);
+    nxt = nn;
+    ext_nxt = extent_finish(raw_nn);
+    nn = nwarps_grid + __shfl_sync(FULL, pending, 0);
   }
   bulk_wait_all();
   __syncthreads();
