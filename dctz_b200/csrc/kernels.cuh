@@ -1013,26 +1013,62 @@ __global__ void __launch_bounds__(256) k_count_bins(const uint8_t *__restrict__ 
 
 // ------------------------------------------------------------------------------------------
 // K3: dequantise + DCT-III + de-scale (dctz-decomp-lib.c:389-511).
-// Shared memory: [ centre table 256 T ] + per warp [ tile: swizzled slabs ][ double: outlier stage 8 KB;
-// float: the stage aliases the tile ][ bin ids 2 KB ][ DC 128 B ]
+// Shared memory: static [ centre table 256 T ] + dynamic, per warp [ tile: swizzled slabs ][ outlier stage: 8 KB (double) /
+// 4 KB (float) ][ bin ids 2 KB ][ DC 128 B ]
 // ------------------------------------------------------------------------------------------
 template <typename T, bool QT> struct DecompressCfg {
   static constexpr int WARPS = 4;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int CTAS_PER_SM = (sizeof(T) == 8) ? 2 : 3;
-  // double: registers limit residency to 2 CTAs/SM anyway, so each warp affords its own outlier stage and the
-  // next tile's outliers are PREFETCHED by TMA together with its bin ids.  float: the stage aliases the tile
-  // (dead until the inverse transform writes it) so that 3 CTAs/SM stay resident; outliers are loaded late.
-  static constexpr bool PREFETCH = (sizeof(T) == 8);
-  static constexpr int STAGE_BYTES = PREFETCH ? 8192 : 0;      // 16 B lead-in + 63*32 floats + alignment slack
-  static constexpr int OFF_STAGE = PREFETCH ? WarpTile<T>::BYTES : 0;
-  static constexpr int OFF_BINS = WarpTile<T>::BYTES + STAGE_BYTES;
+  // Every warp has its own outlier stage: the next tile's outliers are PREFETCHED by TMA together with its bin ids.
+  // The stage holds FAST_MAX finished coefficients of type T (half of a tile's coefficients).  double: it also
+  // holds the raw floats of ANY tile (2048 >= 3 + 63*32).  float: a tile with more than FAST_MAX outliers does not
+  // fit (a bigger stage would cost the third resident CTA); such a tile loads its outliers late, into the tile
+  // buffer, which is dead until the inverse transform writes it.
+  static constexpr int FAST_MAX = 1024;
+  static constexpr int STAGE_BYTES = FAST_MAX * (int)sizeof(T);
+  static constexpr int OFF_STAGE = WarpTile<T>::BYTES;
+  static constexpr int OFF_BINS = OFF_STAGE + STAGE_BYTES;
   static constexpr int OFF_DC = OFF_BINS + WTILE * BLK;
   static constexpr int WARP_BYTES = ((OFF_DC + WTILE * 4 + 1023) / 1024) * 1024;  // tiles need 1 KB alignment (swizzle atom)
-  static constexpr int OFF_WARPS = 2048;                                         // centre table: 256 T
-  static constexpr int SMEM = OFF_WARPS + WARPS * WARP_BYTES + 1024;             // + slack to align the base
+  static constexpr int SMEM = WARPS * WARP_BYTES + 1024;                         // + slack to align the base (the centre table is static)
   static_assert(WarpTile<T>::BYTES >= 63 * WTILE * 4, "the tile must hold a full tile of outliers");
+  static_assert(sizeof(T) == 4 || STAGE_BYTES >= (3 + 63 * WTILE + 3) * 4, "double: the stage must hold a full tile of raw outliers");
 };
+
+// Rebuild one coefficient of a tile that has outliers: `idb` = bin id * sizeof(T) (byte offset into the centre table);
+// the marker 255 redirects the load to the lane's next finished outlier (`spd` = its shared address minus the
+// marker's table address) and advances it.  Five instructions, no branch, one load either way.
+__device__ __forceinline__ void pick_coefficient(double &x, unsigned &spd, unsigned idb /* by value: clobbered */, unsigned center_s) {
+  asm volatile(
+      "{\n.reg .pred q;\n.reg .u32 a;\n"
+      "setp.eq.u32 q, %2, 0x7f8;\n"
+      "@q add.u32 %2, %2, %1;\n"
+      "add.u32 a, %2, %3;\n"
+      "ld.shared.f64 %0, [a];\n"
+      "@q add.u32 %1, %1, 8;\n}\n"
+      : "=d"(x), "+r"(spd), "+r"(idb)
+      : "r"(center_s)
+      : "memory");
+}
+__device__ __forceinline__ void pick_coefficient(float &x, unsigned &spd, unsigned idb, unsigned center_s) {
+  asm volatile(
+      "{\n.reg .pred q;\n.reg .u32 a;\n"
+      "setp.eq.u32 q, %2, 0x3fc;\n"
+      "@q add.u32 %2, %2, %1;\n"
+      "add.u32 a, %2, %3;\n"
+      "ld.shared.f32 %0, [a];\n"
+      "@q add.u32 %1, %1, 4;\n}\n"
+      : "=f"(x), "+r"(spd), "+r"(idb)
+      : "r"(center_s)
+      : "memory");
+}
+// byte offset of bin id number b (0..3) of the word w in a table of T
+template <typename T> __device__ __forceinline__ unsigned id_offset(unsigned w, int b) {
+  constexpr int SH = (sizeof(T) == 8) ? 3 : 2;
+  constexpr unsigned MASK = 0xFFu << SH;
+  return (8 * b >= SH) ? ((w >> (8 * b - SH)) & MASK) : ((w << (SH - 8 * b)) & MASK);
+}
 
 __device__ __forceinline__ double qt_unscale_one(float acf, double q, const QtConsts<double> &k) {
   const double v = (double)acf;  // :402
@@ -1066,9 +1102,16 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  T *center = reinterpret_cast<T *>(smem);
-  unsigned char *wsm = smem + Cfg::OFF_WARPS + warp * Cfg::WARP_BYTES;
-  constexpr bool PF = Cfg::PREFETCH;
+  __shared__ __align__(16) T center[256];  // static: its address is an immediate of the lookups
+  unsigned char *wsm = smem + warp * Cfg::WARP_BYTES;
+  // EC: a tile's outliers are turned into coefficients (converted to T, times sf) ONCE, cooperatively and
+  // conflict-free, before the lanes pick them up -- the per-coefficient work of a lane is then a select between two
+  // shared-memory addresses (pick_coefficient).  double: the converted values need 8 bytes each, so the prefetched
+  // floats are put in the upper half of the stage and expanded in place from the bottom.  Tiles with more than
+  // FAST_MAX outliers (double) and QT tiles (whose outliers are rescaled with a per-position table entry,
+  // dctz-decomp-lib.c:404-409) take the per-lane conversion path.
+  constexpr bool WIDE = (sizeof(T) == 8);
+  constexpr unsigned FAST_MAX = (unsigned)Cfg::FAST_MAX;
   float *stage = reinterpret_cast<float *>(wsm + Cfg::OFF_STAGE);
   unsigned char *binbuf = wsm + Cfg::OFF_BINS;
   float *dcbuf = reinterpret_cast<float *>(wsm + Cfg::OFF_DC);
@@ -1108,16 +1151,22 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     e.base = r.gp + before;
     return e;
   };
-  // Stage layout (PF): the stage mirrors the 16-byte granules of AC_exact that hold the tile's run: outlier i lives at
-  // stage[lead + i], lead = (elements between the previous 16-byte boundary and the run's first element), so ONE bulk
-  // copy of the aligned superset of the run fetches everything (up to 3 foreign floats on either side are copied and
-  // ignored).  Only where the superset would leave the array -- before AC_exact[0] when the array itself is not
+  // Stage layout: the stage mirrors the 16-byte granules of AC_exact that hold the tile's run: outlier i lives at
+  // stage[fofs + lead + i], lead = (elements between the previous 16-byte boundary and the run's first element), so ONE
+  // bulk copy of the aligned superset of the run fetches everything (up to 3 foreign floats on either side are copied
+  // and ignored).  Only where the superset would leave the array -- before AC_exact[0] when the array itself is not
   // 16-byte aligned, or past the last outlier of the field -- the copy is clipped to whole granules inside the array
   // and the at most 3 + 3 ragged elements are fetched by plain loads.
-  const unsigned long long n_ac = PF ? __ldg(n_outliers_total) : 0ull;
-  auto lead_of = [&](const Extent &e) -> unsigned {
-    if (!PF) return 0u;
-    return (unsigned)(((unsigned long long)(uintptr_t)(ac_in + e.base) & 15ull) >> 2);
+  const unsigned long long n_ac = __ldg(n_outliers_total);
+  struct Plan { unsigned lead, kend, fofs; bool fits, prefetch; };  // warp-uniform, a function of the extent alone
+  auto plan_of = [&](const Extent &e) -> Plan {
+    Plan p;
+    p.lead = (unsigned)(((unsigned long long)(uintptr_t)(ac_in + e.base) & 15ull) >> 2);
+    p.kend = p.lead + e.total;
+    p.fits = p.kend <= FAST_MAX;
+    p.prefetch = e.total != 0u && (WIDE || p.fits);
+    p.fofs = (WIDE && !QT && p.fits) ? FAST_MAX : 0u;  // double EC: raw floats in the upper half, expanded downwards
+    return p;
   };
   // The ragged elements are LOADED when the tile's copies are issued and STORED to the stage only at the end of the
   // iteration (park_ragged), so the global-load latency hides behind the inverse transform.
@@ -1126,32 +1175,31 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     const unsigned rows = rows_of(t);
     // the DC slice is 4*rows bytes: bulk copies need a multiple of 16, so partial tiles load DC directly
     const bool dc_bulk = (rows == WTILE);
-    unsigned lead = 0, k0 = 0, k1 = 0, kend = 0;  // stage indices: bulk copy covers [k0, k1), the run is [lead, kend)
-    if (PF && e.total) {
-      lead = lead_of(e);
-      kend = lead + e.total;
-      k0 = (e.base < (unsigned long long)lead) ? 4u : 0u;                                 // would start before AC_exact[0]
-      k1 = (kend + 3u) & ~3u;
-      if (e.base + (unsigned long long)(k1 - lead) > n_ac) k1 = kend & ~3u;               // would end past the last outlier
+    const Plan pl = plan_of(e);
+    unsigned k0 = 0, k1 = 0;  // stage indices: the bulk copy covers [k0, k1), the run is [lead, kend)
+    if (pl.prefetch) {
+      k0 = (e.base < (unsigned long long)pl.lead) ? 4u : 0u;                                 // would start before AC_exact[0]
+      k1 = (pl.kend + 3u) & ~3u;
+      if (e.base + (unsigned long long)(k1 - pl.lead) > n_ac) k1 = pl.kend & ~3u;            // would end past the last outlier
       if (k1 < k0) k1 = k0;
     }
     if (lane == 0) {
       mbar_expect_tx(mb, rows * BLK + (dc_bulk ? WTILE * 4 : 0) + (k1 - k0) * 4u);
       bulk_g2s(smem_u32(binbuf), bins + (unsigned long long)t * WTILE * BLK, rows * BLK, mb);
       if (dc_bulk) bulk_g2s(smem_u32(dcbuf), dc_in + (unsigned long long)t * WTILE, WTILE * 4, mb);
-      if (k1 > k0) bulk_g2s(smem_u32(stage) + k0 * 4u, ac_in + e.base + k0 - lead, (k1 - k0) * 4u, mb);
+      if (k1 > k0) bulk_g2s(smem_u32(stage) + (pl.fofs + k0) * 4u, ac_in + e.base + k0 - pl.lead, (k1 - k0) * 4u, mb);
     }
     Ragged r;
     r.v = 0.f; r.idx = -1;
-    if (PF && e.total) {
-      const unsigned kh = lead + (unsigned)lane;         // head: stage indices lead .. k0-1 (k0 = 4 only)
+    if (pl.prefetch) {
+      const unsigned kh = pl.lead + (unsigned)lane;      // head: stage indices lead .. k0-1 (k0 = 4 only)
       const unsigned kt = k1 + (unsigned)(lane - 8);     // tail: stage indices k1 .. kend-1 (at most 3), lanes 8..10
-      if (kh < k0 && kh < kend) { r.idx = (int)kh; r.v = __ldg(ac_in + e.base + lane); }
-      else if (lane >= 8 && lane < 12 && kt < kend) { r.idx = (int)kt; r.v = __ldg(ac_in + e.base + (kt - lead)); }
+      if (kh < k0 && kh < pl.kend) { r.idx = (int)(pl.fofs + kh); r.v = __ldg(ac_in + e.base + lane); }
+      else if (lane >= 8 && lane < 12 && kt < pl.kend) { r.idx = (int)(pl.fofs + kt); r.v = __ldg(ac_in + e.base + (kt - pl.lead)); }
     }
     return r;
   };
-  auto park_ragged = [&](const Ragged &r) { if (PF && r.idx >= 0) stage[r.idx] = r.v; };
+  auto park_ragged = [&](const Ragged &r) { if (r.idx >= 0) stage[r.idx] = r.v; };
   auto take_ticket = [&]() -> unsigned {
     unsigned t = 0;
     if (lane == 0) t = atomicAdd(&ctl->ticket, 1u);
@@ -1206,27 +1254,67 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
 #pragma unroll
     for (int q = 0; q < 16; q++) cnt += __popc(ff_bytes(q == 0 ? (w[0] & 0xFFFFFF00u) : w[q]));  // position 0 is the DC marker
     const unsigned my_off = warp_inclusive_scan(cnt, lane) - cnt;
-    const unsigned lead = lead_of(ext_cur);
+    const Plan pl = plan_of(ext_cur);
 
-    if (!PF) {  // ---- stage this tile's outliers now (coalesced); the stage aliases the tile buffer ----
+    // ---- the tile's outliers: finished coefficients at rdy[0..total) (`ready`), or raw floats at raw[0..total) ----
+    bool ready = false;  // warp-uniform
+    const T *rdy = reinterpret_cast<const T *>(stage);
+    const float *raw = stage + pl.fofs + pl.lead;
+    if (!WIDE && ext_cur.total != 0u && !pl.fits) {
+      // float, more than FAST_MAX outliers: nothing was prefetched; load them now (coalesced) into the tile buffer
       if (lane == 0) bulk_wait_read();  // the previous tile's output has left shared memory
       __syncwarp();
-      for (unsigned i = lane; i < ext_cur.total; i += 32) stage[i] = __ldg(ac_in + ext_cur.base + i);
+      float *tb = reinterpret_cast<float *>(wsm);
+      if (QT) {
+        for (unsigned i = lane; i < ext_cur.total; i += 32) tb[i] = __ldg(ac_in + ext_cur.base + i);
+        raw = tb;
+      } else {
+        for (unsigned i = lane; i < ext_cur.total; i += 32) tb[i] = __fmul_rn(__ldg(ac_in + ext_cur.base + i), (float)sf);
+        rdy = reinterpret_cast<const T *>(tb);
+        ready = true;
+      }
       __syncwarp();
+    } else if (!QT && ext_cur.total != 0u && pl.fits) {
+      if constexpr (WIDE) {
+        // in-place expansion float -> double: batch b reads floats [32b, 32b+32) of the upper half and writes doubles
+        // [32b, 32b+32) from the bottom; a write only ever lands on floats of batches <= b (8i+8 <= 4096+4(32b+32)
+        // for i < 32b+32 <= 1024), which every lane has read once the batch's __syncwarp is passed.
+        T *dst = reinterpret_cast<T *>(stage);
+        for (unsigned i0 = 0; i0 < ext_cur.total; i0 += 32) {
+          const unsigned i = i0 + lane;
+          T v = (T)0;
+          if (i < ext_cur.total) v = mul_rn<T>((T)raw[i], sf);  // :402-403 and the de-scale
+          __syncwarp();
+          if (i < ext_cur.total) dst[i] = v;
+        }
+      } else {
+        float *f = stage + pl.lead;
+        for (unsigned i = lane; i < ext_cur.total; i += 32) f[i] = __fmul_rn(f[i], (float)sf);
+        rdy = reinterpret_cast<const T *>(f);
+      }
+      fence_async_smem();  // the stage was written through the generic proxy; TMA writes it next
+      __syncwarp();
+      ready = true;
     }
 
     // ---- rebuild coefficients (dctz-decomp-lib.c:392-416), already multiplied by sf ----
     T x[BLK];
     x[0] = mul_rn<T>((T)dcv, sf);  // :392
+    if (ready && ext_cur.total != 0) {
+      // marker 255 -> next finished outlier of this block, anything else -> its bin centre: one load either way
+      const unsigned center_s = smem_u32(center);
+      unsigned spd = smem_u32(rdy) + my_off * (unsigned)sizeof(T) - 255u * (unsigned)sizeof(T) - center_s;
 #pragma unroll
-    for (int j = 1; j < BLK; j++) {
-      const unsigned id = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-      x[j] = center[id];  // entry 255 is a dummy, fixed below
+      for (int j = 1; j < BLK; j++) pick_coefficient(x[j], spd, id_offset<T>(w[j >> 2], j & 3), center_s);
+    } else {
+#pragma unroll
+      for (int j = 1; j < BLK; j++)
+        x[j] = *reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(center) + id_offset<T>(w[j >> 2], j & 3));  // entry 255 is a dummy, fixed below
     }
-    if (cnt != 0) {
+    if (!ready && cnt != 0) {
       // eight coefficients at a time: the (predicated) stage loads first, the conversions after them, so the
       // shared-memory latency is paid once per group and not once per outlier
-      unsigned p = lead + my_off;
+      unsigned p = my_off;
 #pragma unroll
       for (int g = 0; g < 8; g++) {
         unsigned m0 = ff_bytes(w[2 * g]);
@@ -1238,7 +1326,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
           for (int b = 0; b < 8; b++) {
             const bool hit = ((b < 4 ? m0 >> (8 * b) : m1 >> (8 * (b - 4))) & 1u) != 0u;
             a[b] = 0.f;
-            if (hit) a[b] = stage[p++];  // :402-403
+            if (hit) a[b] = raw[p++];  // :402-403
           }
 #pragma unroll
           for (int b = 0; b < 8; b++) {
@@ -1262,10 +1350,8 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     dct64_inverse<A>(x);
 
     // ---- registers -> own row of the swizzled tile -> TMA tensor stores (rows beyond the field are clipped) ----
-    if (PF) {
-      if (lane == 0) bulk_wait_read();  // the previous tile's output has left shared memory
-      __syncwarp();
-    }
+    if (lane == 0) bulk_wait_read();  // the previous tile's output has left shared memory
+    __syncwarp();
 #pragma unroll
     for (int q = 0; q < L::SLABS; q++) {
 #pragma unroll

@@ -266,3 +266,40 @@ def test_compress_with_known_statistics_is_verified(ctx, dtype):
     spike = x_next.copy()
     spike[-3] = dtype(55.0)
     assert run(spike)["i"]["status"] == -6
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("qt", [False, True])
+def test_decompress_mixed_outlier_density_and_unaligned_outlier_array(ctx, dtype, qt):
+    """Tiles of every staging class in one field -- no outliers, a few, more than half of the coefficients, all of
+    them -- and the outlier array at every 4-byte phase of a 16-byte granule (the kernel fetches the aligned
+    superset of a tile's run and must clip it at both ends of the array)."""
+    rng = np.random.default_rng(99)
+    ntile = 40
+    amp = np.repeat(np.concatenate([[0.0, 0.0], np.geomspace(1e-3, 3.0, ntile - 6), [0.0, 5.0, 0.0, 5.0]]), 2048)
+    t = np.arange(amp.size)
+    x = (2.0 + np.sin(t / 300.0) * (t >= 4096) + amp * rng.standard_normal(amp.size)).astype(dtype)  # tiles 0, 1: constant
+    x = np.concatenate([x, x[:37]])  # ragged tail
+    eb = 1e-4
+    orc = reflib.oracle_compress(x, eb, qt, want_coef=False)
+    sf = orc["stat"]["sf"]
+    per_tile = (orc["bin_index"][: ntile * 2048].reshape(ntile, 2048) == 255).sum(axis=1) - 32
+    assert per_tile.min() == 0 and 0 < np.sum((per_tile > 0) & (per_tile < 1000)) and per_tile.max() > 1900, per_tile
+    want = reflib.oracle_decompress(orc["bin_index"], orc["dc"], orc["ac"], orc["qtable"], x.size, eb, sf, qt, np.dtype(dtype))
+    code = DOUBLE if dtype == np.float64 else FLOAT
+    tdt = torch.float64 if code == DOUBLE else torch.float32
+    s = torch.cuda.current_stream().cuda_stream
+    bins, dc = _dev(orc["bin_index"]), _dev(orc["dc"])
+    qtab = _dev(orc["qtable"].astype(dtype)) if qt else None
+    tol = (1e-12 if dtype == np.float64 else 1e-5) * float(np.max(np.abs(want))) * 8
+    for phase in range(4):
+        buf = torch.full((orc["ac"].size + 8,), float("nan"), dtype=torch.float32, device="cuda")  # NaN guards on both sides
+        ac = buf[phase:phase + orc["ac"].size]
+        ac.copy_(torch.from_numpy(orc["ac"]))
+        out = torch.empty(x.size, dtype=tdt, device="cuda")
+        ctx.decompress_dev(bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), qtab.data_ptr() if qt else 0, x.size, code, eb, sf, qt,
+                           out.data_ptr(), s)
+        got = out.cpu().numpy()
+        assert np.all(np.isfinite(got)), f"phase {phase}: a guard value leaked into the reconstruction"
+        diff = float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64))))
+        assert diff <= tol, (phase, diff, tol)
