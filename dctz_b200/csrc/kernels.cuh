@@ -524,17 +524,16 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     return t;  // valid in lane 0 only; broadcast when consumed
   };
 
-  // The first tile of every warp is its global warp index; later tiles come from the ticket counter
-  // (which therefore starts at the number of warps).  A ticket is taken when the warp starts waiting for
-  // its current tile, so tiles t-1 and t are always picked up at about the same time by two warps that
-  // are at the same point of their loop: the look-back below never waits long.
+  // The first tile of every warp is its global warp index; later tiles are number-of-warps + a ticket from the
+  // shared counter (dynamic scheduling: a warp that drew tiles full of outliers simply takes fewer of them).
   const unsigned nwarps_grid = gridDim.x * Cfg::WARPS;
   unsigned cur = blockIdx.x * Cfg::WARPS + warp;
   if (cur < ntiles) issue_tile(cur);
-  unsigned phase = 0;
+  unsigned nxt = nwarps_grid + __shfl_sync(FULL, take_ticket(), 0);  // tickets run two tiles ahead: the atomic's
+  unsigned phase = 0;                                                // round trip has a whole iteration to complete
 
   while (cur < ntiles) {
-    const unsigned pending = take_ticket();  // latency overlaps the wait for the tile
+    const unsigned pending = take_ticket();
     mbar_wait(mb, phase);
     phase ^= 1u;
     T x[BLK];
@@ -549,7 +548,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
       }
     }
     __syncwarp();                        // every lane holds its row in registers
-    const unsigned nxt = nwarps_grid + __shfl_sync(FULL, pending, 0);
     if (nxt < ntiles) issue_tile(nxt);   // refill the tile buffer; overlaps everything below
 
     const unsigned rows = rows_of(cur);
@@ -569,7 +567,7 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     if (lane == 0) bulk_wait_read();  // the previous tile's bin ids have left shared memory
     __syncwarp();
     uint4 *brow = reinterpret_cast<uint4 *>(binbuf + lane * BLK);
-    unsigned cnt = 0;
+    unsigned mlo = 0, mhi = 0;  // bit j: coefficient j is an outlier (bin id 255)
 #pragma unroll
     for (int q4 = 0; q4 < 4; q4++) {
       unsigned wq[4];
@@ -582,13 +580,15 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
           if (j == 0) continue;
           word |= qz.quantize(x[j]) << (8 * b);
         }
-        cnt += __popc(ff_bytes(word));
+        const unsigned nib = (ff_bytes(word) * 0x01020408u) >> 24;  // flag of byte b -> bit b
+        if (q4 < 2) mlo |= nib << (16 * q4 + 4 * k); else mhi |= nib << (16 * (q4 - 2) + 4 * k);
         wq[k] = word;
       }
       brow[q4] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
     }
-    cnt -= 1;  // the DC marker
-    if (!active) cnt = 0;
+    mlo &= ~1u;  // the DC marker is not an outlier
+    if (!active) { mlo = 0; mhi = 0; }
+    const unsigned cnt = __popc(mlo) + __popc(mhi);
 
     const unsigned incl = warp_inclusive_scan(cnt, lane);
     const unsigned tile_total = __shfl_sync(FULL, incl, 31);
@@ -613,21 +613,16 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     //      k_gather_* only has to move whole tile runs ----
     if (tile_total != 0) {
       const unsigned long long run = (unsigned long long)cur * TILE_SLOT + my_off;
-      uint4 wv[4];
-#pragma unroll
-      for (int q4 = 0; q4 < 4; q4++) wv[q4] = brow[q4];  // the block's 64 bin ids back from shared memory (4 x 128-bit)
-      const unsigned *wrow = reinterpret_cast<const unsigned *>(wv);
       if constexpr (QT) {  // raw coefficient + position, rescaled by K2b once the global qtable is known
         unsigned pos = 0;
 #pragma unroll
         for (int q = 0; q < 16; q++) {
-          unsigned m = ff_bytes(wrow[q]);
-          if (q == 0) m &= ~1u;  // the DC marker is not an outlier
-          if (m) {
+          const unsigned nib = ((q < 8 ? mlo >> (4 * q) : mhi >> (4 * (q - 8))) & 0xFu);
+          if (nib) {
 #pragma unroll
             for (int b = 0; b < 4; b++) {
               const int j = 4 * q + b;
-              if (j >= 1 && (m & (1u << (8 * b)))) {
+              if (j >= 1 && (nib & (1u << b))) {
                 const T c = qz.scaled(x[j]);
                 raw_slots[run + pos] = c;
                 j_slots[run + pos] = (uint8_t)j;
@@ -639,31 +634,32 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
         }
       } else {
         // Uniform, branch-free part: every lane parks all 63 scaled AC coefficients as float (:537, USE_TRUNCATE) in
-        // its own column of the candidate array (conflict-free; register indices stay compile-time), and packs
-        // the outlier flags of its 64 bin ids into a bit mask.  Then a short loop over the set bits -- its trip
-        // count is the largest per-block count of the warp -- copies the outliers to the block's run.
+        // its own column of the candidate array (conflict-free; register indices stay compile-time).  Then a short
+        // loop over the set bits of the lane's outlier mask -- its trip count is the largest per-block count of the
+        // warp -- copies the outliers to the block's run.
         float *cand = reinterpret_cast<float *>(wsm + Cfg::OFF_CAND) + lane;
 #pragma unroll
         for (int j = 1; j < BLK; j++) cand[(j - 1) * WTILE] = qz.outlier(x[j]);
-        unsigned mlo = 0, mhi = 0;
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-          const unsigned nib = (ff_bytes(wrow[q]) * 0x01020408u) >> 24;  // flag of byte k -> bit k
-          if (q < 8) mlo |= nib << (4 * q); else mhi |= nib << (4 * (q - 8));
-        }
-        mlo &= ~1u;  // the DC marker is not an outlier
-        const unsigned trips = __reduce_max_sync(FULL, cnt);
-        float *dst = ac_slots + run;
+        // two independent chains per trip: the lowest remaining position goes to the front of the run, the highest
+        // to its back
+        const unsigned trips = (__reduce_max_sync(FULL, cnt) + 1u) >> 1;
+        float *lo = ac_slots + run, *hi = lo + cnt;
         for (unsigned it = 0; it < trips; it++) {
           if (mlo | mhi) {
             const int j = mlo ? (__ffs(mlo) - 1) : (31 + __ffs(mhi));
-            *dst++ = cand[(j - 1) * WTILE];
+            *lo++ = cand[(j - 1) * WTILE];
             if (mlo) mlo &= mlo - 1u; else mhi &= mhi - 1u;
+          }
+          if (mlo | mhi) {
+            const int j = mhi ? (63 - __clz(mhi)) : (31 - __clz(mlo));
+            *--hi = cand[(j - 1) * WTILE];
+            if (mhi) mhi &= ~(1u << (j - 32)); else mlo &= ~(1u << j);
           }
         }
       }
     }
     cur = nxt;
+    nxt = nwarps_grid + __shfl_sync(FULL, pending, 0);
   }
 
   // ---- epilogue ----
@@ -879,15 +875,43 @@ __device__ __forceinline__ unsigned long long tile_base_of(const unsigned *__res
 __global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
                                                    const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles,
                                                    const float *__restrict__ ac_slots, float *__restrict__ ac_out) {
-  const int lane = threadIdx.x & 31;
-  const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
-  for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += wpg) {
-    const unsigned n = __ldg(counts + t);
-    if (n == 0) continue;
-    float *dst = ac_out + tile_base_of(counts, group_prefix, chunk_prefix, t, lane);
-    const float *src = ac_slots + (unsigned long long)t * TILE_SLOT;
-#pragma unroll 4
-    for (unsigned i = lane; i < n; i += 32) dst[i] = __ldg(src + i);
+  // One CTA per GROUP of 32 tiles.  The group's outliers are one contiguous destination range; a thread takes the
+  // elements tid, tid + 256, ... of it, finds the tile each one comes from by a 5-step search of the group's scanned
+  // counts, and keeps four independent loads in flight -- the work is spread evenly whatever the per-tile counts
+  // are.  (A warp per tile was bound by the latency of its three dependent loads: 2.3 TB/s.)
+  __shared__ unsigned s_incl[32];
+  const unsigned ngroups = (ntiles + 31u) >> 5;
+  for (unsigned g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    if (threadIdx.x < 32) {
+      const unsigned t = g * 32u + threadIdx.x;
+      s_incl[threadIdx.x] = warp_inclusive_scan((t < ntiles) ? __ldg(counts + t) : 0u, (int)threadIdx.x);
+    }
+    __syncthreads();
+    const unsigned gtotal = s_incl[31];
+    if (gtotal != 0) {
+      float *gdst = ac_out + prefix_of_group(group_prefix, chunk_prefix, g);
+      const float *gsrc = ac_slots + (unsigned long long)g * 32u * TILE_SLOT;
+      for (unsigned e0 = 0; e0 < gtotal; e0 += 1024u) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const unsigned e = e0 + 256u * k + threadIdx.x;
+          v[k] = 0.f;
+          if (e < gtotal) {
+            unsigned t = 0;  // smallest t with s_incl[t] > e
+#pragma unroll
+            for (unsigned step = 16; step; step >>= 1) if (s_incl[t + step - 1] <= e) t += step;
+            v[k] = __ldg(gsrc + t * TILE_SLOT + (e - (t ? s_incl[t - 1] : 0u)));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const unsigned e = e0 + 256u * k + threadIdx.x;
+          if (e < gtotal) gdst[e] = v[k];
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
