@@ -228,6 +228,59 @@ struct TileControl {
   unsigned long long max_bits;  // VERIFY variant of K2: largest |x| bit pattern seen so far
 };
 
+// Keep the first USE of a long-latency result (a ticket atomic, a prefetched global load) where the source puts it:
+// the volatile move cannot be hoisted above the other volatile statements of the loop body (barrier waits, bulk
+// copies), so the consumer lands in the last basic block of the iteration instead of right behind the request --
+// where the warp would sit out the whole round trip.
+__device__ __forceinline__ unsigned pin_here(unsigned v) {
+  unsigned r;
+  asm volatile("mov.u32 %0, %1;\n" : "=r"(r) : "r"(v) : "memory");
+  return r;
+}
+__device__ __forceinline__ unsigned long long pin_here(unsigned long long v) {
+  unsigned long long r;
+  asm volatile("mov.u64 %0, %1;\n" : "=l"(r) : "l"(v) : "memory");
+  return r;
+}
+
+// Ticket counter increment by ONE lane.  atomicAdd() -- also as a bare PTX `atom.add` -- under `if (lane == 0)` is
+// turned by ptxas into the warp-aggregated form (leader election + atomic + SHFL of the result to the "other"
+// lanes): that shuffle consumes the atomic's result immediately and stalls the warp for the whole L2 round trip.
+// `atom.inc` (old + 1, wrapping at the bound) is not aggregated; with a bound no ticket ever reaches it is a plain increment (ptxas turns the bound 2^32-1 back into an add).
+__device__ __forceinline__ unsigned ticket_next(unsigned *counter) {
+  unsigned r;
+  asm volatile("atom.global.inc.u32 %0, [%1], 0xfffffff0;\n" : "=r"(r) : "l"(counter) : "memory");
+  return r;
+}
+
+// The sequence of tiles a warp works on: batches of `batch` consecutive tiles.  The first batch is the warp's own
+// index; later ones come from the shared ticket counter (dynamic scheduling: a warp that drew tiles full of outliers
+// simply takes fewer batches).  The ticket for the batch after the current one is requested when the current one
+// is entered, so the atomic's round trip has `batch` iterations to complete; and one atomic per `batch` tiles keeps
+// the single counter far from its throughput limit (at one ticket per tile a 2^30-element slab issues 375 M same-
+// address atomics per second -- measured: the whole kernel slows down by 25%).  Small fields use batch = 1.
+struct TileSeq {
+  unsigned next, end, pend, base, batch;
+  unsigned *counter;
+  __device__ __forceinline__ void init(unsigned *ticket_counter, unsigned warp_global, unsigned nwarps_grid, unsigned batch_, int lane) {
+    counter = ticket_counter;
+    batch = batch_;
+    base = nwarps_grid;
+    next = warp_global * batch;
+    end = next + batch;
+    pend = 0;
+    if (lane == 0) pend = ticket_next(counter);
+  }
+  __device__ __forceinline__ unsigned advance(int lane) {  // warp-uniform
+    if (next < end) return next++;
+    const unsigned start = (base + __shfl_sync(0xFFFFFFFFu, pin_here(pend), 0)) * batch;
+    if (lane == 0) pend = ticket_next(counter);
+    next = start + 1u;
+    end = start + batch;
+    return start;
+  }
+};
+
 // inclusive warp scan of one small count per lane
 __device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, int lane) {
 #pragma unroll

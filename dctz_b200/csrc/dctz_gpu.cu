@@ -352,6 +352,10 @@ static int check_common(dctz_gpu_ctx *ctx, int datatype, double eb) {
 }
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
+// Tiles per ticket (TileSeq, common.cuh): 4 once every warp has many batches to go through, 1 for small fields, where
+// whole batches would leave part of the grid without work.
+static unsigned tile_batch(size_t ntiles, size_t nwarps) { return ntiles >= 16 * nwarps ? 4u : 1u; }
+
 struct ScanBufs { unsigned *counts; ScanOut out; unsigned nchunks; };
 static size_t up128(size_t v) { return (v + 127) / 128 * 128; }
 static int scan_bufs(dctz_gpu_ctx *ctx, size_t n_entries, ScanBufs *sb) {
@@ -467,14 +471,15 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     fused.out = sb.out;
     fused.total = &d_info->n_outliers;
     fused.n_entries = (rem == 0 && (n_entries + 31) / 32 <= 1024) ? (unsigned)n_entries : 0u;  // small field: the last CTA scans
+    const unsigned batch = tile_batch(ntiles, (size_t)grid * Cfg::WARPS);
     if (verify)
       k_compress<T, QT, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts,
                                                                      ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0],
-                                                                     d_info, fused, verify_lower);
+                                                                     d_info, fused, verify_lower, batch);
     else
       k_compress<T, QT, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts,
                                                                       ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0],
-                                                                      d_info, fused, 0);
+                                                                      d_info, fused, 0, batch);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -631,7 +636,8 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
     CUtensorMap tmap;
     TRY(make_tile_map(ctx, &tmap, d_out, BLK * sizeof(T), nblk_full));
     k_decompress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, tmap, sb.counts,
-                                                               sb.out.group_prefix, sb.out.chunk_prefix, ctx->d_nconsumed, &ctx->d_ctl[1]);
+                                                               sb.out.group_prefix, sb.out.chunk_prefix, ctx->d_nconsumed, &ctx->d_ctl[1],
+                                                               tile_batch(ntiles, (size_t)grid * Cfg::WARPS));
     ctx->launches++;
     CU(cudaGetLastError());
   }

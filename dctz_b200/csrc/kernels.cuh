@@ -11,12 +11,12 @@
 //
 // Mapping: ONE THREAD OWNS ONE 64-ELEMENT BLOCK, all 64 values live in registers and go through
 // the generated straight-line transform (dct64_gen.cuh, 592 FP ops, no shuffles, no indexing).
-// The kernels are persistent and WARP-AUTONOMOUS: a warp takes a tile of 32 consecutive blocks from
-// an atomic ticket (fetched one iteration ahead), each lane's row arrives by one TMA bulk copy
-// (cp.async.bulk -> per-warp mbarrier) into a padded, bank-conflict-free shared-memory tile, and the
-// next tile's copy is issued as soon as the registers are loaded, so it overlaps the whole compute
-// phase.  There is no CTA-wide barrier inside the main loops; the ordered outlier offsets come from
-// a single-pass decoupled look-back scan over the warp tiles.
+// The kernels are persistent and WARP-AUTONOMOUS: a warp takes tiles of 32 consecutive blocks in batches
+// from an atomic ticket counter (TileSeq: requested a batch ahead), a tile arrives by TMA tensor copies
+// (-> per-warp mbarrier) into a 128-byte-swizzled, bank-conflict-free shared-memory tile, and the next
+// tile's copy is issued as soon as the registers are loaded, so it overlaps the whole compute phase.
+// There is no CTA-wide barrier inside the main loops and no waiting between warps: the ordered outlier
+// offsets come from per-tile counts + a scan kernel (common.cuh, "Ordered outlier compaction").
 #pragma once
 #include <cuda.h>  // CUtensorMap (type only; the encoder is fetched from the driver at run time)
 #include <type_traits>
@@ -481,7 +481,7 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
            T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
            typename BitsOf<T>::U *qmax_bits,                  // QT: 64 per-position maxima (bit patterns), entries 1..63
            T *qtable0,                                        // QT: entry 0 of the same table: the last full block's DC
-           TileControl *ctl, Info *info, FusedScan fused, int verify_lower) {
+           TileControl *ctl, Info *info, FusedScan fused, int verify_lower, unsigned batch) {
   typedef typename ArithOf<T>::type A;
   typedef CompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -518,22 +518,14 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
       for (int q = 0; q < L::SLABS; q++) tma_load_2d(tile_s + q * L::SLAB_BYTES, &tmap_in, q * 128, (int)(t * WTILE), mb);
     }
   };
-  auto take_ticket = [&]() -> unsigned {
-    unsigned t = 0;
-    if (lane == 0) t = atomicAdd(&ctl->ticket, 1u);
-    return t;  // valid in lane 0 only; broadcast when consumed
-  };
-
-  // The first tile of every warp is its global warp index; later tiles are number-of-warps + a ticket from the
-  // shared counter (dynamic scheduling: a warp that drew tiles full of outliers simply takes fewer of them).
-  const unsigned nwarps_grid = gridDim.x * Cfg::WARPS;
-  unsigned cur = blockIdx.x * Cfg::WARPS + warp;
+  TileSeq seq;
+  seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
+  unsigned cur = seq.advance(lane);
   if (cur < ntiles) issue_tile(cur);
-  unsigned nxt = nwarps_grid + __shfl_sync(FULL, take_ticket(), 0);  // tickets run two tiles ahead: the atomic's
-  unsigned phase = 0;                                                // round trip has a whole iteration to complete
+  unsigned nxt = seq.advance(lane);
+  unsigned phase = 0;
 
   while (cur < ntiles) {
-    const unsigned pending = take_ticket();
     mbar_wait(mb, phase);
     phase ^= 1u;
     T x[BLK];
@@ -659,7 +651,7 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
       }
     }
     cur = nxt;
-    nxt = nwarps_grid + __shfl_sync(FULL, pending, 0);
+    nxt = seq.advance(lane);
   }
 
   // ---- epilogue ----
@@ -1115,7 +1107,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
              const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
              const __grid_constant__ CUtensorMap tmap_out, const unsigned *__restrict__ counts,
              const unsigned long long *__restrict__ group_prefix, const unsigned long long *__restrict__ chunk_prefix,
-             const unsigned long long *__restrict__ n_outliers_total, TileControl *ctl) {
+             const unsigned long long *__restrict__ n_outliers_total, TileControl *ctl, unsigned batch) {
   typedef typename ArithOf<T>::type A;
   typedef DecompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -1224,24 +1216,14 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     return r;
   };
   auto park_ragged = [&](const Ragged &r) { if (r.idx >= 0) stage[r.idx] = r.v; };
-  auto take_ticket = [&]() -> unsigned {
-    unsigned t = 0;
-    if (lane == 0) t = atomicAdd(&ctl->ticket, 1u);
-    return t;
-  };
-
-  // Tickets run three tiles ahead (there is no ordering between tiles): `nxt` and its outlier extent are known when an
+  // Tiles are known three ahead (there is no ordering between tiles): `nxt` and its outlier extent are known when an
   // iteration starts, so all of its loads are issued as soon as the current tile's inputs are consumed; the counts
   // behind the extent of the tile after it (`nn`) are loaded at the top of the iteration and reduced at its end.
-  const unsigned nwarps_grid = gridDim.x * Cfg::WARPS;
-  unsigned cur = blockIdx.x * Cfg::WARPS + warp;
-  unsigned nxt, nn;
-  {
-    unsigned t2 = 0;
-    if (lane == 0) t2 = atomicAdd(&ctl->ticket, 2u);
-    nxt = nwarps_grid + __shfl_sync(FULL, t2, 0);
-    nn = nxt + 1u;
-  }
+  TileSeq seq;
+  seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
+  unsigned cur = seq.advance(lane);
+  unsigned nxt = seq.advance(lane);
+  unsigned nn = seq.advance(lane);
   Extent ext_cur, ext_nxt;
   ext_cur.base = 0; ext_cur.total = 0;
   ext_nxt = ext_cur;
@@ -1250,7 +1232,6 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   unsigned phase = 0;
 
   while (cur < ntiles) {
-    const unsigned pending = take_ticket();
     ExtentRaw raw_nn;
     raw_nn.gp = 0; raw_nn.c = 0; raw_nn.k = 0;
     if (nn < ntiles) raw_nn = extent_load(nn);  // loads in flight for the whole iteration
@@ -1303,13 +1284,18 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
         // in-place expansion float -> double: batch b reads floats [32b, 32b+32) of the upper half and writes doubles
         // [32b, 32b+32) from the bottom; a write only ever lands on floats of batches <= b (8i+8 <= 4096+4(32b+32)
         // for i < 32b+32 <= 1024), which every lane has read once the batch's __syncwarp is passed.
+        // (four batches per barrier: the same argument holds for the union of the batches)
         T *dst = reinterpret_cast<T *>(stage);
-        for (unsigned i0 = 0; i0 < ext_cur.total; i0 += 32) {
-          const unsigned i = i0 + lane;
-          T v = (T)0;
-          if (i < ext_cur.total) v = mul_rn<T>((T)raw[i], sf);  // :402-403 and the de-scale
+        for (unsigned i0 = 0; i0 < ext_cur.total; i0 += 128) {
+          float a[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const unsigned i = i0 + 32 * k + lane; a[k] = (i < ext_cur.total) ? raw[i] : 0.f; }
           __syncwarp();
-          if (i < ext_cur.total) dst[i] = v;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const unsigned i = i0 + 32 * k + lane;
+            if (i < ext_cur.total) dst[i] = mul_rn<T>((T)a[k], sf);  // :402-403 and the de-scale
+          }
         }
       } else {
         float *f = stage + pl.lead;
@@ -1398,8 +1384,10 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     cur = nxt;
     ext_cur = ext_nxt;
     nxt = nn;
+    raw_nn.c = pin_here(raw_nn.c);
+    raw_nn.gp = pin_here(raw_nn.gp);
     ext_nxt = extent_finish(raw_nn);
-    nn = nwarps_grid + __shfl_sync(FULL, pending, 0);
+    nn = seq.advance(lane);
   }
   bulk_wait_all();
   __syncthreads();
