@@ -496,7 +496,7 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
   if (!QT) {
     const size_t want = (n_entries + 31) / 32;  // one CTA per group of 32 tiles
     const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? want : (size_t)ctx->sm_count * 8);
-    k_gather_ec<<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, (unsigned)n_entries, ac_slots, d_ac);
+    k_gather_ec<<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, (unsigned)n_entries, ac_slots, d_ac, &d_info->n_outliers);
     ctx->launches++;
   }
   CU(cudaGetLastError());

@@ -866,44 +866,41 @@ __device__ __forceinline__ unsigned long long tile_base_of(const unsigned *__res
 
 __global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
                                                    const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles,
-                                                   const float *__restrict__ ac_slots, float *__restrict__ ac_out) {
+                                                   const float *__restrict__ ac_slots, float *__restrict__ ac_out,
+                                                   const unsigned long long *__restrict__ n_total) {
+  if (__ldg(n_total) == 0ull) return;  // nothing to move (the scan has counted)
   // One CTA per GROUP of 32 tiles.  The group's outliers are one contiguous destination range; a thread takes the
   // elements tid, tid + 256, ... of it, finds the tile each one comes from by a 5-step search of the group's scanned
-  // counts, and keeps four independent loads in flight -- the work is spread evenly whatever the per-tile counts
-  // are.  (A warp per tile was bound by the latency of its three dependent loads: 2.3 TB/s.)
-  __shared__ unsigned s_incl[32];
+  // counts (held one per lane, read by shuffles), and keeps four independent loads in flight -- the work is spread
+  // evenly whatever the per-tile counts are.  (A warp per tile was bound by the latency of its three dependent loads.)
+  const int lane = threadIdx.x & 31;
   const unsigned ngroups = (ntiles + 31u) >> 5;
   for (unsigned g = blockIdx.x; g < ngroups; g += gridDim.x) {
-    if (threadIdx.x < 32) {
-      const unsigned t = g * 32u + threadIdx.x;
-      s_incl[threadIdx.x] = warp_inclusive_scan((t < ntiles) ? __ldg(counts + t) : 0u, (int)threadIdx.x);
-    }
-    __syncthreads();
-    const unsigned gtotal = s_incl[31];
-    if (gtotal != 0) {
-      float *gdst = ac_out + prefix_of_group(group_prefix, chunk_prefix, g);
-      const float *gsrc = ac_slots + (unsigned long long)g * 32u * TILE_SLOT;
-      for (unsigned e0 = 0; e0 < gtotal; e0 += 1024u) {
-        float v[4];
+    const unsigned t0 = g * 32u + (unsigned)lane;
+    const unsigned incl = warp_inclusive_scan((t0 < ntiles) ? __ldg(counts + t0) : 0u, lane);  // every warp: the same 128 bytes
+    const unsigned gtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (gtotal == 0) continue;
+    float *gdst = ac_out + prefix_of_group(group_prefix, chunk_prefix, g);
+    const float *gsrc = ac_slots + (unsigned long long)g * 32u * TILE_SLOT;
+    for (unsigned e0 = 0; e0 < gtotal; e0 += 1024u) {  // warp-uniform trip count: the shuffles below are full-warp
+      float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const unsigned e = e0 + 256u * k + threadIdx.x;
-          v[k] = 0.f;
-          if (e < gtotal) {
-            unsigned t = 0;  // smallest t with s_incl[t] > e
+      for (int k = 0; k < 4; k++) {
+        const unsigned e = e0 + 256u * k + threadIdx.x;
+        unsigned t = 0;  // smallest t with incl[t] > e (e < gtotal; lanes past the end search too and are ignored)
 #pragma unroll
-            for (unsigned step = 16; step; step >>= 1) if (s_incl[t + step - 1] <= e) t += step;
-            v[k] = __ldg(gsrc + t * TILE_SLOT + (e - (t ? s_incl[t - 1] : 0u)));
-          }
-        }
+        for (unsigned step = 16; step; step >>= 1)
+          if (__shfl_sync(0xFFFFFFFFu, incl, (int)(t + step - 1)) <= e) t += step;
+        const unsigned before = __shfl_sync(0xFFFFFFFFu, incl, (int)((t ? t : 1u) - 1u));
+        v[k] = 0.f;
+        if (e < gtotal) v[k] = __ldg(gsrc + t * TILE_SLOT + (e - (t ? before : 0u)));
+      }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const unsigned e = e0 + 256u * k + threadIdx.x;
-          if (e < gtotal) gdst[e] = v[k];
-        }
+      for (int k = 0; k < 4; k++) {
+        const unsigned e = e0 + 256u * k + threadIdx.x;
+        if (e < gtotal) gdst[e] = v[k];
       }
     }
-    __syncthreads();
   }
 }
 
@@ -1150,12 +1147,13 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   // the earlier tiles of its group; its size is the tile's count from k_count_bins.  The loads (extent_load) and the
   // warp reduction that consumes them (extent_finish) are a whole iteration apart, so their latency is never waited for.
   struct Extent { unsigned long long base; unsigned total; };
-  struct ExtentRaw { unsigned long long gp; unsigned c; unsigned k; };
+  struct ExtentRaw { unsigned long long gp, cp; unsigned c; unsigned k; };  // loaded values, untouched until extent_finish
   auto extent_load = [&](unsigned t) -> ExtentRaw {
     ExtentRaw r;
     r.k = t & 31u;
     r.c = ((unsigned)lane <= r.k) ? __ldg(counts + (t & ~31u) + lane) : 0u;  // lanes < k: earlier tiles of the group; lane k: the tile
-    r.gp = prefix_of_group(group_prefix, chunk_prefix, t >> 5);
+    r.gp = __ldg(group_prefix + (t >> 5));
+    r.cp = __ldg(chunk_prefix + (t >> 15));  // prefix_of_group(), its addition left to extent_finish
     return r;
   };
   auto extent_finish = [&](const ExtentRaw &r) -> Extent {
@@ -1164,7 +1162,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     unsigned before = ((unsigned)lane < r.k) ? r.c : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(FULL, before, o);
-    e.base = r.gp + before;
+    e.base = r.gp + r.cp + before;
     return e;
   };
   // Stage layout: the stage mirrors the 16-byte granules of AC_exact that hold the tile's run: outlier i lives at
@@ -1233,7 +1231,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
 
   while (cur < ntiles) {
     ExtentRaw raw_nn;
-    raw_nn.gp = 0; raw_nn.c = 0; raw_nn.k = 0;
+    raw_nn.gp = 0; raw_nn.cp = 0; raw_nn.c = 0; raw_nn.k = 0;
     if (nn < ntiles) raw_nn = extent_load(nn);  // loads in flight for the whole iteration
     const unsigned rows = rows_of(cur);
     const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
@@ -1386,6 +1384,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     nxt = nn;
     raw_nn.c = pin_here(raw_nn.c);
     raw_nn.gp = pin_here(raw_nn.gp);
+    raw_nn.cp = pin_here(raw_nn.cp);
     ext_nxt = extent_finish(raw_nn);
     nn = seq.advance(lane);
   }
