@@ -270,7 +270,8 @@ def test_compress_with_known_statistics_is_verified(ctx, dtype):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("qt", [False, True])
-def test_decompress_mixed_outlier_density_and_unaligned_outlier_array(ctx, dtype, qt):
+@pytest.mark.parametrize("last_total", [1, 2, 3])
+def test_decompress_mixed_outlier_density_and_unaligned_outlier_array(ctx, dtype, qt, last_total):
     """Tiles of every staging class in one field -- no outliers, a few, more than half of the coefficients, all of
     them -- and the outlier array at every 4-byte phase of a 16-byte granule (the kernel fetches the aligned
     superset of a tile's run and must clip it at both ends of the array)."""
@@ -279,12 +280,21 @@ def test_decompress_mixed_outlier_density_and_unaligned_outlier_array(ctx, dtype
     amp = np.repeat(np.concatenate([[0.0, 0.0], np.geomspace(1e-3, 3.0, ntile - 6), [0.0, 5.0, 0.0, 5.0]]), 2048)
     t = np.arange(amp.size)
     x = (2.0 + np.sin(t / 300.0) * (t >= 4096) + amp * rng.standard_normal(amp.size)).astype(dtype)  # tiles 0, 1: constant
-    x = np.concatenate([x, x[:37]])  # ragged tail
+    # the field ends with constant tiles that carry 3, then 2, then `last_total` isolated outliers (single DCT basis
+    # functions): the last runs of the outlier array are shorter than a 16-byte granule, at every alignment
+    n64 = np.arange(64)
+    quiet = np.full(4 * 2048, 2.0)
+    for b, ks in ((40, (5, 9, 33)), (64 + 9, (3, 17)), (96 + 31, (1, 2, 60)[:last_total])):
+        for k in ks:
+            quiet[b * 64:(b + 1) * 64] += 0.3 * np.cos(np.pi * (2 * n64 + 1) * k / 128.0)
+    x = np.concatenate([x, quiet.astype(dtype), x[:37]])  # + ragged tail
     eb = 1e-4
     orc = reflib.oracle_compress(x, eb, qt, want_coef=False)
     sf = orc["stat"]["sf"]
     per_tile = (orc["bin_index"][: ntile * 2048].reshape(ntile, 2048) == 255).sum(axis=1) - 32
     assert per_tile.min() == 0 and 0 < np.sum((per_tile > 0) & (per_tile < 1000)) and per_tile.max() > 1900, per_tile
+    tail_tiles = (orc["bin_index"][ntile * 2048:(ntile + 4) * 2048].reshape(4, 2048) == 255).sum(axis=1) - 32
+    assert list(tail_tiles) == [0, 3, 2, last_total], tail_tiles
     want = reflib.oracle_decompress(orc["bin_index"], orc["dc"], orc["ac"], orc["qtable"], x.size, eb, sf, qt, np.dtype(dtype))
     code = DOUBLE if dtype == np.float64 else FLOAT
     tdt = torch.float64 if code == DOUBLE else torch.float32
