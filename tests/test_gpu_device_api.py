@@ -313,3 +313,50 @@ def test_decompress_mixed_outlier_density_and_unaligned_outlier_array(ctx, dtype
         assert np.all(np.isfinite(got)), f"phase {phase}: a guard value leaked into the reconstruction"
         diff = float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64))))
         assert diff <= tol, (phase, diff, tol)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("qt", [False, True])
+def test_decompress_fuzz_synthetic_streams(ctx, dtype, qt):
+    """Decoder-only fuzz: synthetic (bin_index, DC, AC_exact) streams with a random outlier density per warp tile
+    (none / a handful / half / all), random sizes around the tile and group boundaries, the outlier array at a random
+    4-byte phase -- against the oracle's decoder (dctz-decomp-lib.c:358-511)."""
+    rng = np.random.default_rng(4242 + (1 if qt else 0) + (2 if dtype == np.float32 else 0))
+    code = DOUBLE if dtype == np.float64 else FLOAT
+    tdt = torch.float64 if code == DOUBLE else torch.float32
+    s = torch.cuda.current_stream().cuda_stream
+    eb, sf = 1e-3, 10.0
+    for case in range(24):
+        nblk = int(rng.choice([1, 31, 32, 33, 64 * 32 - 1, 64 * 32 + 5, 3000, 5000]))
+        rem = int(rng.choice([0, 0, 1, 37, 63]))
+        n = nblk * 64 + rem
+        ntile = (nblk + 31) // 32
+        dens = rng.choice([0.0, 0.0, 2e-4, 2e-3, 0.05, 0.5, 0.9, 1.0], size=ntile)
+        if case % 6 == 0:
+            dens[:] = 0.0
+            dens[rng.integers(ntile)] = 2e-3  # a single tile with a few outliers
+        pm = np.repeat(dens, 2048)[: nblk * 64]
+        pm = np.concatenate([pm, np.full(rem, 0.3)])
+        bins = rng.integers(0, 255, size=n, dtype=np.uint8)
+        bins[rng.random(n) < pm] = 255
+        bins[::64] = 255  # the DC markers
+        n_out = int(np.count_nonzero(bins == 255)) - (nblk + (1 if rem else 0))
+        mag = 0.255 + rng.random(n_out) * 3.0
+        acv = (mag * rng.choice([-1.0, 1.0], size=n_out)).astype(np.float32)
+        dcv = (rng.standard_normal(nblk + (1 if rem else 0)) * 5).astype(np.float32)
+        qtab = (1.0 + rng.random(64) * 20).astype(dtype) if qt else None
+        want = reflib.oracle_decompress(bins, dcv, acv, qtab, n, eb, sf, qt, np.dtype(dtype))
+        phase = int(rng.integers(4))
+        buf = torch.full((n_out + 8,), float("nan"), dtype=torch.float32, device="cuda")
+        ac = buf[phase:phase + n_out]
+        if n_out:
+            ac.copy_(torch.from_numpy(acv))
+        out = torch.empty(n, dtype=tdt, device="cuda")
+        d_bins, d_dc, d_qt = _dev(bins), _dev(dcv), (_dev(qtab) if qt else None)  # (kept alive across the call)
+        ctx.decompress_dev(d_bins.data_ptr(), d_dc.data_ptr(), ac.data_ptr() if n_out else 0, d_qt.data_ptr() if qt else 0,
+                           n, code, eb, sf, qt, out.data_ptr(), s)
+        got = out.cpu().numpy()
+        assert np.all(np.isfinite(got)), f"case {case}: a guard value leaked (n={n}, outliers={n_out}, phase={phase})"
+        tol = (1e-12 if dtype == np.float64 else 1e-5) * float(np.max(np.abs(want))) * 8
+        diff = float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64))))
+        assert diff <= tol, (case, n, n_out, phase, diff, tol)
