@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--f32", action="store_true", help="c5-slab only: cast the slab to float (single-precision path)")
     ap.add_argument("--noise", type=float, default=0.0, help="c5-slab only: add Gaussian noise of this std (raw units) to study the outlier path")
     ap.add_argument("--no-outlier-leg", action="store_true", help="skip the extra (reported, not headline) measurement with ~5%% outliers")
+    ap.add_argument("--watchdog", type=int, default=1500, help="seconds after which a stuck run dumps every thread's Python stack to stderr and exits 3 (0 = off)")
     return ap.parse_args()
 
 
@@ -451,6 +452,30 @@ def main_ours(args):
         for h in (hx, hout, hb, hdc, hac):
             h.free()
 
+    # (every rank takes part: barrier + max over ranks -- hence before the other ranks leave)
+    # Reported beside the headline, never as it: compress with KNOWN statistics (those of the previous step, as a
+    # time-stepping simulation would have them) -- dctz_gpu_compress_known_stats_dev reads the input once and verifies
+    # the scaling factor on the fly.
+    known_leg = None
+    if args.workload == "c5-slab" and not qt:
+        evk = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for _ in range(2):
+            ctx.compress_known_stats_dev(x.data_ptr(), n, n_total, code, EB, False, stats_all.data_ptr(), world if slabbed else 1, first,
+                                         bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), qraw.data_ptr(), info_d.data_ptr(), sh)
+        barrier()
+        evk[0].record(stream)
+        for _ in range(5):
+            ctx.compress_known_stats_dev(x.data_ptr(), n, n_total, code, EB, False, stats_all.data_ptr(), world if slabbed else 1, first,
+                                         bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), qraw.data_ptr(), info_d.data_ptr(), sh)
+        evk[1].record(stream)
+        barrier()
+        tk = torch.tensor([evk[0].elapsed_time(evk[1]) / 5e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        ik = read_info()
+        known_leg = dict(compress_ms=1e3 * float(tk.item()), compress_gbs=world * n * es / 1e9 / float(tk.item()), verified=(ik["status"] == 0),
+                         note="statistics supplied by the caller (previous step) and verified in the kernel: one read of the input")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -542,29 +567,6 @@ def main_ours(args):
                            max_abs_err=float((out[:n2] - x2).abs().max().item()))
         del x2
 
-    # Reported beside the headline, never as it: compress with KNOWN statistics (those of the previous step, as a
-    # time-stepping simulation would have them) -- dctz_gpu_compress_known_stats_dev reads the input once and verifies
-    # the scaling factor on the fly.
-    known_leg = None
-    if args.workload == "c5-slab" and not qt:
-        evk = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        for _ in range(2):
-            ctx.compress_known_stats_dev(x.data_ptr(), n, n_total, code, EB, False, stats_all.data_ptr(), world if slabbed else 1, first,
-                                         bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), qraw.data_ptr(), info_d.data_ptr(), sh)
-        barrier()
-        evk[0].record(stream)
-        for _ in range(5):
-            ctx.compress_known_stats_dev(x.data_ptr(), n, n_total, code, EB, False, stats_all.data_ptr(), world if slabbed else 1, first,
-                                         bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), qraw.data_ptr(), info_d.data_ptr(), sh)
-        evk[1].record(stream)
-        barrier()
-        tk = torch.tensor([evk[0].elapsed_time(evk[1]) / 5e3], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
-        ik = read_info()
-        known_leg = dict(compress_ms=1e3 * float(tk.item()), compress_gbs=world * n * es / 1e9 / float(tk.item()), verified=(ik["status"] == 0),
-                         note="statistics supplied by the caller (previous step) and verified in the kernel: one read of the input")
-
     line = dict(metric=METRIC, value=gb_all / t_rt, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * t_rt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f64" if es == 8 else "f32", data="synthetic", config=workload_config(args, world),
@@ -590,4 +592,8 @@ if __name__ == "__main__":
     _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     sys.stdout = sys.stderr
+    if a.watchdog > 0:  # a hung collective or kernel must not sit on the GPU box until somebody else's timeout fires
+        import faulthandler
+
+        faulthandler.dump_traceback_later(a.watchdog, exit=True)
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
