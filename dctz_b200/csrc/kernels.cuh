@@ -888,36 +888,30 @@ __global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ 
                                                    const float *__restrict__ ac_slots, float *__restrict__ ac_out,
                                                    const unsigned long long *__restrict__ n_total) {
   if (__ldg(n_total) == 0ull) return;  // nothing to move (the scan has counted)
-  // One CTA per GROUP of 32 tiles.  The group's outliers are one contiguous destination range; a thread takes the
-  // elements tid, tid + 256, ... of it, finds the tile each one comes from by a 5-step search of the group's scanned
-  // counts (held one per lane, read by shuffles), and keeps four independent loads in flight -- the work is spread
-  // evenly whatever the per-tile counts are.  (A warp per tile was bound by the latency of its three dependent loads.)
-  const int lane = threadIdx.x & 31;
+  // One CTA per GROUP of 32 tiles: every warp scans the group's 32 counts itself (the same 128 bytes, one per lane; no
+  // shared memory, no barrier) and copies the packed runs of tiles warp, warp + 8, ... to their final place with up to
+  // eight independent loads in flight per lane.  (A warp per tile was bound by the latency of its three dependent
+  // loads; a flat element index with a per-element search of the scanned counts was bound by its instructions.)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned ngroups = (ntiles + 31u) >> 5;
   for (unsigned g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const unsigned t0 = g * 32u + (unsigned)lane;
-    const unsigned incl = warp_inclusive_scan((t0 < ntiles) ? __ldg(counts + t0) : 0u, lane);  // every warp: the same 128 bytes
-    const unsigned gtotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (gtotal == 0) continue;
+    const unsigned c = (t0 < ntiles) ? __ldg(counts + t0) : 0u;
+    const unsigned incl = warp_inclusive_scan(c, lane);
+    if (__shfl_sync(0xFFFFFFFFu, incl, 31) == 0u) continue;
     float *gdst = ac_out + prefix_of_group(group_prefix, chunk_prefix, g);
     const float *gsrc = ac_slots + (unsigned long long)g * 32u * TILE_SLOT;
-    for (unsigned e0 = 0; e0 < gtotal; e0 += 1024u) {  // warp-uniform trip count: the shuffles below are full-warp
-      float v[4];
+    for (int s = warp; s < 32; s += 8) {
+      const unsigned n = __shfl_sync(0xFFFFFFFFu, c, s);
+      const unsigned off = __shfl_sync(0xFFFFFFFFu, incl - c, s);
+      const float *src = gsrc + (unsigned)s * TILE_SLOT;
+      float *dst = gdst + off;
+      for (unsigned i0 = 0; i0 < n; i0 += 256u) {
+        float v[8];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const unsigned e = e0 + 256u * k + threadIdx.x;
-        unsigned t = 0;  // smallest t with incl[t] > e (e < gtotal; lanes past the end search too and are ignored)
+        for (int k = 0; k < 8; k++) { const unsigned i = i0 + 32u * k + lane; v[k] = (i < n) ? __ldg(src + i) : 0.f; }
 #pragma unroll
-        for (unsigned step = 16; step; step >>= 1)
-          if (__shfl_sync(0xFFFFFFFFu, incl, (int)(t + step - 1)) <= e) t += step;
-        const unsigned before = __shfl_sync(0xFFFFFFFFu, incl, (int)((t ? t : 1u) - 1u));
-        v[k] = 0.f;
-        if (e < gtotal) v[k] = __ldg(gsrc + t * TILE_SLOT + (e - (t ? before : 0u)));
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const unsigned e = e0 + 256u * k + threadIdx.x;
-        if (e < gtotal) gdst[e] = v[k];
+        for (int k = 0; k < 8; k++) { const unsigned i = i0 + 32u * k + lane; if (i < n) dst[i] = v[k]; }
       }
     }
   }
