@@ -41,3 +41,28 @@ def test_gpu_arm_refuses_to_run_without_a_device():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
                        timeout=300, cwd=ROOT)
     assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)
+
+
+def test_no_collective_after_the_other_ranks_have_left():
+    """main_ours() lets every rank but 0 leave once the timed region and the all-rank legs are done; a barrier or
+    collective further down would wait for ranks that are gone (this hung the N>1 runs once).  Static check: after
+    the `if rank != 0: ... return` statement no call mentions barrier() or the dist module except its teardown."""
+    import ast
+
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "main_ours")
+    leave = None
+    for i, st in enumerate(fn.body):
+        if (isinstance(st, ast.If) and isinstance(st.test, ast.Compare) and isinstance(st.test.left, ast.Name) and st.test.left.id == "rank"
+                and any(isinstance(x, ast.Return) for x in ast.walk(st))):
+            leave = i
+    assert leave is not None, "the rank != 0 exit was not found"
+    bad = []
+    for st in fn.body[leave + 1:]:
+        for call in (n for n in ast.walk(st) if isinstance(n, ast.Call)):
+            f = call.func
+            name = f.id if isinstance(f, ast.Name) else (f.attr if isinstance(f, ast.Attribute) else "")
+            owner = f.value.id if isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) else ""
+            if name == "barrier" or (owner == "dist" and name != "destroy_process_group"):
+                bad.append((call.lineno, f"{owner}.{name}" if owner else name))
+    assert not bad, f"collectives after the other ranks have left: {bad}"
