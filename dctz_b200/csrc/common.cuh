@@ -1,4 +1,4 @@
-// common.cuh -- arithmetic policies, exact division, look-back scan and staging helpers shared by
+// common.cuh -- arithmetic policies, exact division, TMA / mbarrier wrappers, tile scheduling and scan helpers shared by
 // the sm_100a kernels of the DCTZ hot path.
 #pragma once
 #include <cuda_runtime.h>
