@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / quality legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--f32", action="store_true", help="c5-slab only: cast the slab to float (single-precision path)")
+    ap.add_argument("--qt", action="store_true", help="c5-slab only, one GPU: quantiser (QT) mode instead of error-bounded (EC)")
     ap.add_argument("--noise", type=float, default=0.0, help="c5-slab only: add Gaussian noise of this std (raw units) to study the outlier path")
     ap.add_argument("--no-outlier-leg", action="store_true", help="skip the extra (reported, not headline) measurement with ~5%% outliers")
     ap.add_argument("--watchdog", type=int, default=1500, help="seconds after which a stuck run dumps every thread's Python stack to stderr and exits 3 (0 = off)")
@@ -198,14 +199,15 @@ def main_reference(args):
 def workload_config(args, world):
     if args.workload == "c5-slab":
         n = 1 << args.slab_log2
+        mode = "qt" if getattr(args, "qt", False) else "ec"
         if getattr(args, "f32", False):
-            return dict(workload=f"c5-slab-f32: per-GPU slab of 2^{args.slab_log2} floats (the {HASH_DIM}^3 field cast to float), EC, eb 1E-3",
-                        mode="ec", error_bound=EB, elements_per_gpu=n, block=64, l2="inputs larger than L2 (no flush needed)",
+            return dict(workload=f"c5-slab-f32: per-GPU slab of 2^{args.slab_log2} floats (the {HASH_DIM}^3 field cast to float), {mode.upper()}, eb 1E-3",
+                        mode=mode, error_bound=EB, elements_per_gpu=n, block=64, l2="inputs larger than L2 (no flush needed)",
                         parallelism=f"slab{world}")
         return dict(workload=f"c5-slab: per-GPU contiguous slab of 2^{args.slab_log2} doubles ({n * 8 / 2**30:.0f} GiB) of the "
-                             f"{HASH_DIM}^3 double field (BASELINE config[4]), EC mode, error bound 1E-3; "
+                             f"{HASH_DIM}^3 double field (BASELINE config[4]), {mode.upper()} mode, error bound 1E-3; "
                              f"{world} slab(s) = {world * n * 8 / 2**30:.0f} GiB",
-                    mode="ec", error_bound=EB, elements_per_gpu=n, block=64, l2="inputs larger than L2 (no flush needed)",
+                    mode=mode, error_bound=EB, elements_per_gpu=n, block=64, l2="inputs larger than L2 (no flush needed)",
                     parallelism=f"slab{world}")
     desc = {"c1": "config[0] CESM-ATM-shaped 1800x3600 double, EC", "c2": "config[1] 1800x3600 float, QT",
             "c3": "config[2] Hurricane-shaped 100x500x500 float, EC", "c4": "config[3] NYX-shaped 512^3 double, EC"}[args.workload]
@@ -308,7 +310,10 @@ def main_ours(args):
 
     # ---- workload resident in HBM -------------------------------------------------------------
     qt = False
+    if args.qt and (args.workload != "c5-slab" or world > 1):
+        raise SystemExit("bench.py: --qt applies to the c5-slab workload on one GPU (c2 is the QT config)")
     if args.workload == "c5-slab":
+        qt = bool(args.qt)
         n = 1 << args.slab_log2
         tdt, code, es = torch.float64, DOUBLE, 8
         x = torch.empty(n, dtype=tdt, device=dev)
@@ -532,7 +537,7 @@ def main_ours(args):
                        ratio=ns * es / zsz)
 
     outlier_leg = None
-    if world == 1 and args.workload == "c5-slab" and not args.f32 and args.noise == 0 and not args.no_outlier_leg:
+    if world == 1 and args.workload == "c5-slab" and not args.f32 and not qt and args.noise == 0 and not args.no_outlier_leg:
         # The headline field is smooth (no AC coefficient leaves the bin range).  Reported beside it, never as the
         # headline: the same slab shape with white noise added so that ~5 % of the coefficients are outliers.
         n2 = min(n, 1 << 28)

@@ -57,6 +57,7 @@ struct dctz_gpu_ctx {
   DevBuf slots;         // EC: tile-strided outlier scratch (TILE_SLOT floats per warp tile)
   DevBuf qt_raw, qt_j;  // QT: tile-strided un-rescaled outliers + their coefficient position
   unsigned qt_entries = 0;  // tiles (incl. the tail slot) of the last QT compress call
+  unsigned qt_tail_tile = 0xFFFFFFFFu;  // index of that tail slot (its raw values are scaled already), none = ~0
 
   // sf tables: host copies + device copies
   std::vector<double> thr_d, sfv_d;
@@ -218,8 +219,8 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->stat_grid = ctx->sm_count * 8;
   CU(cudaMalloc(&ctx->d_partials, sizeof(StatPartial) * ctx->stat_grid));
-  CU(cudaMalloc(&ctx->d_done, 4 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups, [2] k_quality, [3] k_count_bins
-  CU(cudaMemset(ctx->d_done, 0, 4 * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->d_done, 5 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups, [2] k_quality, [3] k_count_bins, [4] k_qt_max
+  CU(cudaMemset(ctx->d_done, 0, 5 * sizeof(unsigned)));
   CU(cudaMalloc(&ctx->d_stats3, 3 * sizeof(double)));
   CU(cudaMalloc(&ctx->d_params, sizeof(DevParams)));
   CU(cudaMalloc(&ctx->d_info, sizeof(Info)));
@@ -458,6 +459,7 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     raw = (T *)ctx->qt_raw.p;
     jpos = (uint8_t *)ctx->qt_j.p;
     ctx->qt_entries = (unsigned)n_entries;
+    ctx->qt_tail_tile = rem ? (unsigned)ntiles : 0xFFFFFFFFu;
   } else {
     TRY(grow(ctx, ctx->slots, n_entries * TILE_SLOT * sizeof(float)));
     ac_slots = (float *)ctx->slots.p;
@@ -482,6 +484,13 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
                                                                       d_info, fused, 0, batch);
     ctx->launches++;
     CU(cudaGetLastError());
+    if (QT) {  // per-position maxima of the parked (unscaled) outliers, scaled by the kernel's last CTA (before the tail
+               // block adds its own, scaled, values)
+      const size_t groups = (ntiles + 31) / 32;
+      const int gq = (int)(groups < (size_t)ctx->sm_count * 8 ? groups : (size_t)ctx->sm_count * 8);
+      k_qt_max<T><<<gq, 256, 0, st>>>(sb.counts, (unsigned)ntiles, raw, jpos, (U *)d_qtable_raw, ctx->d_params, ctx->d_done + 4);
+      ctx->launches++;
+    }
   }
   if (rem) {
     k_tail_compress<T, QT><<<1, 32, 0, st>>>(d_in + nblk_full * BLK, rem, nblk_full, (unsigned)ntiles, ctx->d_params, qc, d_bins, d_dc,
@@ -562,11 +571,12 @@ static int launch_qt_finish(dctz_gpu_ctx *ctx, double eb, const T *d_qraw, T *d_
   const unsigned n_entries = ctx->qt_entries;
   ScanBufs sb;
   TRY(scan_bufs(ctx, n_entries, &sb));  // same layout as in the compress call: nothing is reallocated
-  const size_t want = ((size_t)n_entries + 7) / 8;
-  const int grid = (int)(want < (size_t)ctx->sm_count * 16 ? (want ? want : 1) : (size_t)ctx->sm_count * 16);
+  const size_t want = ((size_t)n_entries + 31) / 32;  // one CTA per group of 32 tiles
+  const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? (want ? want : 1) : (size_t)ctx->sm_count * 8);
   k_qt_gather<T><<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p,
-                                       d_qraw, d_qtable, k, d_ac, d_info);
-  k_qt_compact<T><<<1, 32, 0, st>>>(sb.counts, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, k, d_ac, d_info);
+                                       d_qraw, d_qtable, k, d_ac, d_info, ctx->d_params, ctx->qt_tail_tile);
+  k_qt_compact<T><<<1, 32, 0, st>>>(sb.counts, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, k, d_ac, d_info,
+                                    ctx->d_params, ctx->qt_tail_tile);
   ctx->launches += 2;
   CU(cudaGetLastError());
   return DCTZ_GPU_OK;

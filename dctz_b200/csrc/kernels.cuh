@@ -484,7 +484,7 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
            unsigned *__restrict__ counts,                     // outliers per warp tile
            float *__restrict__ ac_slots,                      // EC: outlier scratch, TILE_SLOT entries per tile, packed
            T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
-           typename BitsOf<T>::U *qmax_bits,                  // QT: 64 per-position maxima (bit patterns), entries 1..63
+           typename BitsOf<T>::U *qmax_bits,                  // QT: 64 per-position maxima (bit patterns): filled by k_qt_max, unused here
            T *qtable0,                                        // QT: entry 0 of the same table: the last full block's DC
            TileControl *ctl, Info *info, FusedScan fused, int verify_lower, unsigned batch) {
   typedef typename ArithOf<T>::type A;
@@ -494,7 +494,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
   constexpr unsigned FULL = 0xFFFFFFFFu;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
-  __shared__ U s_qmax[QT ? BLK : 1];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -505,7 +504,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
   const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
 
   if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
-  if (QT) { if (threadIdx.x < BLK) s_qmax[threadIdx.x] = 0; }
   __syncthreads();  // the only CTA-wide barrier before the epilogue
 
   Quantizer<T> qz;
@@ -610,23 +608,20 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     //      k_gather_* only has to move whole tile runs ----
     if (tile_total != 0) {
       const unsigned long long run = (unsigned long long)cur * TILE_SLOT + my_off;
-      if constexpr (QT) {  // raw coefficient + position, rescaled by K2b once the global qtable is known
-        unsigned pos = 0;
+      if constexpr (QT) {  // raw (unscaled) coefficient + position; scaled and rescaled by K2b once the global qtable is known
+        T *raw_run = raw_slots + (unsigned long long)cur * TILE_SLOT;  // warp-uniform bases, 32-bit lane offsets
+        uint8_t *j_run = j_slots + (unsigned long long)cur * TILE_SLOT;
+        unsigned off = my_off;
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-          const unsigned nib = ((q < 8 ? mlo >> (4 * q) : mhi >> (4 * (q - 8))) & 0xFu);
-          if (nib) {
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-              const int j = 4 * q + b;
-              if (j >= 1 && (nib & (1u << b))) {
-                const T c = qz.scaled(x[j]);
-                raw_slots[run + pos] = c;
-                j_slots[run + pos] = (uint8_t)j;
-                atomicMax(&s_qmax[j], BitsOf<T>::abs_bits(c));  // :371-372, 396-397
-                pos++;
-              }
-            }
+        for (int j = 1; j < BLK; j++) {
+          if ((j < 32 ? mlo >> j : mhi >> (j - 32)) & 1u) {
+            // The UNSCALED coefficient is parked.  The exact division by sf is done once per outlier by the gather
+            // (k_qt_gather), and the per-position maxima (:371-372, 396-397) are taken by k_qt_max over the parked
+            // values: here they would cost a look-up and a branch per coefficient POSITION (measured: the branches,
+            // not the arithmetic, held this kernel at half its EC speed).
+            raw_run[off] = x[j];
+            j_run[off] = (uint8_t)j;
+            off++;
           }
         }
       } else {
@@ -676,9 +671,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
   // ---- epilogue ----
   bulk_wait_all();
   __syncthreads();
-  if (QT) {
-    if (threadIdx.x >= 1 && threadIdx.x < BLK && s_qmax[threadIdx.x] != 0) atomicMax(&qmax_bits[threadIdx.x], s_qmax[threadIdx.x]);
-  }
   __shared__ bool s_last;
   if constexpr (VERIFY) {
 #pragma unroll
@@ -872,17 +864,7 @@ __global__ void __launch_bounds__(1024) k_scan_groups(const unsigned *__restrict
   if (threadIdx.x == 0) { *total = carry; *out.done = 0u; }
 }
 
-// Gather: one warp per tile copies the tile's packed run to its final position
-// prefix_of_group + (totals of the earlier tiles of the group).
-__device__ __forceinline__ unsigned long long tile_base_of(const unsigned *__restrict__ counts,
-                                                           const unsigned long long *__restrict__ group_prefix,
-                                                           const unsigned long long *__restrict__ chunk_prefix, unsigned tile, int lane) {
-  unsigned e = ((unsigned)lane < (tile & 31u)) ? __ldg(counts + (tile & ~31u) + lane) : 0u;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
-  return prefix_of_group(group_prefix, chunk_prefix, tile >> 5) + e;
-}
-
+// Gather: a tile's packed run goes to prefix_of_group + (totals of the earlier tiles of its group).
 __global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ counts, const unsigned long long *__restrict__ group_prefix,
                                                    const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles,
                                                    const float *__restrict__ ac_slots, float *__restrict__ ac_out,
@@ -923,6 +905,73 @@ __global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ 
 // inside the bin range are dropped by the reference (their bin_index stays 255; :494-506): they are
 // flagged here and squeezed out by k_qt_compact, which is a no-op unless that ever happens.
 // ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ Divisor<T> sf_divisor(const DevParams *p);
+template <> __device__ __forceinline__ Divisor<double> sf_divisor<double>(const DevParams *p) {
+  Divisor<double> d;
+  d.b = p->sf_d; d.y = p->inv_sf_d; d.iters = p->scale_iters;
+  return d;
+}
+template <> __device__ __forceinline__ Divisor<float> sf_divisor<float>(const DevParams *p) {
+  Divisor<float> d;
+  d.b = p->sf_f; d.y = p->inv_sf_f; d.iters = p->scale_iters;
+  return d;
+}
+// QT: per-position maxima of |coefficient| over the parked outliers of the full tiles (dctz-comp-lib.c:371-372, 396-397),
+// as bit patterns (non-negative floats order like unsigned integers).  One CTA per group of 32 tiles, a warp per tile
+// run; per-CTA maxima in shared memory, looked at before the atomic (they stop moving quickly), flushed once.
+template <typename T>
+__global__ void __launch_bounds__(256) k_qt_max(const unsigned *__restrict__ counts, unsigned ntiles /* full tiles only */,
+                                                const T *__restrict__ raw_slots, const uint8_t *__restrict__ j_slots,
+                                                typename BitsOf<T>::U *qmax_bits, const DevParams *__restrict__ params,
+                                                unsigned *done_counter) {
+  typedef typename BitsOf<T>::U U;
+  __shared__ U s_max[BLK];
+  __shared__ bool s_last;
+  if (threadIdx.x < BLK) s_max[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned ngroups = (ntiles + 31u) >> 5;
+  for (unsigned g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const unsigned t0 = g * 32u + (unsigned)lane;
+    const unsigned c = (t0 < ntiles) ? __ldg(counts + t0) : 0u;
+    for (int s = warp; s < 32; s += 8) {
+      const unsigned n = __shfl_sync(0xFFFFFFFFu, c, s);
+      const unsigned long long src = (unsigned long long)(g * 32u + (unsigned)s) * TILE_SLOT;
+      for (unsigned i0 = 0; i0 < n; i0 += 128u) {
+        U a[4];
+        unsigned jj[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const unsigned i = i0 + 32u * u + lane;
+          a[u] = 0; jj[u] = 1u;
+          if (i < n) { a[u] = BitsOf<T>::abs_bits(__ldg(raw_slots + src + i)); jj[u] = __ldg(j_slots + src + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (a[u] > *reinterpret_cast<volatile U *>(&s_max[jj[u]])) atomicMax(&s_max[jj[u]], a[u]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= 1 && threadIdx.x < BLK && s_max[threadIdx.x] != 0) atomicMax(&qmax_bits[threadIdx.x], s_max[threadIdx.x]);
+  // The maxima are those of the UNSCALED coefficients; the last CTA turns them into the maxima of the scaled ones:
+  // max |c| / sf == max |c / sf| (exact division is monotone).  The tail block's kernel, whose values are scaled
+  // already, runs after this one.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+    if (s_last) *done_counter = 0u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x >= 1 && threadIdx.x < BLK) {
+    __threadfence();
+    volatile T *t = reinterpret_cast<volatile T *>(qmax_bits);
+    const T v = t[threadIdx.x];
+    t[threadIdx.x] = div_exact(v, sf_divisor<T>(params));
+  }
+}
+
 template <typename T> struct QtConsts {
   double eb;        // error_bound (double in both paths)
   T rmin, rmax;     // compress-side range (dctz-comp-lib.c:274-275 / 279-280)
@@ -950,8 +999,10 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
                                                    const unsigned long long *__restrict__ chunk_prefix, unsigned ntiles,
                                                    const T *__restrict__ raw_slots, const uint8_t *__restrict__ j_slots,
                                                    const T *__restrict__ qraw /* global maxima, [0] = last DC */,
-                                                   T *__restrict__ qtable_out, QtConsts<T> k, float *__restrict__ ac_out, Info *info) {
+                                                   T *__restrict__ qtable_out, QtConsts<T> k, float *__restrict__ ac_out, Info *info,
+                                                   const DevParams *__restrict__ params, unsigned tail_tile /* its values are scaled already */) {
   __shared__ T qt[BLK];
+  const Divisor<T> sfdiv = sf_divisor<T>(params);
   if (threadIdx.x < BLK) {
     T v = qraw[threadIdx.x];
     if (threadIdx.x >= 1 && v < (T)1.0) v = (T)1.0;  // :450-461
@@ -959,18 +1010,41 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
     if (blockIdx.x == 0 && qtable_out) qtable_out[threadIdx.x] = v;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
+  // one CTA per group of 32 tiles, whole packed runs per warp (as k_gather_ec)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned ngroups = (ntiles + 31u) >> 5;
   unsigned dropped = 0;
-  for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += wpg) {
-    const unsigned n = __ldg(counts + t);
-    if (n == 0) continue;
-    float *dst = ac_out + tile_base_of(counts, group_prefix, chunk_prefix, t, lane);
-    const unsigned long long src = (unsigned long long)t * TILE_SLOT;
-    for (unsigned i = lane; i < n; i += 32) {
-      float o;
-      if (!qt_rescale_one(raw_slots[src + i], qt[j_slots[src + i]], k, &o)) dropped++;
-      dst[i] = o;
+  for (unsigned g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const unsigned t0 = g * 32u + (unsigned)lane;
+    const unsigned c = (t0 < ntiles) ? __ldg(counts + t0) : 0u;
+    const unsigned incl = warp_inclusive_scan(c, lane);
+    if (__shfl_sync(0xFFFFFFFFu, incl, 31) == 0u) continue;
+    float *gdst = ac_out + prefix_of_group(group_prefix, chunk_prefix, g);
+    for (int s = warp; s < 32; s += 8) {
+      const unsigned n = __shfl_sync(0xFFFFFFFFu, c, s);
+      const unsigned off = __shfl_sync(0xFFFFFFFFu, incl - c, s);
+      const unsigned long long src = (unsigned long long)(g * 32u + (unsigned)s) * TILE_SLOT;
+      const bool unscaled = (g * 32u + (unsigned)s) != tail_tile;
+      float *dst = gdst + off;
+      for (unsigned i0 = 0; i0 < n; i0 += 128u) {
+        T r[4];
+        unsigned jj[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const unsigned i = i0 + 32u * u + lane;
+          r[u] = (T)0; jj[u] = 1u;
+          if (i < n) { r[u] = __ldg(raw_slots + src + i); jj[u] = __ldg(j_slots + src + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const unsigned i = i0 + 32u * u + lane;
+          if (i < n) {
+            float o;
+            if (!qt_rescale_one(unscaled ? div_exact(r[u], sfdiv) : r[u], qt[jj[u]], k, &o)) dropped++;
+            dst[i] = o;
+          }
+        }
+      }
     }
   }
   if (dropped) atomicAdd(&info->n_qt_dropped, (unsigned long long)dropped);
@@ -982,9 +1056,10 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(32) k_qt_compact(const unsigned *__restrict__ counts, unsigned ntiles, const T *__restrict__ raw_slots,
                                                    const uint8_t *__restrict__ j_slots, const T *__restrict__ qraw, QtConsts<T> k,
-                                                   float *ac_out, Info *info) {
+                                                   float *ac_out, Info *info, const DevParams *__restrict__ params, unsigned tail_tile) {
   if (info->n_qt_dropped == 0) return;  // the only path ever taken in practice
   if (threadIdx.x != 0) return;
+  const Divisor<T> sfdiv = sf_divisor<T>(params);
   unsigned long long w = 0;
   for (unsigned t = 0; t < ntiles; t++) {
     const unsigned long long slot = (unsigned long long)t * TILE_SLOT;
@@ -992,7 +1067,8 @@ __global__ void __launch_bounds__(32) k_qt_compact(const unsigned *__restrict__ 
       T q = qraw[j_slots[slot + i]];
       if (j_slots[slot + i] >= 1 && q < (T)1.0) q = (T)1.0;
       float o;
-      if (qt_rescale_one(raw_slots[slot + i], q, k, &o)) ac_out[w++] = o;
+      const T c = (t != tail_tile) ? div_exact(raw_slots[slot + i], sfdiv) : raw_slots[slot + i];
+      if (qt_rescale_one(c, q, k, &o)) ac_out[w++] = o;
     }
   }
   info->n_outliers = w;
@@ -1192,7 +1268,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     p.kend = p.lead + e.total;
     p.fits = p.kend <= FAST_MAX;
     p.prefetch = e.total != 0u && (WIDE || p.fits);
-    p.fofs = (WIDE && !QT && p.fits) ? FAST_MAX : 0u;  // double EC: raw floats in the upper half, expanded downwards
+    p.fofs = (WIDE && p.fits) ? FAST_MAX : 0u;  // double: raw floats in the upper half, expanded downwards
     return p;
   };
   // The ragged elements are LOADED when the tile's copies are issued and STORED to the stage only at the end of the
@@ -1290,7 +1366,21 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
         ready = true;
       }
       __syncwarp();
-    } else if (!QT && ext_cur.total != 0u && pl.fits) {
+    } else if (ext_cur.total != 0u && pl.fits) {
+      // QT: an outlier is rescaled with the table entry of its coefficient position (dctz-decomp-lib.c:404-409,
+      // 450-454).  Every lane first notes the positions of its block's outliers, in order, in the bin-id buffer
+      // (every lane holds its bin ids in registers by now; the buffer is dead until the next tile's copy), so that
+      // the cooperative pass below finds outlier i of the tile next to its position.
+      uint8_t *jpos = binbuf;
+      if constexpr (QT) {
+        __syncwarp();  // all lanes have read their bin ids
+        unsigned p = my_off;
+#pragma unroll
+        for (int j = 1; j < BLK; j++) {
+          if (((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) == 255u) jpos[p++] = (uint8_t)j;
+        }
+        __syncwarp();
+      }
       if constexpr (WIDE) {
         // in-place expansion float -> double: batch b reads floats [32b, 32b+32) of the upper half and writes doubles
         // [32b, 32b+32) from the bottom; a write only ever lands on floats of batches <= b (8i+8 <= 4096+4(32b+32)
@@ -1305,12 +1395,20 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             const unsigned i = i0 + 32 * k + lane;
-            if (i < ext_cur.total) dst[i] = mul_rn<T>((T)a[k], sf);  // :402-403 and the de-scale
+            if (i < ext_cur.total) {
+              T v;
+              if (QT) v = qt_unscale_one(a[k], s_qt[jpos[i]], qk); else v = (T)a[k];  // :402-409
+              dst[i] = mul_rn<T>(v, sf);                                               // and the de-scale
+            }
           }
         }
       } else {
         float *f = stage + pl.lead;
-        for (unsigned i = lane; i < ext_cur.total; i += 32) f[i] = __fmul_rn(f[i], (float)sf);
+        for (unsigned i = lane; i < ext_cur.total; i += 32) {
+          float v = f[i];
+          if (QT) v = (float)qt_unscale_one(v, s_qt[jpos[i]], qk);  // :450-454
+          f[i] = __fmul_rn(v, (float)sf);
+        }
         rdy = reinterpret_cast<const T *>(f);
       }
       fence_async_smem();  // the stage was written through the generic proxy; TMA writes it next
