@@ -226,6 +226,8 @@ struct TileControl {
   unsigned ticket;   // next tile index (dynamic scheduling)
   unsigned done;     // CTAs that have exited; the last one resets the fields for the next launch
   unsigned long long max_bits;  // VERIFY variant of K2: largest |x| bit pattern seen so far
+  unsigned corrupt;  // K3: set when the bin indices mark more outliers than the caller's AC_exact array holds
+  unsigned pad_;
 };
 
 // Keep the first USE of a long-latency result (a ticket atomic, a prefetched global load) where the source puts it:

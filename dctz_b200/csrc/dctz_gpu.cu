@@ -57,6 +57,7 @@ struct dctz_gpu_ctx {
   DevBuf slots;         // EC: tile-strided outlier scratch (TILE_SLOT floats per warp tile)
   DevBuf qt_raw, qt_j;  // QT: tile-strided un-rescaled outliers + their coefficient position
   unsigned qt_entries = 0;  // tiles (incl. the tail slot) of the last QT compress call
+  unsigned long long ac_limit = ~0ull;  // decompress: readable length of AC_exact (set by the host-buffer entry point)
   unsigned qt_tail_tile = 0xFFFFFFFFu;  // index of that tail slot (its raw values are scaled already), none = ~0
 
   // sf tables: host copies + device copies
@@ -646,14 +647,14 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
     CUtensorMap tmap;
     TRY(make_tile_map(ctx, &tmap, d_out, BLK * sizeof(T), nblk_full));
     k_decompress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, tmap, sb.counts,
-                                                               sb.out.group_prefix, sb.out.chunk_prefix, ctx->d_nconsumed, &ctx->d_ctl[1],
+                                                               sb.out.group_prefix, sb.out.chunk_prefix, ctx->d_nconsumed, ctx->ac_limit, &ctx->d_ctl[1],
                                                                tile_batch(ntiles, (size_t)grid * Cfg::WARPS));
     ctx->launches++;
     CU(cudaGetLastError());
   }
   if (rem) {
     k_tail_decompress<T, QT><<<1, 32, 0, st>>>(d_bins, d_dc, d_ac, d_qtable, rem, nblk_full, bw, sfT, qk, d_out,
-                                               nblk_full ? ctx->d_nconsumed : nullptr, 0ull);
+                                               nblk_full ? ctx->d_nconsumed : nullptr, 0ull, ctx->ac_limit, &ctx->d_ctl[1]);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -828,10 +829,19 @@ extern "C" int dctz_gpu_decompress_core(dctz_gpu_ctx *ctx, const uint8_t *bin_in
   CU(cudaMemcpyAsync(ctx->dc.p, DC, nblk * 4, cudaMemcpyHostToDevice, st));
   if (n_outliers) CU(cudaMemcpyAsync(ctx->ac.p, AC_exact, n_outliers * 4, cudaMemcpyHostToDevice, st));
   if (mode_qt) CU(cudaMemcpyAsync(ctx->qt.p, qtable, BLK * es, cudaMemcpyHostToDevice, st));
-  TRY(dctz_gpu_decompress_dev(ctx, (const uint8_t *)ctx->bins.p, (const float *)ctx->dc.p, (const float *)ctx->ac.p, ctx->qt.p, N,
-                              datatype, eb, sf, mode_qt, ctx->out.p, st));
+  // The kernels never read past the n_outliers floats the caller handed over: a stream whose bin indices mark more
+  // outliers than that is reported as corrupt (the reference would read whatever follows its buffer).
+  CU(cudaMemsetAsync(&ctx->d_ctl[1].corrupt, 0, sizeof(unsigned), st));
+  ctx->ac_limit = n_outliers;
+  const int rc = dctz_gpu_decompress_dev(ctx, (const uint8_t *)ctx->bins.p, (const float *)ctx->dc.p, (const float *)ctx->ac.p, ctx->qt.p, N,
+                                         datatype, eb, sf, mode_qt, ctx->out.p, st);
+  ctx->ac_limit = ~0ull;
+  TRY(rc);
+  unsigned corrupt = 0;
+  CU(cudaMemcpyAsync(&corrupt, &ctx->d_ctl[1].corrupt, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(out, ctx->out.p, N * es, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (corrupt) return fail(ctx, DCTZ_GPU_ECORRUPT, "decompress_core: the bin indices mark more outliers than the %llu given", (unsigned long long)n_outliers);
   return DCTZ_GPU_OK;
 }
 

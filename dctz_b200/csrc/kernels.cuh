@@ -1193,7 +1193,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
              const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
              const __grid_constant__ CUtensorMap tmap_out, const unsigned *__restrict__ counts,
              const unsigned long long *__restrict__ group_prefix, const unsigned long long *__restrict__ chunk_prefix,
-             const unsigned long long *__restrict__ n_outliers_total, TileControl *ctl, unsigned batch) {
+             const unsigned long long *__restrict__ n_outliers_total, unsigned long long n_limit, TileControl *ctl, unsigned batch) {
   typedef typename ArithOf<T>::type A;
   typedef DecompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -1235,7 +1235,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   // Outlier extent of a tile (warp-uniform): offset of its first outlier = scanned group prefix + the counts of
   // the earlier tiles of its group; its size is the tile's count from k_count_bins.  The loads (extent_load) and the
   // warp reduction that consumes them (extent_finish) are a whole iteration apart, so their latency is never waited for.
-  struct Extent { unsigned long long base; unsigned total; };
+  struct Extent { unsigned long long base; unsigned total; bool bad; };  // bad: the run would leave the caller's AC_exact array
   struct ExtentRaw { unsigned long long gp, cp; unsigned c; unsigned k; };  // loaded values, untouched until extent_finish
   auto extent_load = [&](unsigned t) -> ExtentRaw {
     ExtentRaw r;
@@ -1252,6 +1252,10 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(FULL, before, o);
     e.base = r.gp + r.cp + before;
+    // A stream whose bin indices mark more outliers than AC_exact holds (n_limit: its length as the caller states it)
+    // is corrupt: such a tile decodes without its outliers and the launch is flagged; nothing is read out of bounds.
+    e.bad = e.base + e.total > n_limit;
+    if (e.bad) { e.total = 0u; ctl->corrupt = 1u; }
     return e;
   };
   // Stage layout: the stage mirrors the 16-byte granules of AC_exact that hold the tile's run: outlier i lives at
@@ -1260,7 +1264,8 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   // and ignored).  Only where the superset would leave the array -- before AC_exact[0] when the array itself is not
   // 16-byte aligned, or past the last outlier of the field -- the copy is clipped to whole granules inside the array
   // and the at most 3 + 3 ragged elements are fetched by plain loads.
-  const unsigned long long n_ac = __ldg(n_outliers_total);
+  const unsigned long long n_scan = __ldg(n_outliers_total);
+  const unsigned long long n_ac = n_scan < n_limit ? n_scan : n_limit;  // end of the readable part of AC_exact
   struct Plan { unsigned lead, kend, fofs; bool fits, prefetch; };  // warp-uniform, a function of the extent alone
   auto plan_of = [&](const Extent &e) -> Plan {
     Plan p;
@@ -1312,7 +1317,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   unsigned nxt = seq.advance(lane);
   unsigned nn = seq.advance(lane);
   Extent ext_cur, ext_nxt;
-  ext_cur.base = 0; ext_cur.total = 0;
+  ext_cur.base = 0; ext_cur.total = 0; ext_cur.bad = false;
   ext_nxt = ext_cur;
   if (cur < ntiles) { ext_cur = extent_finish(extent_load(cur)); park_ragged(issue_tile(cur, ext_cur)); }
   if (nxt < ntiles) ext_nxt = extent_finish(extent_load(nxt));
@@ -1430,7 +1435,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
       for (int j = 1; j < BLK; j++)
         x[j] = *reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(center) + id_offset<T>(w[j >> 2], j & 3));  // entry 255 is a dummy, fixed below
     }
-    if (!ready && cnt != 0) {
+    if (!ready && !ext_cur.bad && cnt != 0) {
       // eight coefficients at a time: the (predicated) stage loads first, the conversions after them, so the
       // shared-memory latency is paid once per group and not once per outlier
       unsigned p = my_off;
@@ -1514,7 +1519,8 @@ __global__ void __launch_bounds__(32) k_tail_decompress(const uint8_t *__restric
                                                         const float *__restrict__ ac_in, const T *__restrict__ qtable,
                                                         int rem, unsigned long long blk_index, T bin_width, T sf,
                                                         QtConsts<T> qk, T *out, const unsigned long long *n_consumed,
-                                                        unsigned long long pos0_if_no_full_blocks) {
+                                                        unsigned long long pos0_if_no_full_blocks, unsigned long long n_limit,
+                                                        TileControl *ctl) {
   __shared__ double cs[BLK];
   const int lane = threadIdx.x;
   unsigned long long base = n_consumed ? *n_consumed : pos0_if_no_full_blocks;
@@ -1528,7 +1534,9 @@ __global__ void __launch_bounds__(32) k_tail_decompress(const uint8_t *__restric
       T v;
       if (j == 0) v = (T)dc_in[blk_index];
       else if (outl) {
-        const float a = ac_in[base + __popc(m & ((1u << lane) - 1u))];
+        const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
+        float a = 0.f;
+        if (at < n_limit) a = ac_in[at]; else ctl->corrupt = 1u;  // more markers than outliers: corrupt stream
         if (QT) v = (T)qt_unscale_one(a, qtable[j], qk); else v = (T)a;
       } else {
         if (sizeof(T) == 8) v = (T)__dmul_rn((double)center_multiple(id), (double)bin_width);

@@ -48,6 +48,7 @@ extern "C" {
 #define DCTZ_GPU_ENOMEM (-4)
 #define DCTZ_GPU_EDEGENERATE (-5) /* max|x| is 0, inf or NaN: the reference computes sf = 0/NaN (util.c:28) */
 #define DCTZ_GPU_ESTALE (-6)      /* compress_known_stats: the data's true max|x| gives another scaling factor */
+#define DCTZ_GPU_ECORRUPT (-7)    /* decompress_core: bin_index marks more outliers than AC_exact holds */
 
 #define DCTZ_GPU_BLK 64    /* BLK_SZ, dctz.h:28 */
 #define DCTZ_GPU_NBINS 255 /* NBINS,  dctz.h:66 */

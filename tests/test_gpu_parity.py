@@ -187,3 +187,23 @@ def test_randomised_sweep(ctx, dtype, qt):
                 parity.check_decompress(ctx, x, eb, qt)
             except AssertionError as e:  # pragma: no cover
                 raise AssertionError(f"n={n} kind={kind} eb={eb} scale={scale}: {e}") from e
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_corrupt_stream_is_reported_not_read_out_of_bounds(ctx, dtype):
+    """More outlier markers in bin_index than floats in AC_exact (a truncated or damaged stream): the reference reads
+    whatever follows its buffer; the GPU path must neither fault nor read past the array -- it reports
+    DCTZ_GPU_ECORRUPT (-7) -- and the context stays usable."""
+    import dctz_b200
+
+    x = (_signal(64 * 3000 + 21, dtype, noise=0.05) * 3).astype(dtype)
+    eb = 1e-3
+    g = ctx.compress_core(x, eb)
+    n_out = g["ac"].size
+    assert n_out > 5000
+    for keep in (n_out - 1, n_out // 2, 3, 0):  # the last, a middle and the first tiles run out of outliers
+        with pytest.raises(dctz_b200.DctzGpuError) as e:
+            ctx.decompress_core(g["bin_index"], g["dc"], g["ac"][:keep], x.size, dtype, eb, g["sf"])
+        assert e.value.code == -7, e.value
+    ok = ctx.decompress_core(g["bin_index"], g["dc"], g["ac"], x.size, dtype, eb, g["sf"])  # same context, intact stream
+    assert np.all(np.isfinite(ok)) and float(np.max(np.abs(ok - x))) < 0.2
