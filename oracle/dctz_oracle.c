@@ -312,7 +312,7 @@ int oracle_compress_core_d(double *buf, long n, double eb, int qt, unsigned char
 
   oracle_calc_stat_d(buf, n, st);                                   /* :186 */
   if (st->sf != 1.0) for (i = 0; i < n; i++) buf[i] /= st->sf;      /* :193-201 */
-  memset(bin_index, 0, (size_t)n);                                  /* :151 */
+  if (n > 0) memset(bin_index, 0, (size_t)n);                       /* :151 */
   for (j = 0; j < ORACLE_BLK; j++) qtab[j] = 0.0;                   /* :160-162 */
 
   for (i = 0; i < nblk; i++) { /* :325-416 */
@@ -384,7 +384,7 @@ int oracle_compress_core_f(float *buf, long n, double eb, int qt, unsigned char 
     const float sf = (float)st->sf;
     if (sf != 1.0) for (i = 0; i < n; i++) buf[i] /= sf; /* :208-216 */
   }
-  memset(bin_index, 0, (size_t)n);
+  if (n > 0) memset(bin_index, 0, (size_t)n);
   for (j = 0; j < ORACLE_BLK; j++) qtab[j] = 0.0;
 
   for (i = 0; i < nblk; i++) {
