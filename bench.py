@@ -544,32 +544,41 @@ def main_ours(args):
         gen = torch.Generator(device=dev).manual_seed(SEED)
         x2 = x[:n2] + 1.3 * torch.randn(n2, generator=gen, device=dev, dtype=torch.float64)
         st2 = torch.zeros(3, dtype=torch.float64, device=dev)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        tc = td = 0.0
-        ctx.stats_dev(x2.data_ptr(), n2, code, st2.data_ptr(), sh)
-        ctx.compress_dev(x2.data_ptr(), n2, n2, code, EB, False, st2.data_ptr(), 1, True, bins.data_ptr(), dc.data_ptr(), ac.data_ptr(),
-                         qraw.data_ptr(), info_d.data_ptr(), sh)
-        torch.cuda.synchronize()
-        sf2 = read_info()["sf"]
-        for it in range(3 + 5):
-            ev[0].record(stream)
-            ctx.stats_dev(x2.data_ptr(), n2, code, st2.data_ptr(), sh)
-            ctx.compress_dev(x2.data_ptr(), n2, n2, code, EB, False, st2.data_ptr(), 1, True, bins.data_ptr(), dc.data_ptr(), ac.data_ptr(),
-                             qraw.data_ptr(), info_d.data_ptr(), sh)
-            ev[1].record(stream)
-            ctx.decompress_dev(bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), 0, n2, code, EB, sf2, False, out.data_ptr(), sh)
-            ev[2].record(stream)
+
+        def noisy_leg(mode_qt):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            tc = td = 0.0
+
+            def comp():
+                ctx.stats_dev(x2.data_ptr(), n2, code, st2.data_ptr(), sh)
+                ctx.compress_dev(x2.data_ptr(), n2, n2, code, EB, mode_qt, st2.data_ptr(), 1, True, bins.data_ptr(), dc.data_ptr(),
+                                 ac.data_ptr(), qraw.data_ptr(), info_d.data_ptr(), sh)
+                if mode_qt:
+                    ctx.qt_finish_dev(code, EB, qraw.data_ptr(), qtab.data_ptr(), ac.data_ptr(), info_d.data_ptr(), sh)
+
+            comp()
             torch.cuda.synchronize()
-            if it >= 3:
-                tc += ev[0].elapsed_time(ev[1]) / 1e3
-                td += ev[1].elapsed_time(ev[2]) / 1e3
-        i2 = read_info()
-        p2 = i2["n_outliers"] / n2
-        outlier_leg = dict(workload=f"first 2^{n2.bit_length() - 1} elements of the slab + Gaussian noise (std 1.3)", outlier_fraction=p2,
-                           value=n2 * es * 5 / 1e9 / (tc + td), compress_gbs=n2 * es * 5 / 1e9 / tc, decompress_gbs=n2 * es * 5 / 1e9 / td,
-                           compress_frac=(2 * es + 1 + 4 / 64 + 4 * p2) * n2 * 5 / tc / 1e9 / peak,
-                           decompress_frac=(es + 1 + 4 / 64 + 4 * p2) * n2 * 5 / td / 1e9 / peak,
-                           max_abs_err=float((out[:n2] - x2).abs().max().item()))
+            sf2 = read_info()["sf"]
+            for it in range(3 + 5):
+                ev[0].record(stream)
+                comp()
+                ev[1].record(stream)
+                ctx.decompress_dev(bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), qtab.data_ptr() if mode_qt else 0, n2, code, EB, sf2, mode_qt,
+                                   out.data_ptr(), sh)
+                ev[2].record(stream)
+                torch.cuda.synchronize()
+                if it >= 3:
+                    tc += ev[0].elapsed_time(ev[1]) / 1e3
+                    td += ev[1].elapsed_time(ev[2]) / 1e3
+            p2 = read_info()["n_outliers"] / n2
+            return dict(workload=f"first 2^{n2.bit_length() - 1} elements of the slab + Gaussian noise (std 1.3), {'QT' if mode_qt else 'EC'} mode",
+                        outlier_fraction=p2, value=n2 * es * 5 / 1e9 / (tc + td), compress_gbs=n2 * es * 5 / 1e9 / tc,
+                        decompress_gbs=n2 * es * 5 / 1e9 / td, compress_frac=(2 * es + 1 + 4 / 64 + 4 * p2) * n2 * 5 / tc / 1e9 / peak,
+                        decompress_frac=(es + 1 + 4 / 64 + 4 * p2) * n2 * 5 / td / 1e9 / peak,
+                        max_abs_err=float((out[:n2] - x2).abs().max().item()))
+
+        outlier_leg = noisy_leg(False)
+        outlier_leg["qt_mode"] = noisy_leg(True)  # the quantiser mode on the same data (not strictly error bounded by design)
         del x2
 
     line = dict(metric=METRIC, value=gb_all / t_rt, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,

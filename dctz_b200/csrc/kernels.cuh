@@ -1080,23 +1080,42 @@ __global__ void __launch_bounds__(256) k_count_bins(const uint8_t *__restrict__ 
   const int lane = threadIdx.x & 31;
   const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
   const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
-  for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += wpg) {
-    const unsigned long long first = (unsigned long long)t * WTILE;
-    const unsigned rows = (nblk_full - first < (unsigned long long)WTILE) ? (unsigned)(nblk_full - first) : (unsigned)WTILE;
-    const uint4 *p = reinterpret_cast<const uint4 *>(bins + first * BLK);
-    unsigned cnt = 0;
+  // two tiles per warp and trip: eight independent 16-byte loads in flight per lane
+  for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += 2 * wpg) {
+    uint4 v[2][4];
+    unsigned rows[2];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const unsigned chunk = i * 32 + lane;  // 16-byte chunk of the tile; 4 chunks per block
-      if (chunk < rows * 4u) {
-        const uint4 v = __ldg(p + chunk);
-        const unsigned x0 = (chunk & 3u) ? v.x : (v.x & 0xFFFFFF00u);  // byte 0 of a block is the DC marker
-        cnt += __popc(ff_bytes(x0)) + __popc(ff_bytes(v.y)) + __popc(ff_bytes(v.z)) + __popc(ff_bytes(v.w));
+    for (int h = 0; h < 2; h++) {
+      const unsigned th = t + h * wpg;
+      rows[h] = 0;
+      if (th < ntiles) {
+        const unsigned long long first = (unsigned long long)th * WTILE;
+        rows[h] = (nblk_full - first < (unsigned long long)WTILE) ? (unsigned)(nblk_full - first) : (unsigned)WTILE;
+        const uint4 *p = reinterpret_cast<const uint4 *>(bins + first * BLK);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const unsigned chunk = i * 32 + lane;  // 16-byte chunk of the tile; 4 chunks per block
+          v[h][i] = (chunk < rows[h] * 4u) ? __ldg(p + chunk) : make_uint4(0u, 0u, 0u, 0u);
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-    if (lane == 0) counts[t] = cnt;
+    for (int h = 0; h < 2; h++) {
+      const unsigned th = t + h * wpg;
+      if (th >= ntiles) break;
+      unsigned cnt = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const unsigned chunk = i * 32 + lane;
+        if (chunk < rows[h] * 4u) {
+          const unsigned x0 = (chunk & 3u) ? v[h][i].x : (v[h][i].x & 0xFFFFFF00u);  // byte 0 of a block is the DC marker
+          cnt += __popc(ff_bytes(x0)) + __popc(ff_bytes(v[h][i].y)) + __popc(ff_bytes(v[h][i].z)) + __popc(ff_bytes(v[h][i].w));
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+      if (lane == 0) counts[th] = cnt;
+    }
   }
   if (!fused.n_entries) return;
   __shared__ bool s_last;
