@@ -456,6 +456,26 @@ __device__ __forceinline__ void cta_scan_small(const unsigned *counts, const Fus
 // K2: fused scale + DCT-II + quantise + ordered outlier compaction.
 // Shared memory per warp: [ tile: 4 (2) swizzled slabs ][ EC: outlier candidates 63 x 32 floats ][ bin ids 2 KB ]
 // ------------------------------------------------------------------------------------------
+// QT outlier emission: store value and position and advance both cursors, all under one predicate.
+__device__ __forceinline__ void park_if(double *&praw, uint8_t *&pj, double v, unsigned j, unsigned hit) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.u32 q, %4, 0;\n"
+      "@q st.global.f64 [%0], %2;\n@q st.global.u8 [%1], %3;\n"
+      "@q add.u64 %0, %0, 8;\n@q add.u64 %1, %1, 1;\n}\n"
+      : "+l"(praw), "+l"(pj)
+      : "d"(v), "r"(j), "r"(hit)
+      : "memory");
+}
+__device__ __forceinline__ void park_if(float *&praw, uint8_t *&pj, float v, unsigned j, unsigned hit) {
+  asm volatile(
+      "{\n.reg .pred q;\nsetp.ne.u32 q, %4, 0;\n"
+      "@q st.global.f32 [%0], %2;\n@q st.global.u8 [%1], %3;\n"
+      "@q add.u64 %0, %0, 4;\n@q add.u64 %1, %1, 1;\n}\n"
+      : "+l"(praw), "+l"(pj)
+      : "f"(v), "r"(j), "r"(hit)
+      : "memory");
+}
+
 template <typename T, bool QT> struct CompressCfg {
   // EC outlier emission: a tile in which some block has more than DENSE_MIN outliers takes the dense form (predicated
   // convert + store per coefficient), sparser tiles the parked-candidates loop.  Measured on B200 (2^28-element slab
@@ -609,21 +629,15 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     if (tile_total != 0) {
       const unsigned long long run = (unsigned long long)cur * TILE_SLOT + my_off;
       if constexpr (QT) {  // raw (unscaled) coefficient + position; scaled and rescaled by K2b once the global qtable is known
-        T *raw_run = raw_slots + (unsigned long long)cur * TILE_SLOT;  // warp-uniform bases, 32-bit lane offsets
-        uint8_t *j_run = j_slots + (unsigned long long)cur * TILE_SLOT;
-        unsigned off = my_off;
+        // The UNSCALED coefficient is parked.  The exact division by sf is done once per outlier by the gather
+        // (k_qt_gather), and the per-position maxima (:371-372, 396-397) are taken by k_qt_max over the parked
+        // values: here they would cost a look-up and a branch per coefficient POSITION (measured: the branches,
+        // not the arithmetic, held this kernel at half its EC speed).  For the same reason the stores are predicated
+        // by hand -- the compiler turns the plain `if` into 63 divergent branches.
+        T *praw = raw_slots + (unsigned long long)cur * TILE_SLOT + my_off;
+        uint8_t *pj = j_slots + (unsigned long long)cur * TILE_SLOT + my_off;
 #pragma unroll
-        for (int j = 1; j < BLK; j++) {
-          if ((j < 32 ? mlo >> j : mhi >> (j - 32)) & 1u) {
-            // The UNSCALED coefficient is parked.  The exact division by sf is done once per outlier by the gather
-            // (k_qt_gather), and the per-position maxima (:371-372, 396-397) are taken by k_qt_max over the parked
-            // values: here they would cost a look-up and a branch per coefficient POSITION (measured: the branches,
-            // not the arithmetic, held this kernel at half its EC speed).
-            raw_run[off] = x[j];
-            j_run[off] = (uint8_t)j;
-            off++;
-          }
-        }
+        for (int j = 1; j < BLK; j++) park_if(praw, pj, x[j], (unsigned)j, (j < 32 ? mlo >> j : mhi >> (j - 32)) & 1u);
       } else {
         // Uniform, branch-free part: every lane parks all 63 scaled AC coefficients as float (:537, USE_TRUNCATE) in
         // its own column of the candidate array (conflict-free; register indices stay compile-time).  Then a short
