@@ -21,7 +21,8 @@ EXPORTS = [
     "dctz_gpu_compress_core_with_stats", "dctz_gpu_quality", "dctz_gpu_quality_dev",
     "dctz_gpu_stats_dev", "dctz_gpu_compress_dev", "dctz_gpu_compress_known_stats_dev", "dctz_gpu_qt_finish_dev", "dctz_gpu_compress_field_dev",
     "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_dct64_dev", "dctz_gpu_fill_hash_field",
-    "dctz_gpu_sf_from_max", "dctz_gpu_selftest_division", "dctz_gpu_launch_count", "dctz_gpu_set_option",
+    "dctz_gpu_sf_from_max", "dctz_gpu_selftest_division", "dctz_gpu_launch_count", "dctz_gpu_compress_core_cb",
+    "dctz_gpu_set_timing", "dctz_gpu_last_call_stats",
 ]
 
 
@@ -72,7 +73,7 @@ def load_library():
         "dctz_gpu_compress_known_stats_dev": (i32, [vp, vp, sz, sz, i32, dbl, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "dctz_gpu_qt_finish_dev": (i32, [vp, i32, dbl, vp, vp, vp, vp, vp]),
         "dctz_gpu_compress_field_dev": (i32, [vp, vp, sz, i32, dbl, i32, vp, vp, vp, vp, vp, vp, vp]),
-        "dctz_gpu_decompress_dev": (i32, [vp, vp, vp, vp, vp, sz, i32, dbl, dbl, i32, vp, vp]),
+        "dctz_gpu_decompress_dev": (i32, [vp, vp, vp, vp, u64, vp, sz, i32, dbl, dbl, i32, vp, vp, vp]),
         "dctz_gpu_scale_dev": (i32, [vp, vp, sz, i32, dbl, i32, vp]),
         "dctz_gpu_dct_blocks": (i32, [vp, vp, vp, sz, i32, i32, i32]),
         "dctz_gpu_dct64_dev": (i32, [vp, vp, vp, sz, i32, i32, i32, vp]),
@@ -80,7 +81,9 @@ def load_library():
         "dctz_gpu_sf_from_max": (dbl, [vp, dbl, i32]),
         "dctz_gpu_selftest_division": (i32, [vp, i32, dbl, u64, C.c_uint32, C.POINTER(u64)]),
         "dctz_gpu_launch_count": (u64, [vp]),
-        "dctz_gpu_set_option": (i32, [vp, C.c_char_p, i32]),
+        "dctz_gpu_compress_core_cb": (i32, [vp, vp, sz, i32, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(GpuInfo), vp, vp]),
+        "dctz_gpu_set_timing": (i32, [vp, i32]),
+        "dctz_gpu_last_call_stats": (i32, [vp, C.POINTER(dbl), C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -172,14 +175,19 @@ class Context:
     def launch_count(self):
         return int(self._lib.dctz_gpu_launch_count(self._h))
 
+    def set_timing(self, on):
+        return self._lib.dctz_gpu_set_timing(self._h, int(bool(on)))
+
+    def last_call_stats(self):
+        """stage timers (ms) and PCIe bytes of the last host-buffer call"""
+        t = (C.c_double * 8)()
+        h, d = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.dctz_gpu_last_call_stats(self._h, t, C.byref(h), C.byref(d)))
+        return dict(upload_ms=t[0], stats_ms=t[1], transform_ms=t[2], wall_to_kernels_ms=t[3], wall_downloads_ms=t[4],
+                    h2d_bytes=int(h.value), d2h_bytes=int(d.value))
+
     def sf_from_max(self, max_abs, dtype):
         return self._lib.dctz_gpu_sf_from_max(self._h, float(max_abs), _code(dtype))
-
-    def set_option(self, name, value):
-        rc = self._lib.dctz_gpu_set_option(self._h, name.encode(), int(value))
-        if rc < 0:
-            self._check(rc)
-        return rc
 
     # ---- host-buffer API -----------------------------------------------------------------
     def compress_core(self, x, eb, qt=False, want_scaled=False, out=None):
@@ -289,9 +297,11 @@ class Context:
         self._check(self._lib.dctz_gpu_compress_field_dev(self._h, d_in, n, code, float(eb), int(bool(qt)), d_bins, d_dc, d_ac,
                                                           d_qtable or None, d_qtable_raw or None, d_info, stream or None))
 
-    def decompress_dev(self, d_bins, d_dc, d_ac, d_qtable, n, code, eb, sf, qt, d_out, stream=0):
-        self._check(self._lib.dctz_gpu_decompress_dev(self._h, d_bins, d_dc, d_ac or None, d_qtable or None, n, code, float(eb),
-                                                      float(sf), int(bool(qt)), d_out, stream or None))
+    def decompress_dev(self, d_bins, d_dc, d_ac, n_outliers, d_qtable, n, code, eb, sf, qt, d_out, stream=0, d_corrupt=0):
+        """n_outliers = readable floats at d_ac; d_corrupt = optional device uint32 set to 1 when the bin indices
+        mark more outliers than that"""
+        self._check(self._lib.dctz_gpu_decompress_dev(self._h, d_bins, d_dc, d_ac or None, int(n_outliers), d_qtable or None, n, code,
+                                                      float(eb), float(sf), int(bool(qt)), d_out, d_corrupt or None, stream or None))
 
     def scale_dev(self, d_x, n, code, sf, multiply, stream=0):
         self._check(self._lib.dctz_gpu_scale_dev(self._h, d_x, n, code, float(sf), int(bool(multiply)), stream or None))

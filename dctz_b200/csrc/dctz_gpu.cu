@@ -15,7 +15,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/dctz_gpu.h"
@@ -33,13 +40,113 @@ struct DevBuf {  // grow-only device allocation
   size_t cap = 0;
 };
 
+// ------------------------------------------------------------------------------------------
+// Host worker threads of the host-buffer API: staging copies between the caller's pageable memory and
+// the pinned ring, and the caller-visible x/sf (IEEE division) that the reference leaves in its input
+// buffer.  One job at a time; parts are handed out by an atomic counter.
+// ------------------------------------------------------------------------------------------
+class HostPool {
+  struct Job {  // immutable per start(): a straggler that still holds the previous job can never touch the next one
+    std::function<void(int)> fn;
+    int nparts = 0;
+    std::atomic<int> next{0};
+    int pending = 0;  // guarded by mu_
+  };
+
+ public:
+  explicit HostPool(int nthreads) {
+    for (int t = 0; t < nthreads; t++) workers_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &w : workers_) w.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // fn(part) for part in [0, nparts): start() returns at once, wait() joins (the calling thread works too)
+  void start(int nparts, std::function<void(int)> fn) {
+    auto j = std::make_shared<Job>();
+    j->fn = std::move(fn);
+    j->nparts = nparts;
+    j->pending = nparts;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = j;
+      gen_++;
+    }
+    cv_.notify_all();
+  }
+  void wait() {
+    std::shared_ptr<Job> j;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      j = job_;
+    }
+    if (!j) return;
+    run_parts(*j);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return j->pending == 0; });
+    if (job_ == j) job_.reset();
+  }
+  void parallel_for(int nparts, std::function<void(int)> fn) {
+    start(nparts, std::move(fn));
+    wait();
+  }
+
+ private:
+  void run_parts(Job &j) {
+    for (;;) {
+      const int i = j.next.fetch_add(1);
+      if (i >= j.nparts) return;
+      j.fn(i);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--j.pending == 0) done_cv_.notify_all();
+    }
+  }
+  void loop() {
+    unsigned long seen = 0;
+    for (;;) {
+      std::shared_ptr<Job> j;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        j = job_;
+      }
+      if (j) run_parts(*j);
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  std::shared_ptr<Job> job_;
+  unsigned long gen_ = 0;
+  bool stop_ = false;
+};
+
+constexpr size_t STAGE_BYTES = (size_t)16 << 20;  // one slot of the pinned staging ring
+constexpr int NSTAGE = 3;
+constexpr size_t PINNED_CHUNK = (size_t)64 << 20;  // copy granularity when the caller's memory is already page-locked
+
 struct dctz_gpu_ctx {
   int device = 0;
   int sm_count = 0;
-  cudaStream_t stream = nullptr;  // used by the host-buffer API
+  cudaStream_t stream = nullptr;  // used by the host-buffer API (kernels)
+  cudaStream_t copy_stream = nullptr;  // host-buffer API: H2D / D2H copies, overlapped with the kernels through events
+  cudaEvent_t ev_chain = nullptr, ev_time[4] = {nullptr, nullptr, nullptr, nullptr};
+  void *stage[NSTAGE] = {nullptr, nullptr, nullptr};  // pinned staging ring (allocated on first use with pageable memory)
+  cudaEvent_t stage_ev[NSTAGE] = {nullptr, nullptr, nullptr};
+  HostPool *pool = nullptr;
+  DevBuf chunk_stats;  // {max,min,sum} per chunk of a pipelined upload
+  int timing = 0;      // stage timers requested (dctz_gpu_set_timing): the stages then run one after the other
+  double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;  // PCIe traffic of the last host-buffer call
   char err[512] = "";
   uint64_t launches = 0;
-  int opt_dct = 0;
 
   // small fixed scratch
   StatPartial *d_partials = nullptr;
@@ -57,7 +164,6 @@ struct dctz_gpu_ctx {
   DevBuf slots;         // EC: tile-strided outlier scratch (TILE_SLOT floats per warp tile)
   DevBuf qt_raw, qt_j;  // QT: tile-strided un-rescaled outliers + their coefficient position
   unsigned qt_entries = 0;  // tiles (incl. the tail slot) of the last QT compress call
-  unsigned long long ac_limit = ~0ull;  // decompress: readable length of AC_exact (set by the host-buffer entry point)
   unsigned qt_tail_tile = 0xFFFFFFFFu;  // index of that tail slot (its raw values are scaled already), none = ~0
 
   // sf tables: host copies + device copies
@@ -191,11 +297,20 @@ extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
                     &ctx->qt, &ctx->qtraw, &ctx->out};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
   for (double *p : ctx->d_dfrag) if (p) cudaFree(p);
+  if (ctx->chunk_stats.p) cudaFree(ctx->chunk_stats.p);
+  delete ctx->pool;
+  for (int i = 0; i < NSTAGE; i++) {
+    if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+    if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+  }
+  if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
+  for (cudaEvent_t e : ctx->ev_time) if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
-template <typename T> static int upload(dctz_gpu_ctx *ctx, const std::vector<T> &v, const T **dst) {
+template <typename T> static int upload_table(dctz_gpu_ctx *ctx, const std::vector<T> &v, const T **dst) {
   void *p = nullptr;
   CU(cudaMalloc(&p, v.size() * sizeof(T)));
   CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -218,6 +333,9 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
     return fail(ctx, DCTZ_GPU_ENODEV, "device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major, prop.minor);
   ctx->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming));
+  for (cudaEvent_t &e : ctx->ev_time) CU(cudaEventCreate(&e));
   ctx->stat_grid = ctx->sm_count * 8;
   CU(cudaMalloc(&ctx->d_partials, sizeof(StatPartial) * ctx->stat_grid));
   CU(cudaMalloc(&ctx->d_done, 5 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups, [2] k_quality, [3] k_count_bins, [4] k_qt_max
@@ -232,10 +350,10 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   CU(cudaMalloc(&ctx->d_qpartials, sizeof(QualityPartial) * (ctx->stat_grid + 1)));
   CU(cudaMalloc(&ctx->d_stats_host3, 3 * sizeof(double)));
   build_sf_tables(ctx);
-  TRY(upload(ctx, ctx->thr_d, &ctx->tb.thr_d));
-  TRY(upload(ctx, ctx->sfv_d, &ctx->tb.sf_d));
-  TRY(upload(ctx, ctx->thr_f, &ctx->tb.thr_f));
-  TRY(upload(ctx, ctx->sfv_f, &ctx->tb.sf_f));
+  TRY(upload_table(ctx, ctx->thr_d, &ctx->tb.thr_d));
+  TRY(upload_table(ctx, ctx->sfv_d, &ctx->tb.sf_d));
+  TRY(upload_table(ctx, ctx->thr_f, &ctx->tb.thr_f));
+  TRY(upload_table(ctx, ctx->sfv_f, &ctx->tb.sf_f));
   ctx->tb.n_d = (int)ctx->thr_d.size();
   ctx->tb.n_f = (int)ctx->thr_f.size();
   ctx->tb.kmin_d = -306;
@@ -290,17 +408,6 @@ extern "C" void *dctz_gpu_host_alloc(size_t bytes) {
   return p;
 }
 extern "C" void dctz_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
-
-extern "C" int dctz_gpu_set_option(dctz_gpu_ctx *ctx, const char *name, int value) {
-  if (!ctx || !name) return fail(ctx, DCTZ_GPU_EINVAL, "bad option call");
-  if (!strcmp(name, "dct")) {
-    if (value != 0) return fail(ctx, DCTZ_GPU_EINVAL, "dct variant %d not available in this build", value);
-    const int prev = ctx->opt_dct;
-    ctx->opt_dct = value;
-    return prev;
-  }
-  return fail(ctx, DCTZ_GPU_EINVAL, "unknown option '%s'", name);
-}
 
 extern "C" double dctz_gpu_sf_from_max(const dctz_gpu_ctx *ctx, double max_abs, int datatype) {
   if (!ctx) return 0.0;
@@ -576,9 +683,7 @@ static int launch_qt_finish(dctz_gpu_ctx *ctx, double eb, const T *d_qraw, T *d_
   const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? (want ? want : 1) : (size_t)ctx->sm_count * 8);
   k_qt_gather<T><<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p,
                                        d_qraw, d_qtable, k, d_ac, d_info, ctx->d_params, ctx->qt_tail_tile);
-  k_qt_compact<T><<<1, 32, 0, st>>>(sb.counts, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p, d_qraw, k, d_ac, d_info,
-                                    ctx->d_params, ctx->qt_tail_tile);
-  ctx->launches += 2;
+  ctx->launches++;
   CU(cudaGetLastError());
   return DCTZ_GPU_OK;
 }
@@ -613,8 +718,8 @@ extern "C" int dctz_gpu_compress_field_dev(dctz_gpu_ctx *ctx, const void *d_in, 
 // decompress
 // ------------------------------------------------------------------------------------------
 template <typename T, bool QT>
-static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const float *d_dc, const float *d_ac, const T *d_qtable,
-                             size_t N, double eb, double sf, T *d_out, cudaStream_t st) {
+static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const float *d_dc, const float *d_ac, unsigned long long ac_limit,
+                             const T *d_qtable, size_t N, double eb, double sf, T *d_out, unsigned *d_corrupt, cudaStream_t st) {
   typedef DecompressCfg<T, QT> Cfg;
   const unsigned long long nblk_full = N / BLK;
   const int rem = (int)(N % BLK);
@@ -647,14 +752,14 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
     CUtensorMap tmap;
     TRY(make_tile_map(ctx, &tmap, d_out, BLK * sizeof(T), nblk_full));
     k_decompress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, tmap, sb.counts,
-                                                               sb.out.group_prefix, sb.out.chunk_prefix, ctx->d_nconsumed, ctx->ac_limit, &ctx->d_ctl[1],
-                                                               tile_batch(ntiles, (size_t)grid * Cfg::WARPS));
+                                                               sb.out.group_prefix, sb.out.chunk_prefix, ctx->d_nconsumed, ac_limit, &ctx->d_ctl[1],
+                                                               d_corrupt, aligned16(d_dc) ? 1 : 0, tile_batch(ntiles, (size_t)grid * Cfg::WARPS));
     ctx->launches++;
     CU(cudaGetLastError());
   }
   if (rem) {
     k_tail_decompress<T, QT><<<1, 32, 0, st>>>(d_bins, d_dc, d_ac, d_qtable, rem, nblk_full, bw, sfT, qk, d_out,
-                                               nblk_full ? ctx->d_nconsumed : nullptr, 0ull, ctx->ac_limit, &ctx->d_ctl[1]);
+                                               nblk_full ? ctx->d_nconsumed : nullptr, 0ull, ac_limit, d_corrupt);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -662,21 +767,23 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
 }
 
 extern "C" int dctz_gpu_decompress_dev(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const float *d_dc, const float *d_ac,
-                                       const void *d_qtable, size_t N, int datatype, double eb, double sf, int mode_qt, void *d_out,
-                                       void *stream) {
+                                       uint64_t n_outliers, const void *d_qtable, size_t N, int datatype, double eb, double sf, int mode_qt,
+                                       void *d_out, uint32_t *d_corrupt, void *stream) {
   TRY(check_common(ctx, datatype, eb));
-  if (!d_bins || !d_dc || !d_out || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: NULL pointer or N == 0");
+  if (!d_bins || !d_dc || !d_out || N == 0 || (n_outliers && !d_ac)) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: NULL pointer or N == 0");
   if (mode_qt && !d_qtable) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: QT mode needs the qtable");
   if (!aligned16(d_bins) || !aligned16(d_out)) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: bin_index and output must be 16-byte aligned");
+  if (((uintptr_t)d_dc & 3u) || ((uintptr_t)d_ac & 3u)) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: DC / AC_exact must be float-aligned");
   if (!(sf > 0.0) || isinf(sf)) return fail(ctx, DCTZ_GPU_EINVAL, "decompress: scaling factor %g is not a positive finite number", sf);
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
+  unsigned *flag = d_corrupt ? (unsigned *)d_corrupt : &ctx->d_ctl[1].corrupt;  // the caller's flag, else a scratch word nobody reads
   if (datatype == DCTZ_GPU_DOUBLE) {
-    if (mode_qt) return launch_decompress<double, true>(ctx, d_bins, d_dc, d_ac, (const double *)d_qtable, N, eb, sf, (double *)d_out, st);
-    return launch_decompress<double, false>(ctx, d_bins, d_dc, d_ac, (const double *)d_qtable, N, eb, sf, (double *)d_out, st);
+    if (mode_qt) return launch_decompress<double, true>(ctx, d_bins, d_dc, d_ac, n_outliers, (const double *)d_qtable, N, eb, sf, (double *)d_out, flag, st);
+    return launch_decompress<double, false>(ctx, d_bins, d_dc, d_ac, n_outliers, (const double *)d_qtable, N, eb, sf, (double *)d_out, flag, st);
   }
-  if (mode_qt) return launch_decompress<float, true>(ctx, d_bins, d_dc, d_ac, (const float *)d_qtable, N, eb, sf, (float *)d_out, st);
-  return launch_decompress<float, false>(ctx, d_bins, d_dc, d_ac, (const float *)d_qtable, N, eb, sf, (float *)d_out, st);
+  if (mode_qt) return launch_decompress<float, true>(ctx, d_bins, d_dc, d_ac, n_outliers, (const float *)d_qtable, N, eb, sf, (float *)d_out, flag, st);
+  return launch_decompress<float, false>(ctx, d_bins, d_dc, d_ac, n_outliers, (const float *)d_qtable, N, eb, sf, (float *)d_out, flag, st);
 }
 
 extern "C" int dctz_gpu_scale_dev(dctz_gpu_ctx *ctx, void *d_x, size_t N, int datatype, double sf, int multiply, void *stream) {
@@ -695,10 +802,146 @@ extern "C" int dctz_gpu_scale_dev(dctz_gpu_ctx *ctx, void *d_x, size_t N, int da
 
 // ------------------------------------------------------------------------------------------
 // host-buffer API (the drop-in seam)
+//
+// The caller's buffers are ordinary host memory (dctz-test.c:130-174 reads its file into malloc'ed arrays).  A
+// pageable pointer handed to cudaMemcpyAsync goes through the driver's own bounce buffers at a fraction of the link
+// speed and serialises with everything else, so the library stages it itself: a ring of NSTAGE page-locked slots,
+// filled (or drained) by the host worker threads while the previous slot is on the wire.  Page-locked buffers
+// (dctz_gpu_host_alloc, cudaHostRegister) are detected and copied directly.  Uploads are chunked on a copy stream and
+// the statistics kernel of chunk k runs on the compute stream while chunk k+1 is still arriving: the chunks play the
+// part of ranks (k_finalize merges their {max,min,sum} in chunk order), so when the last byte has landed only the
+// transform kernel is left to run.  The caller-visible x/sf (dctz-comp-lib.c:198,213 scale the input in place) is an
+// IEEE division done by the host threads on the caller's own buffer: nothing travels back over PCIe for it.
 // ------------------------------------------------------------------------------------------
+static bool host_is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static int host_threads() {
+  const char *e = getenv("DCTZ_HOST_THREADS");
+  long n = e ? atol(e) : (long)std::thread::hardware_concurrency();
+  if (n < 1) n = 1;
+  if (n > 16) n = 16;
+  return (int)n;
+}
+
+static int ensure_pool(dctz_gpu_ctx *ctx) {
+  if (!ctx->pool) {
+    ctx->pool = new (std::nothrow) HostPool(host_threads() - 1);  // the calling thread works too
+    if (!ctx->pool) return fail(ctx, DCTZ_GPU_ENOMEM, "out of host memory");
+  }
+  return DCTZ_GPU_OK;
+}
+
+static int ensure_stage(dctz_gpu_ctx *ctx) {
+  TRY(ensure_pool(ctx));
+  for (int i = 0; i < NSTAGE; i++) {
+    if (!ctx->stage[i]) CU(cudaMallocHost(&ctx->stage[i], STAGE_BYTES));
+    if (!ctx->stage_ev[i]) CU(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+  }
+  return DCTZ_GPU_OK;
+}
+
+static void pool_memcpy(HostPool *pool, void *dst, const void *src, size_t bytes) {
+  const size_t piece = (size_t)1 << 20;
+  const int parts = (int)((bytes + piece - 1) / piece);
+  if (parts <= 1) { memcpy(dst, src, bytes); return; }
+  pool->parallel_for(parts, [=](int i) {
+    const size_t off = (size_t)i * piece, len = bytes - off < piece ? bytes - off : piece;
+    memcpy((char *)dst + off, (const char *)src + off, len);
+  });
+}
+
+// Host -> device, chunked on the copy stream.  after_chunk(index, byte offset, bytes) is called once the chunk's copy
+// has been enqueued and the compute stream has been told to wait for it.
+static int upload(dctz_gpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, size_t chunk_align,
+                  const std::function<int(size_t, size_t, size_t)> &after_chunk) {
+  if (bytes == 0) return DCTZ_GPU_OK;
+  const bool pinned = host_is_pinned(h_src);
+  if (!pinned) TRY(ensure_stage(ctx));
+  size_t chunk = pinned ? PINNED_CHUNK : STAGE_BYTES;
+  chunk -= chunk % chunk_align;
+  size_t c = 0;
+  for (size_t off = 0; off < bytes; off += chunk, c++) {
+    const size_t len = bytes - off < chunk ? bytes - off : chunk;
+    const void *src = (const char *)h_src + off;
+    const int s = (int)(c % NSTAGE);
+    if (!pinned) {
+      if (c >= (size_t)NSTAGE) CU(cudaEventSynchronize(ctx->stage_ev[s]));  // the slot's previous content is on the device
+      pool_memcpy(ctx->pool, ctx->stage[s], src, len);
+      src = ctx->stage[s];
+    }
+    CU(cudaMemcpyAsync((char *)d_dst + off, src, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (!pinned) CU(cudaEventRecord(ctx->stage_ev[s], ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_chain, ctx->copy_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0));
+    if (after_chunk) TRY(after_chunk(c, off, len));
+  }
+  ctx->h2d_bytes += bytes;
+  return DCTZ_GPU_OK;
+}
+
+// Device -> host of data produced on the compute stream; synchronous.  on_ready(byte offset, bytes) reports every
+// piece as soon as it is valid in the caller's buffer (the host library starts deflating it while the rest is still
+// on its way).
+static int download(dctz_gpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, const std::function<void(size_t, size_t)> &on_ready) {
+  if (bytes == 0) return DCTZ_GPU_OK;
+  CU(cudaEventRecord(ctx->ev_chain, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chain, 0));
+  const bool pinned = host_is_pinned(h_dst);
+  ctx->d2h_bytes += bytes;
+  if (pinned && !on_ready) {
+    CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    return DCTZ_GPU_OK;
+  }
+  TRY(ensure_stage(ctx));  // (the events are used in both modes)
+  const size_t chunk = STAGE_BYTES;
+  const size_t nchunks = (bytes + chunk - 1) / chunk;
+  auto span = [&](size_t c, size_t *off, size_t *len) { *off = c * chunk; *len = bytes - *off < chunk ? bytes - *off : chunk; };
+  for (size_t c = 0; c <= nchunks; c++) {  // chunk c goes on the wire, chunk c-1 is handed over
+    if (c < nchunks) {
+      size_t off, len;
+      span(c, &off, &len);
+      const int s = (int)(c % NSTAGE);
+      void *dst = pinned ? (void *)((char *)h_dst + off) : ctx->stage[s];
+      CU(cudaMemcpyAsync(dst, (const char *)d_src + off, len, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      CU(cudaEventRecord(ctx->stage_ev[s], ctx->copy_stream));
+    }
+    if (c > 0) {
+      size_t off, len;
+      span(c - 1, &off, &len);
+      const int s = (int)((c - 1) % NSTAGE);
+      CU(cudaEventSynchronize(ctx->stage_ev[s]));
+      if (!pinned) pool_memcpy(ctx->pool, (char *)h_dst + off, ctx->stage[s], len);
+      if (on_ready) on_ready(off, len);
+    }
+  }
+  return DCTZ_GPU_OK;
+}
+
+template <typename T> static void host_scale(HostPool *pool, T *dst, const T *src, size_t n, T sf) {
+  const size_t piece = (size_t)1 << 18;
+  const int parts = (int)((n + piece - 1) / piece);
+  auto body = [=](int i) {
+    const size_t a = (size_t)i * piece, b = a + piece < n ? a + piece : n;
+    for (size_t k = a; k < b; k++) dst[k] = src[k] / sf;  // IEEE division, element type: dctz-comp-lib.c:198 / :213
+  };
+  if (parts <= 1 || !pool) { for (int i = 0; i < parts; i++) body(i); return; }
+  pool->parallel_for(parts, body);
+}
+
+static float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+  return ms;
+}
+
 static int compress_core_impl(dctz_gpu_ctx *ctx, const void *in, size_t N, size_t N_total, const double *stats3, int first_piece,
                               int datatype, double eb, int mode_qt, void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact,
-                              void *qtable, void *qtable_raw, dctz_gpu_info *info) {
+                              void *qtable, void *qtable_raw, dctz_gpu_info *info, dctz_gpu_section_cb cb, void *cb_user) {
   TRY(check_common(ctx, datatype, eb));
   if (!in || !bin_index || !DC || !AC_exact || !info || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "compress_core: NULL pointer or N == 0");
   if (mode_qt && !qtable) return fail(ctx, DCTZ_GPU_EINVAL, "compress_core: QT mode needs a qtable output");
@@ -706,49 +949,122 @@ static int compress_core_impl(dctz_gpu_ctx *ctx, const void *in, size_t N, size_
   const size_t es = datatype == DCTZ_GPU_DOUBLE ? 8 : 4;
   const size_t nblk = (N + BLK - 1) / BLK;
   cudaStream_t st = ctx->stream;
+  ctx->h2d_bytes = ctx->d2h_bytes = 0;
+  for (double &t : ctx->times) t = 0.0;
   TRY(grow(ctx, ctx->in, N * es));
   TRY(grow(ctx, ctx->bins, N));
   TRY(grow(ctx, ctx->dc, nblk * 4));
   TRY(grow(ctx, ctx->ac, N * 4));
   TRY(grow(ctx, ctx->qt, BLK * 8));
   TRY(grow(ctx, ctx->qtraw, BLK * 8));
-  CU(cudaMemcpyAsync(ctx->in.p, in, N * es, cudaMemcpyHostToDevice, st));
+  dctz_gpu_info *d_info = (dctz_gpu_info *)ctx->d_info;
+  const bool pinned_in = host_is_pinned(in);
+  const size_t up_chunk = pinned_in ? PINNED_CHUNK : STAGE_BYTES;
+  const size_t nchunks = (N * es + up_chunk - 1) / up_chunk;
+  const auto t_begin = std::chrono::steady_clock::now();
+  if (ctx->timing) CU(cudaEventRecord(ctx->ev_time[0], st));
+
   if (stats3) {  // the caller's global statistics decide the scaling factor
     CU(cudaMemcpyAsync(ctx->d_stats_host3, stats3, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr));
+    if (ctx->timing) { CU(cudaStreamSynchronize(st)); CU(cudaEventRecord(ctx->ev_time[1], st)); CU(cudaEventRecord(ctx->ev_time[2], st)); }
     TRY(dctz_gpu_compress_dev(ctx, ctx->in.p, N, N_total, datatype, eb, mode_qt, ctx->d_stats_host3, 1, first_piece, (uint8_t *)ctx->bins.p,
-                              (float *)ctx->dc.p, (float *)ctx->ac.p, ctx->qtraw.p, (dctz_gpu_info *)ctx->d_info, st));
-    if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, ctx->qtraw.p, ctx->qt.p, (float *)ctx->ac.p, (dctz_gpu_info *)ctx->d_info, st));
-  } else {
+                              (float *)ctx->dc.p, (float *)ctx->ac.p, ctx->qtraw.p, d_info, st));
+    if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, ctx->qtraw.p, ctx->qt.p, (float *)ctx->ac.p, d_info, st));
+  } else if (ctx->timing) {  // stage timers wanted (the reference's -DTIME_DEBUG lines): upload, statistics, transform one after the other
+    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventRecord(ctx->ev_time[1], st));
+    TRY(dctz_gpu_stats_dev(ctx, ctx->in.p, N, datatype, ctx->d_stats3, st));
+    CU(cudaEventRecord(ctx->ev_time[2], st));
+    TRY(dctz_gpu_compress_dev(ctx, ctx->in.p, N, N, datatype, eb, mode_qt, ctx->d_stats3, 1, 1, (uint8_t *)ctx->bins.p, (float *)ctx->dc.p,
+                              (float *)ctx->ac.p, ctx->qtraw.p, d_info, st));
+    if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, ctx->qtraw.p, ctx->qt.p, (float *)ctx->ac.p, d_info, st));
+  } else if (nchunks == 1) {  // one upload, then the single-field path (small fields: one fused launch)
+    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr));
     TRY(dctz_gpu_compress_field_dev(ctx, ctx->in.p, N, datatype, eb, mode_qt, (uint8_t *)ctx->bins.p, (float *)ctx->dc.p,
-                                    (float *)ctx->ac.p, ctx->qt.p, ctx->qtraw.p, (dctz_gpu_info *)ctx->d_info, st));
+                                    (float *)ctx->ac.p, ctx->qt.p, ctx->qtraw.p, d_info, st));
+  } else {  // statistics of chunk k while chunk k+1 is on the wire; the chunks are merged like ranks
+    TRY(grow(ctx, ctx->chunk_stats, nchunks * 3 * sizeof(double)));
+    double *d_cs = (double *)ctx->chunk_stats.p;
+    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, [&](size_t c, size_t off, size_t len) -> int {
+      return dctz_gpu_stats_dev(ctx, (const char *)ctx->in.p + off, len / es, datatype, d_cs + 3 * c, st);
+    }));
+    TRY(dctz_gpu_compress_dev(ctx, ctx->in.p, N, N, datatype, eb, mode_qt, d_cs, (int)nchunks, 1, (uint8_t *)ctx->bins.p,
+                              (float *)ctx->dc.p, (float *)ctx->ac.p, ctx->qtraw.p, d_info, st));
+    if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, ctx->qtraw.p, ctx->qt.p, (float *)ctx->ac.p, d_info, st));
   }
+  if (ctx->timing) CU(cudaEventRecord(ctx->ev_time[3], st));
   CU(cudaMemcpyAsync(info, ctx->d_info, sizeof(Info), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(bin_index, ctx->bins.p, N, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(DC, ctx->dc.p, nblk * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  ctx->d2h_bytes += sizeof(Info);
   if (info->status != 0)
     return fail(ctx, info->status, "compress_core: max|x| = %g gives no usable scaling factor (util.c:28 would yield 0/inf/NaN)", info->max_abs);
-  if (info->n_outliers) CU(cudaMemcpyAsync(AC_exact, ctx->ac.p, info->n_outliers * 4, cudaMemcpyDeviceToHost, st));
+  const auto t_gpu = std::chrono::steady_clock::now();
+
+  // the caller-visible scaled input: host threads, overlapping the downloads when those need no staging copies
+  const bool scale = scaled_out && (info->sf != 1.0 || scaled_out != in);
+  // (the staged downloads need the worker threads themselves: overlap only when none of them is staged)
+  const bool overlap = scale && !cb && host_is_pinned(bin_index) && host_is_pinned(DC) && host_is_pinned(AC_exact);
+  auto do_scale = [&](bool async) -> int {
+    TRY(ensure_pool(ctx));
+    if (info->sf == 1.0) { pool_memcpy(ctx->pool, scaled_out, in, N * es); return DCTZ_GPU_OK; }  // dctz-comp-lib.c:193/:208 skip the loop
+    if (async) {
+      const size_t piece = (size_t)1 << 18;
+      const int parts = (int)((N + piece - 1) / piece);
+      if (es == 8) {
+        double *d = (double *)scaled_out; const double *s2 = (const double *)in; const double sf = info->sf;
+        ctx->pool->start(parts, [=](int i) { const size_t a = (size_t)i * piece, b = a + piece < N ? a + piece : N; for (size_t k = a; k < b; k++) d[k] = s2[k] / sf; });
+      } else {
+        float *d = (float *)scaled_out; const float *s2 = (const float *)in; const float sf = (float)info->sf;
+        ctx->pool->start(parts, [=](int i) { const size_t a = (size_t)i * piece, b = a + piece < N ? a + piece : N; for (size_t k = a; k < b; k++) d[k] = s2[k] / sf; });
+      }
+      return DCTZ_GPU_OK;
+    }
+    if (es == 8) host_scale<double>(ctx->pool, (double *)scaled_out, (const double *)in, N, info->sf);
+    else host_scale<float>(ctx->pool, (float *)scaled_out, (const float *)in, N, (float)info->sf);
+    return DCTZ_GPU_OK;
+  };
+  if (overlap) TRY(do_scale(info->sf != 1.0));
+
+  auto section = [&](int id) -> std::function<void(size_t, size_t)> {
+    if (!cb) return nullptr;
+    return [=](size_t off, size_t len) { cb(cb_user, id, off, len); };
+  };
+  TRY(download(ctx, bin_index, ctx->bins.p, N, section(0)));
+  TRY(download(ctx, DC, ctx->dc.p, nblk * 4, section(1)));
+  TRY(download(ctx, AC_exact, ctx->ac.p, (size_t)info->n_outliers * 4, section(2)));
+  if (cb && info->n_outliers == 0) cb(cb_user, 2, 0, 0);  // every section is reported at least once
   if (mode_qt) {
     CU(cudaMemcpyAsync(qtable, ctx->qt.p, BLK * es, cudaMemcpyDeviceToHost, st));
     if (qtable_raw) CU(cudaMemcpyAsync(qtable_raw, ctx->qtraw.p, BLK * es, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->d2h_bytes += (qtable_raw ? 2 : 1) * BLK * es;
   }
-  if (scaled_out) {  // the reference leaves x/sf in the caller's buffer (dctz-comp-lib.c:198,213)
-    if (info->sf != 1.0) {
-      TRY(dctz_gpu_scale_dev(ctx, ctx->in.p, N, datatype, info->sf, 0, st));
-      CU(cudaMemcpyAsync(scaled_out, ctx->in.p, N * es, cudaMemcpyDeviceToHost, st));
-    } else if (scaled_out != in) {
-      memcpy(scaled_out, in, N * es);
-    }
+  if (overlap) { if (info->sf != 1.0) ctx->pool->wait(); }
+  else if (scale) TRY(do_scale(false));
+  if (ctx->timing) {
+    ctx->times[0] = elapsed_ms(ctx->ev_time[0], ctx->ev_time[1]);  // upload
+    ctx->times[1] = elapsed_ms(ctx->ev_time[1], ctx->ev_time[2]);  // statistics                          (the reference's sf_t)
+    ctx->times[2] = elapsed_ms(ctx->ev_time[2], ctx->ev_time[3]);  // scale + DCT + quantise + outliers   (the reference's dct_t)
   }
-  CU(cudaStreamSynchronize(st));
+  ctx->times[3] = std::chrono::duration<double, std::milli>(t_gpu - t_begin).count();                                   // upload + kernels (wall clock)
+  ctx->times[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_gpu).count();          // downloads + host scaling
   return DCTZ_GPU_OK;
 }
 
 extern "C" int dctz_gpu_compress_core(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, double eb, int mode_qt,
                                       void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact, void *qtable,
                                       void *qtable_raw, dctz_gpu_info *info) {
-  return compress_core_impl(ctx, in, N, N, nullptr, 1, datatype, eb, mode_qt, scaled_out, bin_index, DC, AC_exact, qtable, qtable_raw, info);
+  return compress_core_impl(ctx, in, N, N, nullptr, 1, datatype, eb, mode_qt, scaled_out, bin_index, DC, AC_exact, qtable, qtable_raw, info,
+                            nullptr, nullptr);
+}
+
+extern "C" int dctz_gpu_compress_core_cb(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, double eb, int mode_qt,
+                                         void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact, void *qtable,
+                                         void *qtable_raw, dctz_gpu_info *info, dctz_gpu_section_cb on_ready, void *user) {
+  return compress_core_impl(ctx, in, N, N, nullptr, 1, datatype, eb, mode_qt, scaled_out, bin_index, DC, AC_exact, qtable, qtable_raw, info,
+                            on_ready, user);
 }
 
 extern "C" int dctz_gpu_compress_core_with_stats(dctz_gpu_ctx *ctx, const void *in, size_t N, size_t N_total, const double stats3[3],
@@ -757,7 +1073,22 @@ extern "C" int dctz_gpu_compress_core_with_stats(dctz_gpu_ctx *ctx, const void *
                                                  dctz_gpu_info *info) {
   if (!stats3 || N_total < N) return fail(ctx, DCTZ_GPU_EINVAL, "compress_core_with_stats: bad statistics arguments");
   return compress_core_impl(ctx, in, N, N_total, stats3, first_piece, datatype, eb, mode_qt, scaled_out, bin_index, DC, AC_exact, qtable,
-                            qtable_raw, info);
+                            qtable_raw, info, nullptr, nullptr);
+}
+
+extern "C" int dctz_gpu_set_timing(dctz_gpu_ctx *ctx, int on) {
+  if (!ctx) return fail(nullptr, DCTZ_GPU_EINVAL, "ctx is NULL");
+  const int prev = ctx->timing;
+  ctx->timing = on ? 1 : 0;
+  return prev;
+}
+
+extern "C" int dctz_gpu_last_call_stats(const dctz_gpu_ctx *ctx, double times_ms[8], uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+  if (!ctx) return fail(nullptr, DCTZ_GPU_EINVAL, "ctx is NULL");
+  if (times_ms) for (int i = 0; i < 8; i++) times_ms[i] = ctx->times[i];
+  if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+  return DCTZ_GPU_OK;
 }
 
 template <typename T>
@@ -786,8 +1117,8 @@ extern "C" int dctz_gpu_quality(dctz_gpu_ctx *ctx, const void *a, const void *b,
   cudaStream_t st = ctx->stream;
   TRY(grow(ctx, ctx->in, N * es));
   TRY(grow(ctx, ctx->out, N * es));
-  CU(cudaMemcpyAsync(ctx->in.p, a, N * es, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->out.p, b, N * es, cudaMemcpyHostToDevice, st));
+  TRY(upload(ctx, ctx->in.p, a, N * es, 1024, nullptr));
+  TRY(upload(ctx, ctx->out.p, b, N * es, 1024, nullptr));
   double *d_res = (double *)(ctx->d_qpartials + ctx->stat_grid);
   TRY(dctz_gpu_quality_dev(ctx, ctx->in.p, ctx->out.p, N, datatype, d_res, st));
   CU(cudaMemcpyAsync(out4, d_res, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -802,7 +1133,7 @@ extern "C" int dctz_gpu_stats(dctz_gpu_ctx *ctx, const void *in, size_t N, int d
   const size_t es = datatype == DCTZ_GPU_DOUBLE ? 8 : 4;
   cudaStream_t st = ctx->stream;
   TRY(grow(ctx, ctx->in, N * es));
-  CU(cudaMemcpyAsync(ctx->in.p, in, N * es, cudaMemcpyHostToDevice, st));
+  TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr));
   if (datatype == DCTZ_GPU_DOUBLE) TRY(launch_stats<double>(ctx, (const double *)ctx->in.p, N, ctx->d_stats3, 1, N, nullptr, ctx->d_info, st));
   else TRY(launch_stats<float>(ctx, (const float *)ctx->in.p, N, ctx->d_stats3, 1, N, nullptr, ctx->d_info, st));
   CU(cudaMemcpyAsync(info, ctx->d_info, sizeof(Info), cudaMemcpyDeviceToHost, st));
@@ -825,22 +1156,32 @@ extern "C" int dctz_gpu_decompress_core(dctz_gpu_ctx *ctx, const uint8_t *bin_in
   TRY(grow(ctx, ctx->ac, (n_outliers ? n_outliers : 1) * 4));
   TRY(grow(ctx, ctx->qt, BLK * 8));
   TRY(grow(ctx, ctx->out, N * es));
-  CU(cudaMemcpyAsync(ctx->bins.p, bin_index, N, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->dc.p, DC, nblk * 4, cudaMemcpyHostToDevice, st));
-  if (n_outliers) CU(cudaMemcpyAsync(ctx->ac.p, AC_exact, n_outliers * 4, cudaMemcpyHostToDevice, st));
-  if (mode_qt) CU(cudaMemcpyAsync(ctx->qt.p, qtable, BLK * es, cudaMemcpyHostToDevice, st));
+  ctx->h2d_bytes = ctx->d2h_bytes = 0;
+  for (double &t : ctx->times) t = 0.0;
+  const auto t_begin = std::chrono::steady_clock::now();
+  if (ctx->timing) CU(cudaEventRecord(ctx->ev_time[0], st));
+  TRY(upload(ctx, ctx->bins.p, bin_index, N, 1024, nullptr));
+  TRY(upload(ctx, ctx->dc.p, DC, nblk * 4, 4, nullptr));
+  if (n_outliers) TRY(upload(ctx, ctx->ac.p, AC_exact, n_outliers * 4, 4, nullptr));
+  if (mode_qt) { CU(cudaMemcpyAsync(ctx->qt.p, qtable, BLK * es, cudaMemcpyHostToDevice, st)); ctx->h2d_bytes += BLK * es; }
+  if (ctx->timing) { CU(cudaStreamSynchronize(ctx->copy_stream)); CU(cudaEventRecord(ctx->ev_time[1], st)); }
   // The kernels never read past the n_outliers floats the caller handed over: a stream whose bin indices mark more
   // outliers than that is reported as corrupt (the reference would read whatever follows its buffer).
   CU(cudaMemsetAsync(&ctx->d_ctl[1].corrupt, 0, sizeof(unsigned), st));
-  ctx->ac_limit = n_outliers;
-  const int rc = dctz_gpu_decompress_dev(ctx, (const uint8_t *)ctx->bins.p, (const float *)ctx->dc.p, (const float *)ctx->ac.p, ctx->qt.p, N,
-                                         datatype, eb, sf, mode_qt, ctx->out.p, st);
-  ctx->ac_limit = ~0ull;
-  TRY(rc);
+  TRY(dctz_gpu_decompress_dev(ctx, (const uint8_t *)ctx->bins.p, (const float *)ctx->dc.p, (const float *)ctx->ac.p, n_outliers, ctx->qt.p, N,
+                              datatype, eb, sf, mode_qt, ctx->out.p, &ctx->d_ctl[1].corrupt, st));
+  if (ctx->timing) CU(cudaEventRecord(ctx->ev_time[2], st));
   unsigned corrupt = 0;
   CU(cudaMemcpyAsync(&corrupt, &ctx->d_ctl[1].corrupt, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out, ctx->out.p, N * es, cudaMemcpyDeviceToHost, st));
+  const auto t_gpu = std::chrono::steady_clock::now();
+  TRY(download(ctx, out, ctx->out.p, N * es, nullptr));
   CU(cudaStreamSynchronize(st));
+  if (ctx->timing) {
+    ctx->times[0] = elapsed_ms(ctx->ev_time[0], ctx->ev_time[1]);  // upload
+    ctx->times[2] = elapsed_ms(ctx->ev_time[1], ctx->ev_time[2]);  // outlier scan + dequantise + inverse DCT + de-scale (the reference's idct_t + sf_t)
+  }
+  ctx->times[3] = std::chrono::duration<double, std::milli>(t_gpu - t_begin).count();
+  ctx->times[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_gpu).count();
   if (corrupt) return fail(ctx, DCTZ_GPU_ECORRUPT, "decompress_core: the bin indices mark more outliers than the %llu given", (unsigned long long)n_outliers);
   return DCTZ_GPU_OK;
 }

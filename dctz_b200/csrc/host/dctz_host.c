@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -46,6 +47,17 @@ void dctz_set_device(int device) {
 }
 
 int dctz_build_is_qt(void) { return MODE_QT; }
+
+/* extension: stage timers / PCIe bytes of the GPU call inside the last dctz_compress or dctz_decompress
+ * (dctz_gpu_last_call_stats of the library's own context) */
+int dctz_host_last_call_stats(double times_ms[8], unsigned long long *h2d_bytes, unsigned long long *d2h_bytes) {
+  uint64_t h = 0, d = 0;
+  if (!g_ctx) return -1;
+  if (dctz_gpu_last_call_stats(g_ctx, times_ms, &h, &d) != DCTZ_GPU_OK) return -1;
+  if (h2d_bytes) *h2d_bytes = h;
+  if (d2h_bytes) *d2h_bytes = d;
+  return 0;
+}
 
 static dctz_gpu_ctx *gpu(void) {
   if (!g_ctx) {
@@ -274,6 +286,131 @@ static void deflate_sections(zjob *jobs, int nsec) {
   free(q.chunks);
 }
 
+/* ---- deflate that starts while the sections are still arriving from the GPU ---------------------------------------
+ * dctz_gpu_compress_core_cb reports every piece of bin_index / DC / AC_exact as it lands in host memory; zpipe turns
+ * the pieces of a large section into the same 1 MiB chunk jobs deflate_sections uses and feeds them to worker threads
+ * at once, so the deflate of the first pieces overlaps the PCIe transfer of the later ones and the host-side scaling
+ * of the caller's buffer.  The result is byte-identical to deflate_sections on the complete arrays. */
+typedef struct {
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  const unsigned char *src[3];
+  size_t total[3], ready[3], queued[3], nchunks[3];
+  zchunk *chunks[3];
+  int known[3], parallel[3];
+  size_t *fifo; /* (section << 56) | chunk index */
+  size_t head, tail, cap;
+  int closing, nthreads, started;
+  pthread_t *th;
+} zpipe;
+
+static void *zpipe_worker(void *arg) {
+  zpipe *z = (zpipe *)arg;
+  for (;;) {
+    size_t item;
+    pthread_mutex_lock(&z->mu);
+    while (z->head == z->tail && !z->closing) pthread_cond_wait(&z->cv, &z->mu);
+    if (z->head == z->tail) { pthread_mutex_unlock(&z->mu); return NULL; }
+    item = z->fifo[z->head++];
+    pthread_mutex_unlock(&z->mu);
+    zchunk_run(&z->chunks[item >> 56][item & (((size_t)1 << 56) - 1)]);
+  }
+}
+
+static void zpipe_init(zpipe *z) {
+  int t;
+  memset(z, 0, sizeof *z);
+  pthread_mutex_init(&z->mu, NULL);
+  pthread_cond_init(&z->cv, NULL);
+  z->nthreads = zlib_threads();
+  if (z->nthreads < 2) return; /* DCTZ_ZLIB_THREADS=1: the reference's single-stream calls, after the fact */
+  z->th = (pthread_t *)xmalloc((size_t)z->nthreads * sizeof(pthread_t), "threads");
+  for (t = 0; t < z->nthreads; t++, z->started++)
+    if (pthread_create(&z->th[t], NULL, zpipe_worker, z)) die("Error creating thread", NULL);
+}
+
+/* a section's base pointer and final size become known with its first piece */
+static void zpipe_feed(zpipe *z, int sec, const void *base, size_t total, size_t off, size_t len) {
+  size_t k;
+  pthread_mutex_lock(&z->mu);
+  if (!z->known[sec]) {
+    z->known[sec] = 1;
+    z->src[sec] = (const unsigned char *)base;
+    z->total[sec] = total;
+    z->parallel[sec] = z->nthreads > 1 && total > DCTZ_Z_SERIAL;
+    if (z->parallel[sec]) {
+      z->nchunks[sec] = (total + DCTZ_Z_CHUNK - 1) / DCTZ_Z_CHUNK;
+      z->chunks[sec] = (zchunk *)xmalloc(z->nchunks[sec] * sizeof(zchunk), "zlib chunks");
+      z->fifo = (size_t *)realloc(z->fifo, (z->cap + z->nchunks[sec]) * sizeof(size_t));
+      if (!z->fifo) die("Out of memory", "zlib queue");
+      z->cap += z->nchunks[sec];
+    }
+  }
+  if (off + len > z->ready[sec]) z->ready[sec] = off + len;
+  if (z->parallel[sec]) {
+    for (k = z->queued[sec]; k < z->nchunks[sec]; k++) { /* every chunk whose bytes are all there */
+      const size_t begin = k * DCTZ_Z_CHUNK, end = begin + DCTZ_Z_CHUNK < z->total[sec] ? begin + DCTZ_Z_CHUNK : z->total[sec];
+      zchunk *c = &z->chunks[sec][k];
+      if (end > z->ready[sec]) break;
+      c->src = z->src[sec];
+      c->begin = begin;
+      c->len = end - begin;
+      c->last = (end == z->total[sec]);
+      c->cap = compressBound((uLong)c->len) + 16;
+      c->dst = (unsigned char *)xmalloc(c->cap, "zlib chunk");
+      z->fifo[z->tail++] = ((size_t)sec << 56) | k;
+    }
+    z->queued[sec] = k;
+    pthread_cond_broadcast(&z->cv);
+  }
+  pthread_mutex_unlock(&z->mu);
+}
+
+/* all pieces have been fed: finish the three sections into jobs[i].dst / n_dst (same contract as deflate_sections) */
+static void zpipe_finish(zpipe *z, zjob *jobs, int nsec) {
+  int i, t;
+  pthread_mutex_lock(&z->mu);
+  z->closing = 1;
+  pthread_cond_broadcast(&z->cv);
+  pthread_mutex_unlock(&z->mu);
+  for (i = 0; i < nsec; i++) { /* the small sections meanwhile, on this thread: the reference's own single-stream call */
+    if (z->known[i] && z->parallel[i]) continue;
+    jobs[i].cap = compressBound((uLong)jobs[i].n_src);
+    jobs[i].dst = (unsigned char *)xmalloc(jobs[i].cap, "zlib output");
+    zjob_run(&jobs[i]);
+    if (jobs[i].rc != Z_STREAM_END) die("zlib stream error", "deflate");
+  }
+  for (t = 0; t < z->started; t++) pthread_join(z->th[t], NULL);
+  for (i = 0; i < nsec; i++) {
+    size_t total = 2 + 4, j;
+    uLong ad = adler32(0L, Z_NULL, 0);
+    unsigned char *o;
+    if (!(z->known[i] && z->parallel[i])) continue;
+    if (z->queued[i] != z->nchunks[i] || z->total[i] != jobs[i].n_src) die("internal error", "a stream section was not delivered completely");
+    for (j = 0; j < z->nchunks[i]; j++) {
+      if (z->chunks[i][j].rc != Z_OK) die("zlib stream error", "parallel deflate");
+      total += z->chunks[i][j].n_dst;
+    }
+    o = jobs[i].dst = (unsigned char *)xmalloc(total, "zlib output");
+    *o++ = 0x78; *o++ = 0x9C;
+    for (j = 0; j < z->nchunks[i]; j++) {
+      zchunk *c = &z->chunks[i][j];
+      memcpy(o, c->dst, c->n_dst);
+      o += c->n_dst;
+      ad = adler32_combine(ad, c->adler, (z_off_t)c->len);
+      free(c->dst);
+    }
+    *o++ = (unsigned char)(ad >> 24); *o++ = (unsigned char)(ad >> 16); *o++ = (unsigned char)(ad >> 8); *o++ = (unsigned char)ad;
+    jobs[i].n_dst = total;
+    jobs[i].rc = Z_STREAM_END;
+    free(z->chunks[i]);
+  }
+  free(z->fifo);
+  free(z->th);
+  pthread_mutex_destroy(&z->mu);
+  pthread_cond_destroy(&z->cv);
+}
+
 /* extension, used by the CPU tests: deflate one section exactly the way dctz_compress does.
  * Returns the compressed size, or 0 if `cap` is too small. */
 size_t dctz_host_deflate(const void *src, size_t n, void *dst, size_t cap) {
@@ -289,10 +426,29 @@ size_t dctz_host_deflate(const void *src, size_t n, void *dst, size_t cap) {
   return out;
 }
 
+/* extension, used by the CPU tests: the same section deflated while it "arrives" in pieces of `piece` bytes (zpipe) */
+size_t dctz_host_deflate_streamed(const void *src, size_t n, void *dst, size_t cap, size_t piece) {
+  zpipe z;
+  zjob j;
+  size_t off, out;
+  memset(&j, 0, sizeof j);
+  j.src = src;
+  j.n_src = n;
+  zpipe_init(&z);
+  if (piece == 0) piece = n ? n : 1;
+  for (off = 0; off < n; off += piece) zpipe_feed(&z, 0, src, n, off, n - off < piece ? n - off : piece);
+  if (n == 0) zpipe_feed(&z, 0, src, 0, 0, 0);
+  zpipe_finish(&z, &j, 1);
+  out = j.n_dst <= cap ? j.n_dst : 0;
+  if (out) memcpy(dst, j.dst, out);
+  free(j.dst);
+  return out;
+}
+
 /* ---- stream assembly (dctz-comp-lib.c:583-846): side files, three deflates, header, concatenation ---- */
 static size_t assemble_stream(t_datatype dt, size_t n, double error_bound, const dctz_gpu_info *info, const t_bin_id *bin_index,
                               const float *DC, const float *AC_exact, const void *qtable, const void *qtable_raw, unsigned char *out,
-                              int write_dumps) {
+                              int write_dumps, zpipe *zp) {
   const int is_double = (dt == DOUBLE);
   const size_t es = is_double ? sizeof(double) : sizeof(float);
   const size_t nblk = (n + DCTZ_BLK_SZ - 1) / DCTZ_BLK_SZ, qbytes = MODE_QT ? DCTZ_BLK_SZ * es : 0;
@@ -310,7 +466,8 @@ static size_t assemble_stream(t_datatype dt, size_t n, double error_bound, const
   jobs[0].src = bin_index; jobs[0].n_src = n;
   jobs[1].src = DC;        jobs[1].n_src = nblk * sizeof(float);
   jobs[2].src = AC_exact;  jobs[2].n_src = (size_t)info->n_outliers * sizeof(float);
-  deflate_sections(jobs, 3);
+  if (zp) zpipe_finish(zp, jobs, 3); /* most of the work is done already */
+  else deflate_sections(jobs, 3);
 
   memset(&h, 0, sizeof h); /* the reference leaves padding uninitialised; zero is as valid and reproducible */
   h.datatype = dt;
@@ -338,13 +495,60 @@ static size_t assemble_stream(t_datatype dt, size_t n, double error_bound, const
 }
 
 /* ---- dctz_compress (dctz.h:126) ------------------------------------------------------------------ */
+static double wall(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+static int env_on(const char *name) {
+  const char *e = getenv(name);
+  return e && *e && *e != '0';
+}
+
+typedef struct {
+  zpipe *zp;
+  const void *base[3];
+  size_t n, nblk;
+  const dctz_gpu_info *info;
+} feed_ctx;
+
+static void on_section(void *user, int section, size_t off, size_t bytes) {
+  feed_ctx *f = (feed_ctx *)user;
+  const size_t total = section == 0 ? f->n : section == 1 ? f->nblk * sizeof(float) : (size_t)f->info->n_outliers * sizeof(float);
+  zpipe_feed(f->zp, section, f->base[section], total, off, bytes);
+}
+
+/* -DDCT_FILE_DEBUG of the reference (dctz-comp-lib.c:422-433): the coefficients of the scaled data and the DC array.
+ * The fused kernels never materialise the coefficients, so this debug dump transforms the (by now scaled) input once
+ * more through the DCT-only entry point.  DCTZ_DCT_FILE_DEBUG=1 enables it. */
+static void dump_coefficients(const t_var *var, size_t n, const float *DC, size_t nblk) {
+  const int is_double = (var->datatype == DOUBLE);
+  const size_t es = is_double ? sizeof(double) : sizeof(float), nfull = n / DCTZ_BLK_SZ, rem = n % DCTZ_BLK_SZ;
+  const unsigned char *src = is_double ? (const unsigned char *)var->buf.d : (const unsigned char *)var->buf.f;
+  unsigned char *coef = (unsigned char *)xmalloc(n * es, "dct_result");
+  const int code = is_double ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT;
+  if (nfull && dctz_gpu_dct_blocks(gpu(), src, coef, nfull, DCTZ_BLK_SZ, code, 0) != DCTZ_GPU_OK) die("GPU DCT failed", dctz_gpu_last_error(g_ctx));
+  if (rem && dctz_gpu_dct_blocks(gpu(), src + nfull * DCTZ_BLK_SZ * es, coef + nfull * DCTZ_BLK_SZ * es, 1, (int)rem, code, 0) != DCTZ_GPU_OK)
+    die("GPU DCT failed", dctz_gpu_last_error(g_ctx));
+  dump("dct_result.bin", coef, n * es);
+  dump("DC.bin", DC, nblk * sizeof(float));
+  free(coef);
+}
+
 int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error_bound) {
   const int is_double = (var->datatype == DOUBLE);
+  const int timing = env_on("DCTZ_TIME_DEBUG");
   size_t n, nblk;
   t_bin_id *bin_index;
   float *DC, *AC_exact;
   unsigned char qtable[DCTZ_BLK_SZ * sizeof(double)], qtable_raw[DCTZ_BLK_SZ * sizeof(double)];
   dctz_gpu_info info;
+  zpipe zp;
+  feed_ctx fc;
+  double t0 = wall(), t1, t2;
+  void *data = is_double ? (void *)var->buf.d : (void *)var->buf.f;
+  int rc;
 
   if (error_bound < 1E-6) { /* dctz-comp-lib.c:135-138 */
     fprintf(stderr, "ERROR: error bound should be no less than 1E-6.\n");
@@ -358,23 +562,43 @@ int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error
   AC_exact = (float *)xmalloc(n * sizeof(float), "AC_exact");
 
   /* the whole hot path: statistics, scaling (left in the caller's buffer like dctz-comp-lib.c:198,213),
-   * block DCT, binning quantiser, ordered outliers, QT table + rescale */
-  if (dctz_gpu_compress_core(gpu(), is_double ? (void *)var->buf.d : (void *)var->buf.f, n, is_double ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT,
-                             error_bound, MODE_QT, is_double ? (void *)var->buf.d : (void *)var->buf.f, bin_index, DC, AC_exact,
-                             MODE_QT ? qtable : NULL, MODE_QT ? qtable_raw : NULL, &info) != DCTZ_GPU_OK)
-    die("GPU compress failed", dctz_gpu_last_error(g_ctx));
+   * block DCT, binning quantiser, ordered outliers, QT table + rescale.  The sections are deflated as they arrive. */
+  dctz_gpu_set_timing(gpu(), timing);
+  if (!timing) {
+    zpipe_init(&zp);
+    fc.zp = &zp; fc.base[0] = bin_index; fc.base[1] = DC; fc.base[2] = AC_exact; fc.n = n; fc.nblk = nblk; fc.info = &info;
+    rc = dctz_gpu_compress_core_cb(g_ctx, data, n, is_double ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT, error_bound, MODE_QT, data, bin_index, DC,
+                                   AC_exact, MODE_QT ? qtable : NULL, MODE_QT ? qtable_raw : NULL, &info, on_section, &fc);
+  } else { /* the reference's -DTIME_DEBUG lines: every stage on its own, nothing overlapped */
+    rc = dctz_gpu_compress_core(g_ctx, data, n, is_double ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT, error_bound, MODE_QT, data, bin_index, DC,
+                                AC_exact, MODE_QT ? qtable : NULL, MODE_QT ? qtable_raw : NULL, &info);
+  }
+  if (rc != DCTZ_GPU_OK) die("GPU compress failed", dctz_gpu_last_error(g_ctx));
+  t1 = wall();
+  if (env_on("DCTZ_DCT_FILE_DEBUG") && dumps_enabled()) dump_coefficients(var, n, DC, nblk);
   *outSize = assemble_stream(var->datatype, n, error_bound, &info, bin_index, DC, AC_exact, qtable, qtable_raw,
-                             is_double ? (unsigned char *)var_z->buf.d : (unsigned char *)var_z->buf.f, 1);
+                             is_double ? (unsigned char *)var_z->buf.d : (unsigned char *)var_z->buf.f, 1, timing ? NULL : &zp);
+  t2 = wall();
   free(bin_index);
   free(DC);
   free(AC_exact);
+  if (timing) { /* same lines as dctz-comp-lib.c:762-773; sf_t / dct_t are CUDA-event times of the two kernel stages */
+    double ms[8];
+    dctz_gpu_last_call_stats(g_ctx, ms, NULL, NULL);
+    printf("sf_t=%f(s), dct_t=%f(s), zlib_t(compress)=%f(s)\n", ms[1] / 1e3, ms[2] / 1e3, t2 - t1);
+    printf("h2d_t=%f(s), d2h_scale_t=%f(s)\n", ms[0] / 1e3, ms[4] / 1e3);
+    printf("comp_time = %f (s), compression rate = %f (MB/s)\n", t2 - t0, ((double)n * sizeof(double) / (1024.0 * 1024.0)) / (t2 - t0));
+  }
   printf("outSize = %zu\n", *outSize);
   return 1;
 }
 
 /* ---- dctz_decompress (dctz.h:127) ---------------------------------------------------------------- */
-/* decode one standard stream at `p` into `out` (room for its num_elements); returns the stream's element count */
-static size_t decode_stream(dctz_gpu_ctx *ctx, t_datatype dt, const unsigned char *p, void *out, int chatty) {
+static double g_inflate_s = 0.0; /* wall clock of the three inflates of the last dctz_decompress call */
+
+/* decode one standard stream at `p` into `out` (room for `out_cap` elements; 0 = the caller vouches for the room, as
+ * dctz_decompress's interface does); returns the stream's element count */
+static size_t decode_stream(dctz_gpu_ctx *ctx, t_datatype dt, const unsigned char *p, void *out, size_t out_cap, int chatty) {
   const int is_double = (dt == DOUBLE);
   const size_t es = is_double ? sizeof(double) : sizeof(float);
   struct header h;
@@ -391,6 +615,8 @@ static size_t decode_stream(dctz_gpu_ctx *ctx, t_datatype dt, const unsigned cha
   nblk = (n + DCTZ_BLK_SZ - 1) / DCTZ_BLK_SZ;
   n_out = h.tot_AC_exact_count;
   if (n == 0) die("corrupt stream", "num_elements == 0");
+  if (out_cap && n > out_cap) die("corrupt stream", "num_elements exceeds the room left in the output");
+  if (h.datatype != dt) die("corrupt stream", "datatype in the header differs from the caller's");
   bin_index = (t_bin_id *)xmalloc(n, "bin_index");
   DC = (float *)xmalloc(nblk * sizeof(float), "DC");
   AC_exact = (float *)xmalloc((n_out ? n_out : 1) * sizeof(float), "AC_exact");
@@ -401,7 +627,11 @@ static size_t decode_stream(dctz_gpu_ctx *ctx, t_datatype dt, const unsigned cha
   jobs[2].src = (const unsigned char *)jobs[1].src + h.DC_sz_compressed;
   jobs[2].n_src = h.AC_exact_sz_compressed;     jobs[2].dst = (unsigned char *)AC_exact;  jobs[2].cap = (n_out ? n_out : 1) * sizeof(float);
   jobs[0].inflate_mode = jobs[1].inflate_mode = jobs[2].inflate_mode = 1;
-  run_zjobs(jobs, 3);
+  {
+    const double tz = wall();
+    run_zjobs(jobs, 3);
+    if (chatty) g_inflate_s = wall() - tz;
+  }
   if (jobs[0].n_dst != n || jobs[1].n_dst != nblk * sizeof(float) || jobs[2].n_dst != n_out * sizeof(float))
     die("corrupt stream", "section sizes do not match the header");
   if (chatty) printf("uncompressed bin_index size is: %lu\n", (unsigned long)jobs[0].n_dst);
@@ -420,8 +650,20 @@ static size_t decode_stream(dctz_gpu_ctx *ctx, t_datatype dt, const unsigned cha
 
 int dctz_decompress(t_var *var_z, t_var *var_r) {
   const int is_double = (var_z->datatype == DOUBLE);
-  decode_stream(gpu(), var_z->datatype, is_double ? (const unsigned char *)var_z->buf.d : (const unsigned char *)var_z->buf.f,
-                is_double ? (void *)var_r->buf.d : (void *)var_r->buf.f, 1);
+  const int timing = env_on("DCTZ_TIME_DEBUG");
+  const double t0 = wall();
+  size_t n;
+  dctz_gpu_set_timing(gpu(), timing);
+  n = decode_stream(g_ctx, var_z->datatype, is_double ? (const unsigned char *)var_z->buf.d : (const unsigned char *)var_z->buf.f,
+                    is_double ? (void *)var_r->buf.d : (void *)var_r->buf.f, 0, 1);
+  if (timing) { /* dctz-decomp-lib.c:513-528 */
+    double ms[8];
+    const double t1 = wall();
+    dctz_gpu_last_call_stats(g_ctx, ms, NULL, NULL);
+    printf("sf_t=%f(s), idct_t=%f(s), zlib_t(uncompress)=%f(s)\n", 0.0, ms[2] / 1e3, g_inflate_s);
+    printf("h2d_t=%f(s), d2h_t=%f(s)\n", ms[0] / 1e3, ms[4] / 1e3);
+    printf("decomp_time = %f (s), decompression rate = %f (MB/s)\n", t1 - t0, ((double)n * sizeof(double) / (1024.0 * 1024.0)) / (t1 - t0));
+  }
   return 1;
 }
 
@@ -449,7 +691,9 @@ typedef struct {
   size_t *sizes;
   /* decode */
   const unsigned char *in;
-  const size_t *offs;
+  const size_t *offs;      /* byte offset of every stream in the container */
+  const size_t *elem_offs; /* element offset of every stream in the output (prefix sum of the streams' num_elements) */
+  const size_t *elem_cnt;
   unsigned char *out;
 } large_job;
 
@@ -495,7 +739,7 @@ static void *large_compress_worker(void *arg) {
       j->failed = 1;
     } else {
       j->streams[i] = (unsigned char *)xmalloc(64 + n + n / 8 + nblk * 4 + (size_t)info.n_outliers * 4 + 4096, "stream");
-      j->sizes[i] = assemble_stream(j->dt, n, j->eb, &info, bin_index, DC, AC_exact, qtable, qtable_raw, j->streams[i], 0);
+      j->sizes[i] = assemble_stream(j->dt, n, j->eb, &info, bin_index, DC, AC_exact, qtable, qtable_raw, j->streams[i], 0, NULL);
     }
     free(bin_index); free(DC); free(AC_exact);
     if (j->failed) break;
@@ -510,7 +754,8 @@ static void *large_decode_worker(void *arg) {
   dctz_gpu_ctx *ctx = NULL;
   size_t i;
   if (dctz_gpu_create(&ctx, j->device) != DCTZ_GPU_OK) { j->failed = 1; return NULL; }
-  for (i = (size_t)j->device; i < j->npieces; i += (size_t)j->ndev) decode_stream(ctx, j->dt, j->in + j->offs[i], j->out + i * g_piece * es, 0);
+  for (i = (size_t)j->device; i < j->npieces; i += (size_t)j->ndev)
+    decode_stream(ctx, j->dt, j->in + j->offs[i], j->out + j->elem_offs[i] * es, j->elem_cnt[i], 0);
   dctz_gpu_destroy(ctx);
   return NULL;
 }
@@ -584,17 +829,35 @@ size_t dctz_decompress_large(const void *in, size_t in_size, void *out, size_t o
   const unsigned char *p = (const unsigned char *)in;
   unsigned long long nt;
   unsigned int d, ns;
-  size_t *offs, off, i;
+  size_t *offs, *eoffs, *ecnt, off, eoff, i;
   large_job j;
   if (in_size < 24 || memcmp(p, "DCTZMS01", 8)) die("corrupt stream", "not a DCTZ multi-stream container");
   memcpy(&nt, p + 8, 8); memcpy(&d, p + 16, 4); memcpy(&ns, p + 20, 4);
   if (nt > out_elements) die("output buffer too small", "dctz_decompress_large");
-  offs = (size_t *)xmalloc(ns * sizeof(size_t), "offsets");
+  if (d != (unsigned int)FLOAT && d != (unsigned int)DOUBLE) die("corrupt stream", "container datatype");
+  if (ns == 0 || (size_t)ns > (in_size - 24) / 8) die("corrupt stream", "container stream count");
+  offs = (size_t *)xmalloc(3 * (size_t)ns * sizeof(size_t), "offsets");
+  eoffs = offs + ns; ecnt = eoffs + ns;
+  /* The container does not store a piece length: every stream's place in the output follows from the element counts
+   * in the streams' own headers (prefix sum), checked against the container's total before anything is decoded. */
   off = 24 + 8 * (size_t)ns;
-  for (i = 0; i < ns; i++) { unsigned long long sz; memcpy(&sz, p + 24 + 8 * i, 8); offs[i] = off; off += (size_t)sz; }
-  if (off > in_size) die("corrupt stream", "container sizes exceed the buffer");
+  eoff = 0;
+  for (i = 0; i < ns; i++) {
+    unsigned long long sz;
+    struct header h;
+    memcpy(&sz, p + 24 + 8 * i, 8);
+    if (sz < sizeof h || sz > in_size - off) die("corrupt stream", "container sizes exceed the buffer");
+    memcpy(&h, p + off, sizeof h);
+    if ((unsigned int)h.datatype != d) die("corrupt stream", "a piece's datatype differs from the container's");
+    if (h.num_elements == 0 || (unsigned long long)h.num_elements > nt - eoff) die("corrupt stream", "the pieces hold more elements than the container states");
+    if (i + 1 < ns && h.num_elements % DCTZ_BLK_SZ) die("corrupt stream", "only the last piece may end with a partial block");
+    offs[i] = off; eoffs[i] = eoff; ecnt[i] = h.num_elements;
+    off += (size_t)sz;
+    eoff += h.num_elements;
+  }
+  if (eoff != nt) die("corrupt stream", "the pieces' element counts do not add up to the container's total");
   memset(&j, 0, sizeof j);
-  j.dt = (t_datatype)d; j.N = (size_t)nt; j.npieces = ns; j.in = p; j.offs = offs; j.out = (unsigned char *)out;
+  j.dt = (t_datatype)d; j.N = (size_t)nt; j.npieces = ns; j.in = p; j.offs = offs; j.elem_offs = eoffs; j.elem_cnt = ecnt; j.out = (unsigned char *)out;
   run_large(&j, large_decode_worker);
   free(offs);
   return (size_t)nt;

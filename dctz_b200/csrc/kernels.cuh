@@ -297,22 +297,22 @@ __global__ void k_finalize(const double *stats_all, int nranks, unsigned long lo
 __device__ __forceinline__ unsigned quant_exact_d(double c, double rmin, double rmax, double bw, unsigned *edge) {
   if (c < rmin || c > rmax) return 255u;
   const double q = __ddiv_rn(__dsub_rn(c, rmin), bw);
-  int t = (int)q;  // (t_bin_id) truncation; q in [0, 255]
-  if (t > 254) { t = 254; (*edge)++; }
+  const int t = (int)q;  // (t_bin_id) truncation; q in [0, 255]
+  if (t > 254) { (*edge)++; return 255u; }  // item == range_max: conv_tbl[255] is out of bounds in the reference -> outlier
   return conv_ordinal(t);
 }
 __device__ __forceinline__ unsigned quant_exact(double c, const QuantConsts<double> &q, unsigned *edge) {
   return quant_exact_d(c, q.rmin, q.rmax, q.bw, edge);
 }
-__device__ __forceinline__ unsigned quant_exact_f(float c, float rmin, float rmax, float bw) {
+__device__ __forceinline__ unsigned quant_exact_f(float c, float rmin, float rmax, float bw, unsigned *edge) {
   if (c < rmin || c > rmax) return 255u;
   const float q = __fdiv_rn(__fsub_rn(c, rmin), bw);
-  int t = (int)q;
-  if (t > 254) t = 254;
+  const int t = (int)q;
+  if (t > 254) { (*edge)++; return 255u; }
   return conv_ordinal(t);
 }
-__device__ __forceinline__ unsigned quant_exact(float c, const QuantConsts<float> &q, unsigned *) {
-  return quant_exact_f(c, q.rmin, q.rmax, q.bw);
+__device__ __forceinline__ unsigned quant_exact(float c, const QuantConsts<float> &q, unsigned *edge) {
+  return quant_exact_f(c, q.rmin, q.rmax, q.bw, edge);
 }
 
 template <typename T> struct BitsOf;
@@ -337,6 +337,9 @@ template <> struct BitsOf<float> {
 //           range saturates.
 //   float : F2I with round-down.
 // id = conv_tbl[t] = max(2t-255, 254-2t) = max(b, ~b) with b = 2t-255; t clamped to 255 gives id 255 (outlier).
+// t == 255 includes item == range_max exactly, where the reference indexes conv_tbl[255] one past the table (UB):
+// every path of this library (this quantiser, quant_exact for the tail block) and the oracle store such a
+// coefficient as an outlier.
 template <typename T> struct Quantizer;
 template <> struct Quantizer<double> {
   double kq;
@@ -915,9 +918,9 @@ __global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ 
 
 // ------------------------------------------------------------------------------------------
 // K2b (QT): rescale the ordered raw outliers with the global per-position table
-// (dctz-comp-lib.c:450-461 clamp, 485-533 rescale).  Entries whose rescaled value falls back
-// inside the bin range are dropped by the reference (their bin_index stays 255; :494-506): they are
-// flagged here and squeezed out by k_qt_compact, which is a no-op unless that ever happens.
+// (dctz-comp-lib.c:450-461 clamp, 485-533 rescale).  An entry whose rescaled value falls back inside
+// the bin range would be dropped by the reference (its bin_index stays 255; :494-506); see qt_rescale_one
+// for why that cannot happen -- such entries are only counted (info->n_qt_dropped).
 // ------------------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ Divisor<T> sf_divisor(const DevParams *p);
 template <> __device__ __forceinline__ Divisor<double> sf_divisor<double>(const DevParams *p) {
@@ -993,16 +996,24 @@ template <typename T> struct QtConsts {
   double den;       // error_bound * qt_factor  (dctz-decomp-lib.c:405,450)
 };
 
+// The branch is chosen by the SIGN of the coefficient, not by re-testing it against the range: the element IS an outlier
+// (its bin id says so), and the fast quantiser's verdict may differ from an exact `item > range_max` at a
+// quantisation-boundary tie.  Wherever the reference's own tests (:488/:490, :514/:516) fire, the sign test picks the
+// same branch; at a tie it keeps the outlier an outlier (range_max + something positive), so the stream never desyncs.
+// Returns false if the rescaled value fell back inside the range (the reference would then drop it although its bin
+// id stays 255, :494-506).  That cannot happen for valid input: it needs |c|/qtable[j] * 10 eb <= ulp(255 eb)/2, i.e.
+// qtable[j] >= 168 (float; far more for double) while |c_j| <= sqrt(2/64)*64*10 = 113 for data scaled into (1,10]
+// (DESIGN.md §2); the count is kept as a diagnostic (info->n_qt_dropped, always 0).
 __device__ __forceinline__ bool qt_rescale_one(double item, double q, const QtConsts<double> &k, float *out) {
-  if (item < k.rmin) item = __dadd_rn(__dmul_rn(__dmul_rn(__ddiv_rn(item, q), k.eb), 10.0), k.rmin);
-  else if (item > k.rmax) item = __dadd_rn(__dmul_rn(__dmul_rn(__ddiv_rn(item, q), k.eb), 10.0), k.rmax);
+  if (item < 0.0) item = __dadd_rn(__dmul_rn(__dmul_rn(__ddiv_rn(item, q), k.eb), 10.0), k.rmin);  // :489
+  else item = __dadd_rn(__dmul_rn(__dmul_rn(__ddiv_rn(item, q), k.eb), 10.0), k.rmax);            // :491
   *out = (float)item;  // :497 USE_TRUNCATE
   return (item < k.rmin || item > k.rmax);
 }
 __device__ __forceinline__ bool qt_rescale_one(float item, float q, const QtConsts<float> &k, float *out) {
   // (float/float) in float, then promoted to double by error_bound; qt_factor.f = 10.0f; result stored to float
-  if (item < k.rmin) item = (float)__dadd_rn(__dmul_rn(__dmul_rn((double)__fdiv_rn(item, q), k.eb), (double)10.0f), (double)k.rmin);
-  else if (item > k.rmax) item = (float)__dadd_rn(__dmul_rn(__dmul_rn((double)__fdiv_rn(item, q), k.eb), (double)10.0f), (double)k.rmax);
+  if (item < 0.0f) item = (float)__dadd_rn(__dmul_rn(__dmul_rn((double)__fdiv_rn(item, q), k.eb), (double)10.0f), (double)k.rmin);  // :515
+  else item = (float)__dadd_rn(__dmul_rn(__dmul_rn((double)__fdiv_rn(item, q), k.eb), (double)10.0f), (double)k.rmax);             // :517
   *out = item;
   return (item < k.rmin || item > k.rmax);
 }
@@ -1062,30 +1073,6 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
     }
   }
   if (dropped) atomicAdd(&info->n_qt_dropped, (unsigned long long)dropped);
-}
-
-// Serial fallback for the reference's "rescaled outlier fell back inside the bin range" quirk
-// (dctz-comp-lib.c:494-506: such a value is not stored although its bin index stays 255).  It is a
-// no-op unless that ever happens (it cannot for realistic data).
-template <typename T>
-__global__ void __launch_bounds__(32) k_qt_compact(const unsigned *__restrict__ counts, unsigned ntiles, const T *__restrict__ raw_slots,
-                                                   const uint8_t *__restrict__ j_slots, const T *__restrict__ qraw, QtConsts<T> k,
-                                                   float *ac_out, Info *info, const DevParams *__restrict__ params, unsigned tail_tile) {
-  if (info->n_qt_dropped == 0) return;  // the only path ever taken in practice
-  if (threadIdx.x != 0) return;
-  const Divisor<T> sfdiv = sf_divisor<T>(params);
-  unsigned long long w = 0;
-  for (unsigned t = 0; t < ntiles; t++) {
-    const unsigned long long slot = (unsigned long long)t * TILE_SLOT;
-    for (unsigned i = 0; i < counts[t]; i++) {
-      T q = qraw[j_slots[slot + i]];
-      if (j_slots[slot + i] >= 1 && q < (T)1.0) q = (T)1.0;
-      float o;
-      const T c = (t != tail_tile) ? div_exact(raw_slots[slot + i], sfdiv) : raw_slots[slot + i];
-      if (qt_rescale_one(c, q, k, &o)) ac_out[w++] = o;
-    }
-  }
-  info->n_outliers = w;
 }
 
 // Decompress pre-pass: number of 255 markers at positions j >= 1 per warp tile (32 blocks = 2 KB of bin ids).
@@ -1226,7 +1213,8 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
              const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
              const __grid_constant__ CUtensorMap tmap_out, const unsigned *__restrict__ counts,
              const unsigned long long *__restrict__ group_prefix, const unsigned long long *__restrict__ chunk_prefix,
-             const unsigned long long *__restrict__ n_outliers_total, unsigned long long n_limit, TileControl *ctl, unsigned batch) {
+             const unsigned long long *__restrict__ n_outliers_total, unsigned long long n_limit, TileControl *ctl,
+             unsigned *corrupt_flag, int dc_aligned16, unsigned batch) {
   typedef typename ArithOf<T>::type A;
   typedef DecompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -1288,7 +1276,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     // A stream whose bin indices mark more outliers than AC_exact holds (n_limit: its length as the caller states it)
     // is corrupt: such a tile decodes without its outliers and the launch is flagged; nothing is read out of bounds.
     e.bad = e.base + e.total > n_limit;
-    if (e.bad) { e.total = 0u; ctl->corrupt = 1u; }
+    if (e.bad) { e.total = 0u; *corrupt_flag = 1u; }
     return e;
   };
   // Stage layout: the stage mirrors the 16-byte granules of AC_exact that hold the tile's run: outlier i lives at
@@ -1314,8 +1302,9 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   struct Ragged { float v; int idx; };
   auto issue_tile = [&](unsigned t, const Extent &e) -> Ragged {  // bin ids (2 KB) + DC (128 B) [+ outliers] of tile t
     const unsigned rows = rows_of(t);
-    // the DC slice is 4*rows bytes: bulk copies need a multiple of 16, so partial tiles load DC directly
-    const bool dc_bulk = (rows == WTILE);
+    // the DC slice is 4*rows bytes: bulk copies need a multiple of 16 bytes at a 16-byte aligned address, so partial
+    // tiles -- and slabs whose DC pointer is only float-aligned (a slice of a concatenated DC array) -- load DC directly
+    const bool dc_bulk = (rows == WTILE) && dc_aligned16;
     const Plan pl = plan_of(e);
     unsigned k0 = 0, k1 = 0;  // stage indices: the bulk copy covers [k0, k1), the run is [lead, kend)
     if (pl.prefetch) {
@@ -1375,7 +1364,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
         w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
       }
     }
-    float dcv = (rows == WTILE) ? dcbuf[lane] : (active ? __ldg(dc_in + blk) : 0.f);
+    float dcv = (rows == WTILE && dc_aligned16) ? dcbuf[lane] : (active ? __ldg(dc_in + blk) : 0.f);
     if (!active) {
 #pragma unroll
       for (int q = 0; q < 16; q++) w[q] = 0;
@@ -1538,9 +1527,12 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     nn = seq.advance(lane);
   }
   bulk_wait_all();
+  // every warp still has one look-ahead ticket request outstanding (TileSeq::advance): its result is consumed here, so
+  // the increment has been performed before this thread's fence and therefore before the last CTA resets the counter
+  if (lane == 0) (void)pin_here(seq.pend);
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
     const unsigned prev = atomicAdd(&ctl->done, 1u);
     if (prev == gridDim.x - 1) { ctl->ticket = 0u; ctl->done = 0u; }
   }
@@ -1553,7 +1545,7 @@ __global__ void __launch_bounds__(32) k_tail_decompress(const uint8_t *__restric
                                                         int rem, unsigned long long blk_index, T bin_width, T sf,
                                                         QtConsts<T> qk, T *out, const unsigned long long *n_consumed,
                                                         unsigned long long pos0_if_no_full_blocks, unsigned long long n_limit,
-                                                        TileControl *ctl) {
+                                                        unsigned *corrupt_flag) {
   __shared__ double cs[BLK];
   const int lane = threadIdx.x;
   unsigned long long base = n_consumed ? *n_consumed : pos0_if_no_full_blocks;
@@ -1569,7 +1561,7 @@ __global__ void __launch_bounds__(32) k_tail_decompress(const uint8_t *__restric
       else if (outl) {
         const unsigned long long at = base + __popc(m & ((1u << lane) - 1u));
         float a = 0.f;
-        if (at < n_limit) a = ac_in[at]; else ctl->corrupt = 1u;  // more markers than outliers: corrupt stream
+        if (at < n_limit) a = ac_in[at]; else *corrupt_flag = 1u;  // more markers than outliers: corrupt stream
         if (QT) v = (T)qt_unscale_one(a, qtable[j], qk); else v = (T)a;
       } else {
         if (sizeof(T) == 8) v = (T)__dmul_rn((double)center_multiple(id), (double)bin_width);
@@ -1595,11 +1587,34 @@ __global__ void __launch_bounds__(32) k_tail_decompress(const uint8_t *__restric
 // ------------------------------------------------------------------------------------------
 // Small utility kernels
 // ------------------------------------------------------------------------------------------
+// x <- x / sf (IEEE division; dctz-comp-lib.c:193-216) or x <- x * sf (dctz-test.c:186-210), 128-bit accesses, four
+// independent vectors in flight per thread; the ragged head/tail around the 16-byte-aligned body is done by CTA 0.
 template <typename T>
 __global__ void __launch_bounds__(256) k_scale(T *x, size_t n, T sf, int multiply) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const T v = x[i];
-    x[i] = multiply ? v * sf : v / sf;  // IEEE mul / div (no fast-math, nothing to contract)
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const size_t head = ((16 - ((uintptr_t)x & 15)) & 15) / sizeof(T);  // elements before the first 16-byte boundary
+  const size_t h = head < n ? head : n;
+  uint4 *body = reinterpret_cast<uint4 *>(x + h);
+  const size_t nvec = (n - h) / VEC;
+  auto op = [&](T v) -> T { return multiply ? v * sf : v / sf; };  // IEEE mul / div (no fast-math, nothing to contract)
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (i + u * stride < nvec) v[u] = body[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (i + u * stride < nvec) {
+        T *e = reinterpret_cast<T *>(&v[u]);
+#pragma unroll
+        for (int q = 0; q < VEC; q++) e[q] = op(e[q]);
+        body[i + u * stride] = v[u];
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (size_t k = threadIdx.x; k < h; k += blockDim.x) x[k] = op(x[k]);
+    for (size_t k = h + nvec * VEC + threadIdx.x; k < n; k += blockDim.x) x[k] = op(x[k]);
   }
 }
 
@@ -1779,16 +1794,35 @@ struct QualityPartial { double vmin, vmax, maxdiff, sumsq; };
 template <typename T>
 __global__ void __launch_bounds__(256) k_quality(const T *__restrict__ a, const T *__restrict__ b, size_t n, QualityPartial *partials,
                                                  unsigned *done_counter, QualityPartial *out) {
+  constexpr int VEC = 16 / (int)sizeof(T);
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   double vmin = inf, vmax = -inf, md = 0.0, ss = 0.0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const T va = a[i];
-    const double e = (double)(T)(va - b[i]);
+  auto acc = [&](T va, T vb) {
+    const double e = (double)(T)(va - vb);
     vmin = fmin(vmin, (double)va);
     vmax = fmax(vmax, (double)va);
     md = fmax(md, fabs(e));
     ss = __fma_rn(e, e, ss);
+  };
+  // 128-bit loads when both arrays are 16-byte aligned (two vectors of each in flight per thread), scalar otherwise
+  const bool vec_ok = ((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0;
+  const size_t nvec = vec_ok ? n / VEC : 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint4 *a4 = reinterpret_cast<const uint4 *>(a), *b4 = reinterpret_cast<const uint4 *>(b);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += 2 * stride) {
+    uint4 va[2], vb[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) if (i + u * stride < nvec) { va[u] = __ldg(a4 + i + u * stride); vb[u] = __ldg(b4 + i + u * stride); }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (i + u * stride < nvec) {
+        const T *ea = reinterpret_cast<const T *>(&va[u]), *eb = reinterpret_cast<const T *>(&vb[u]);
+#pragma unroll
+        for (int q = 0; q < VEC; q++) acc(ea[q], eb[q]);
+      }
+    }
   }
+  for (size_t i = nvec * VEC + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc(a[i], b[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     vmin = fmin(vmin, __shfl_xor_sync(0xFFFFFFFFu, vmin, o));

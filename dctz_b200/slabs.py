@@ -75,16 +75,23 @@ def all_gather_stats(stats3, world: int):
     return out
 
 
-def all_reduce_qtable(qraw, rank: int, world: int):
+def last_rank_with_data(n_elements: int, world: int) -> int:
+    """the rank whose slab holds the field's last block (trailing ranks of a small field may hold nothing)"""
+    parts = partition(n_elements, world)
+    return max(r for r, (_, c) in enumerate(parts) if c > 0)
+
+
+def all_reduce_qtable(qraw, rank: int, world: int, src_last: int | None = None):
     """QT mode: entries 1..63 are per-position maxima of |outlier| -> MAX over ranks; entry 0 is the DC
-    coefficient of the field's LAST block -> taken from the last rank that holds data."""
-    import torch
+    coefficient of the field's LAST block -> broadcast from the last rank that HOLDS DATA (`src_last`,
+    see last_rank_with_data; default: the last rank)."""
     import torch.distributed as dist
 
     if world == 1:
         return qraw
+    src = world - 1 if src_last is None else int(src_last)
     first = qraw[0:1].clone()
     dist.all_reduce(qraw, op=dist.ReduceOp.MAX)
-    dist.broadcast(first, src=world - 1)
+    dist.broadcast(first, src=src)
     qraw[0:1] = first
     return qraw

@@ -72,6 +72,9 @@ void idct_finish_f(void);
  * DCTZ_GPU_DEVICE environment variable).  */
 int dctz_build_is_qt(void);
 void dctz_set_device(int device);
+/* stage timers (ms: upload, statistics, transform, wall to kernels, wall of downloads + scaling) and PCIe bytes of the
+ * GPU call inside the last dctz_compress / dctz_decompress; 0 on success */
+int dctz_host_last_call_stats(double times_ms[8], unsigned long long *h2d_bytes, unsigned long long *d2h_bytes);
 /* Large fields (beyond the `int N` / 32-bit header of one stream): a container of block-aligned pieces, each a
  * complete standard DCTZ stream compressed with the GLOBAL scaling factor; DCTZ_GPUS=<n> spreads the pieces over
  * n devices.  dctz_compress_large returns the container size (out must hold dctz_large_bound bytes);
@@ -82,6 +85,8 @@ size_t dctz_decompress_large(const void *in, size_t in_size, void *out, size_t o
 void dctz_large_set_piece(size_t elements);
 /* deflate one stream section the way dctz_compress does (chunk-parallel above 2 MiB); returns the size or 0 */
 size_t dctz_host_deflate(const void *src, size_t n, void *dst, size_t cap);
+/* the same while the section arrives in pieces (what dctz_compress does with the GPU's downloads); byte-identical */
+size_t dctz_host_deflate_streamed(const void *src, size_t n, void *dst, size_t cap, size_t piece);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,9 @@
  *     this layer); outlier counts are 64-bit.
  *   - *_dev entry points take device pointers, enqueue on the given stream and do not
  *     synchronise; host-buffer entry points are synchronous.
+ *   - a context owns scratch (tile tickets, outlier slots, scan prefixes) that every call uses:
+ *     ONE operation in flight per context.  Calls on one context must be issued on one stream (or
+ *     be ordered by the caller); use one context per concurrent stream / host thread.
  */
 #ifndef DCTZ_GPU_H
 #define DCTZ_GPU_H
@@ -63,12 +66,12 @@ typedef struct dctz_gpu_info {
   double min_abs;   /* bs.min */
   double sum;       /* sum over x[1..N-1] (util.c:21-25 skips element 0)                            */
   uint64_t n_outliers; /* tot_AC_exact_count, dctz-comp-lib.c:323                                   */
-  uint64_t n_edge;     /* coefficients at ordinal 255 (item == range_max): the reference indexes
-                          conv_tbl[255] out of bounds; we clamp to ordinal 254 and count (double
-                          path only)                                                 */
+  uint64_t n_edge;     /* partial tail block only: coefficients at ordinal 255 although item <= range_max
+                          (the reference indexes conv_tbl[255] out of bounds there); every path stores
+                          such a coefficient as an outlier, the tail kernel also counts it */
   uint64_t n_exact_path; /* 1 if compress_known_stats found the statistics stale (status ESTALE), else 0     */
-  uint64_t n_qt_dropped; /* QT: rescaled outliers that fell back inside the bin range and are
-                            therefore not stored (dctz-comp-lib.c:494-506 quirk)                     */
+  uint64_t n_qt_dropped; /* QT diagnostic, always 0: rescaled outliers that fell back inside the bin range
+                            (dctz-comp-lib.c:494-506 would drop them; unreachable)        */
   int32_t status;      /* 0, or DCTZ_GPU_EDEGENERATE                                                */
   int32_t scale_mode;  /* 0: sf == 1 (no scaling), 1/2: exact reciprocal division iterations, 3: IEEE div */
 } dctz_gpu_info;
@@ -90,10 +93,23 @@ void dctz_gpu_host_free(void *p);
  * elements of the data type, may be NULL unless mode_qt] = the table after / before the >= 1.0
  * clamp (stream trailer / qtable.bin dump).  If scaled_out is non-NULL it receives x[i]/sf, the
  * value the reference leaves in the caller's input buffer (dctz-comp-lib.c:198,213); passing
- * scaled_out == in reproduces the in-place mutation.                                          */
+ * scaled_out == in reproduces the in-place mutation (an IEEE division done by host threads on the
+ * caller's buffer: nothing travels back over PCIe for it).  Pageable buffers are staged through a
+ * page-locked ring by the library; page-locked ones (dctz_gpu_host_alloc) are copied directly.  */
 int dctz_gpu_compress_core(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, double error_bound,
                            int mode_qt, void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact,
                            void *qtable, void *qtable_raw, dctz_gpu_info *info);
+
+/* compress_core_cb: compress_core that reports its outputs piecewise.  on_ready(user, section, offset, bytes) is
+ * called on the calling thread as soon as bytes [offset, offset+bytes) of section 0 = bin_index, 1 = DC,
+ * 2 = AC_exact are valid in the caller's buffer (in ascending order, every section at least once; AC_exact with
+ * bytes == 0 when there are no outliers), so that the host code can start deflating while the rest is still on
+ * its way over PCIe.  `info` is complete before the first call.                                              */
+typedef void (*dctz_gpu_section_cb)(void *user, int section, size_t offset, size_t bytes);
+int dctz_gpu_compress_core_cb(dctz_gpu_ctx *ctx, const void *in, size_t N, int datatype, double error_bound,
+                              int mode_qt, void *scaled_out, uint8_t *bin_index, float *DC, float *AC_exact,
+                              void *qtable, void *qtable_raw, dctz_gpu_info *info, dctz_gpu_section_cb on_ready,
+                              void *user);
 
 /* decompress_core: inverse of the above; `out` receives N reconstructed elements.
  * qtable (64 elements, clamped table from the stream trailer) is only read when mode_qt.      */
@@ -169,10 +185,16 @@ int dctz_gpu_compress_field_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, i
                                 float *d_AC_exact, void *d_qtable, void *d_qtable_raw,
                                 dctz_gpu_info *d_info, void *stream);
 
-/* Dequantise + inverse DCT + de-scale of a slab.  d_AC_exact points at the slab's first outlier. */
+/* Dequantise + inverse DCT + de-scale of a slab.  d_AC_exact points at the slab's first outlier and holds
+ * n_outliers readable floats (the slab's own count, or everything up to the end of the field's array): the
+ * kernels never read past them.  If the bin indices mark more outliers than that (a truncated or damaged
+ * stream) the affected tiles decode without their outliers and *d_corrupt (a 32-bit word on the device, may be
+ * NULL; the caller clears it beforehand) is set to 1.  d_DC needs float alignment only (a slab's slice of a
+ * concatenated DC array is fine); d_bin_index and d_out must be 16-byte aligned.                          */
 int dctz_gpu_decompress_dev(dctz_gpu_ctx *ctx, const uint8_t *d_bin_index, const float *d_DC,
-                            const float *d_AC_exact, const void *d_qtable, size_t N, int datatype,
-                            double error_bound, double sf, int mode_qt, void *d_out, void *stream);
+                            const float *d_AC_exact, uint64_t n_outliers, const void *d_qtable, size_t N,
+                            int datatype, double error_bound, double sf, int mode_qt, void *d_out,
+                            uint32_t *d_corrupt, void *stream);
 
 /* x[i] <- x[i] / sf with IEEE division (the reference's in-place scaling, dctz-comp-lib.c:193-216),
  * and its inverse x[i] <- x[i] * sf (dctz-test.c:186-210, dctz-decomp-lib.c:494-511).          */
@@ -205,9 +227,14 @@ int dctz_gpu_selftest_division(dctz_gpu_ctx *ctx, int datatype, double b, uint64
                                uint64_t *mismatches);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches).                  */
 uint64_t dctz_gpu_launch_count(const dctz_gpu_ctx *ctx);
-/* Reserved for kernel variant switches; no option is defined in this build (the DMMA comparison is
- * dctz_gpu_dct64_dev's `variant`).  Returns the previous value or a negative error.             */
-int dctz_gpu_set_option(dctz_gpu_ctx *ctx, const char *name, int value);
+/* Stage timers of the host-buffer calls (the reference prints sf_t / dct_t / idct_t under -DTIME_DEBUG,
+ * dctz-comp-lib.c:762-773, dctz-decomp-lib.c:513-528).  set_timing(1) makes compress_core / decompress_core run
+ * upload, statistics and transform strictly one after the other with CUDA events between them (the default
+ * overlaps them); returns the previous setting.  last_call_stats: times_ms[0] upload, [1] statistics,
+ * [2] transform kernels (CUDA events, only with timing on), [3] wall clock until the kernels were done,
+ * [4] wall clock of the downloads + host-side scaling; and the PCIe bytes the call moved.          */
+int dctz_gpu_set_timing(dctz_gpu_ctx *ctx, int on);
+int dctz_gpu_last_call_stats(const dctz_gpu_ctx *ctx, double times_ms[8], uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
 #ifdef __cplusplus
 }

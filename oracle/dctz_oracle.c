@@ -290,8 +290,9 @@ unsigned char oracle_conv_tbl(int t) { return conv_ordinal(t); }
  * `qtable_raw` / `qtable` (64 values, element type; may be NULL when !qt) receive the table
  * before (qtable.bin) and after the >=1.0 clamp (the stream trailer).
  * `n_edge` counts coefficients that hit ordinal 255 (item == range_max after rounding): the
- * reference reads conv_tbl[255], one past the table (undefined behaviour); the oracle -- and the
- * GPU path -- clamp to ordinal 254 and report the count.
+ * reference reads conv_tbl[255], one past the table (undefined behaviour).  The oracle -- and every
+ * GPU path -- stores such a coefficient as an OUTLIER (bin id 255, value kept in AC_exact: no error at
+ * all) and reports the count; in QT mode it is rescaled with the range_max branch.
  * ---------------------------------------------------------------------------------------- */
 int oracle_compress_core_d(double *buf, long n, double eb, int qt, unsigned char *bin_index, float *dc,
                            float *ac_exact, unsigned *n_out, double *qtable_raw, double *qtable,
@@ -329,8 +330,8 @@ int oracle_compress_core_d(double *buf, long n, double eb, int qt, unsigned char
         if (fabs(item) >= qtab[j]) qtab[j] = fabs(item); /* :371-372 (QT only; harmless otherwise) */
       } else {
         int t = (unsigned char)((item - range_min) / bin_width); /* :377 */
-        if (t > 254) { t = 254; edge++; }
-        id = conv_ordinal(t); /* :378 */
+        if (t > 254) { id = ORACLE_NBINS; edge++; if (fabs(item) >= qtab[j]) qtab[j] = fabs(item); }
+        else id = conv_ordinal(t); /* :378 */
       }
       bin_index[i * ORACLE_BLK + j] = id;
     }
@@ -346,7 +347,8 @@ int oracle_compress_core_d(double *buf, long n, double eb, int qt, unsigned char
       if (qt) {
         double item = ax[i * ORACLE_BLK + j];
         if (item < range_min) item = (item / qtab[j]) * eb * qt_factor + range_min;      /* :489 */
-        else if (item > range_max) item = (item / qtab[j]) * eb * qt_factor + range_max; /* :491 */
+        else if (item > range_max || item > 0) item = (item / qtab[j]) * eb * qt_factor + range_max; /* :491; `item > 0` only
+                                                         adds the n_edge elements (ordinal 255 although item <= range_max) */
         /* the reference also stores the rescaled value back into a_x (:493); nothing reads it afterwards, and `coef`
          * is meant to equal the -DDCT_FILE_DEBUG dump taken before this loop (:422-433), so it is not mirrored */
         if (item < range_min || item > range_max) ac_exact[cnt++] = (float)item; /* :494-497 */
@@ -401,8 +403,8 @@ int oracle_compress_core_f(float *buf, long n, double eb, int qt, unsigned char 
         if (fabsf(item) >= qtab[j]) qtab[j] = fabsf(item); /* :396-397 */
       } else {
         int t = (unsigned char)((item - range_min) / bin_width); /* :402, float arithmetic */
-        if (t > 254) { t = 254; edge++; }
-        id = conv_ordinal(t);
+        if (t > 254) { id = ORACLE_NBINS; edge++; if (fabsf(item) >= qtab[j]) qtab[j] = fabsf(item); }
+        else id = conv_ordinal(t);
       }
       bin_index[i * ORACLE_BLK + j] = id;
     }
@@ -419,7 +421,7 @@ int oracle_compress_core_f(float *buf, long n, double eb, int qt, unsigned char 
         float item = ax[i * ORACLE_BLK + j];
         /* :515/:517 -- (float/float) is float, then promoted to double by error_bound */
         if (item < range_min) item = (item / qtab[j]) * eb * qt_factor + range_min;
-        else if (item > range_max) item = (item / qtab[j]) * eb * qt_factor + range_max;
+        else if (item > range_max || item > 0) item = (item / qtab[j]) * eb * qt_factor + range_max; /* `item > 0`: n_edge elements only */
         if (item < range_min || item > range_max) ac_exact[cnt++] = item; /* :520-523 (write-back to a_x not mirrored, see above) */
       } else {
         ac_exact[cnt++] = ax[i * ORACLE_BLK + j]; /* :537 */

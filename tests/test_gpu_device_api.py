@@ -63,12 +63,73 @@ def test_slabs_reproduce_the_single_field_result_ec(ctx, dtype, world):
     s = torch.cuda.current_stream().cuda_stream
     tdt = torch.float64 if code == DOUBLE else torch.float32
     rec = []
-    for (a, c), o in zip(parts, outs):
+    for (a, c), o, i in zip(parts, outs, infos):
         out = torch.empty(c, dtype=tdt, device="cuda")
-        ctx.decompress_dev(o["bins"].data_ptr(), o["dc"].data_ptr(), o["ac"].data_ptr(), 0, c, code, eb, whole["sf"], False, out.data_ptr(), s)
+        ctx.decompress_dev(o["bins"].data_ptr(), o["dc"].data_ptr(), o["ac"].data_ptr(), i["n_outliers"], 0, c, code, eb, whole["sf"], False,
+                           out.data_ptr(), s)
         rec.append(out.cpu().numpy())
     want = ctx.decompress_core(whole["bin_index"], whole["dc"], whole["ac"], x.size, dtype, eb, whole["sf"])
     assert np.array_equal(np.concatenate(rec), want)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("world", [2, 3])
+def test_slabs_reproduce_the_single_field_result_qt(ctx, dtype, world):
+    """QT mode over several slabs (dctz-comp-lib.c:355-372, 443-533): per-slab compress leaves the outliers un-rescaled,
+    the per-position maxima are MAX-reduced over the slabs (entry 0 = DC of the field's last block, from the last slab),
+    then every slab rescales with the global table.  One context per emulated rank (a context holds one call's
+    scratch).  The concatenation must equal the single-field result bit for bit, table included."""
+    import dctz_b200
+
+    x = fields.small_cases(dtype)["tail32"]
+    x = np.concatenate([fields.small_cases(dtype)["heavy_outliers"] * 0.02 + 3, x, fields.small_cases(dtype)["heavy_outliers"][:64 * 77 + 5] * 0.3 + 2]).astype(dtype)
+    eb = 1e-3
+    whole = ctx.compress_core(x, eb, qt=True)
+    code = DOUBLE if dtype == np.float64 else FLOAT
+    tdt = torch.float64 if code == DOUBLE else torch.float32
+    s = torch.cuda.current_stream().cuda_stream
+    parts = slabs.partition(x.size, world)
+    ranks = [dctz_b200.Context(0) for _ in range(world)]
+    try:
+        xs = [_dev(x[a:a + c]) for a, c in parts]
+        stats_all = torch.zeros(3 * world, dtype=torch.float64, device="cuda")
+        for r, (a, c) in enumerate(parts):
+            ranks[r].stats_dev(xs[r].data_ptr(), c, code, stats_all[3 * r:].data_ptr(), s)
+        outs = []
+        for r, (a, c) in enumerate(parts):
+            o = dict(bins=torch.empty(c, dtype=torch.uint8, device="cuda"), dc=torch.empty((c + 63) // 64, dtype=torch.float32, device="cuda"),
+                     ac=torch.empty(c, dtype=torch.float32, device="cuda"), qraw=torch.zeros(64, dtype=tdt, device="cuda"),
+                     qt=torch.zeros(64, dtype=tdt, device="cuda"), info=torch.zeros(binding.INFO_BYTES, dtype=torch.uint8, device="cuda"))
+            ranks[r].compress_dev(xs[r].data_ptr(), c, x.size, code, eb, True, stats_all.data_ptr(), world, r == 0, o["bins"].data_ptr(),
+                                  o["dc"].data_ptr(), o["ac"].data_ptr(), o["qraw"].data_ptr(), o["info"].data_ptr(), s)
+            outs.append(o)
+        # the exchange all_reduce_qtable performs over NCCL: MAX of entries 1..63, entry 0 from the last rank
+        g = torch.stack([o["qraw"] for o in outs]).max(dim=0).values
+        g[0] = outs[-1]["qraw"][0]
+        for r, o in enumerate(outs):
+            o["qraw"].copy_(g)
+            ranks[r].qt_finish_dev(code, eb, o["qraw"].data_ptr(), o["qt"].data_ptr(), o["ac"].data_ptr(), o["info"].data_ptr(), s)
+        torch.cuda.synchronize()
+        infos = [_info(o["info"]) for o in outs]
+        assert all(i["sf"] == whole["sf"] and i["status"] == 0 and i["n_qt_dropped"] == 0 for i in infos)
+        bins = np.concatenate([o["bins"].cpu().numpy() for o in outs])
+        dc = np.concatenate([o["dc"].cpu().numpy() for o in outs])
+        ac = np.concatenate([o["ac"][: i["n_outliers"]].cpu().numpy() for o, i in zip(outs, infos)])
+        assert np.array_equal(bins, whole["bin_index"]) and np.array_equal(dc, whole["dc"])
+        assert all(np.array_equal(o["qt"].cpu().numpy(), whole["qtable"]) for o in outs)
+        assert np.array_equal(g.cpu().numpy(), whole["qtable_raw"])
+        assert np.array_equal(ac, whole["ac"])
+        rec = []
+        for (a, c), o, i, rk in zip(parts, outs, infos, ranks):
+            out = torch.empty(c, dtype=tdt, device="cuda")
+            rk.decompress_dev(o["bins"].data_ptr(), o["dc"].data_ptr(), o["ac"].data_ptr(), i["n_outliers"], o["qt"].data_ptr(), c, code, eb,
+                              whole["sf"], True, out.data_ptr(), s)
+            rec.append(out.cpu().numpy())
+        want = ctx.decompress_core(whole["bin_index"], whole["dc"], whole["ac"], x.size, dtype, eb, whole["sf"], qt=True, qtable=whole["qtable"])
+        assert np.array_equal(np.concatenate(rec), want)
+    finally:
+        for rk in ranks:
+            rk.close()
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -136,7 +197,7 @@ def test_full_size_properties_nyx_like(ctx):
     pos = torch.arange(n, device="cuda") % 64
     assert int(((b0 == 255) & (pos != 0)).sum()) == k and bool(torch.all(b0[::64] == 255))
     out = torch.empty(n, dtype=torch.float64, device="cuda")
-    ctx.decompress_dev(b0.data_ptr(), d0.data_ptr(), a0.data_ptr(), 0, n, DOUBLE, eb, i0["sf"], False, out.data_ptr(), s)
+    ctx.decompress_dev(b0.data_ptr(), d0.data_ptr(), a0.data_ptr(), k, 0, n, DOUBLE, eb, i0["sf"], False, out.data_ptr(), s)
     torch.cuda.synchronize()
     err = ((out - x).abs().max() / i0["sf"]).item()
     assert err <= eb * (1 + 63 * np.sqrt(2)) / 8 * 1.01
@@ -212,7 +273,7 @@ def test_more_elements_than_int32(ctx):
     k_tail = int(((bins[start:] == 255) & (pos != 0)).sum())
     assert k_tail > 0
     out = torch.empty(n, dtype=torch.float64, device="cuda")
-    ctx.decompress_dev(bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), 0, n, DOUBLE, eb, i["sf"], False, out.data_ptr(), s)
+    ctx.decompress_dev(bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), i["n_outliers"], 0, n, DOUBLE, eb, i["sf"], False, out.data_ptr(), s)
     torch.cuda.synchronize()
     err = float(((out - x).abs().max() / i["sf"]).item())
     assert err <= eb * (1 + 63 * np.sqrt(2)) / 8 * 1.01
@@ -307,7 +368,7 @@ def test_decompress_mixed_outlier_density_and_unaligned_outlier_array(ctx, dtype
         ac = buf[phase:phase + orc["ac"].size]
         ac.copy_(torch.from_numpy(orc["ac"]))
         out = torch.empty(x.size, dtype=tdt, device="cuda")
-        ctx.decompress_dev(bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), qtab.data_ptr() if qt else 0, x.size, code, eb, sf, qt,
+        ctx.decompress_dev(bins.data_ptr(), dc.data_ptr(), ac.data_ptr(), orc["ac"].size, qtab.data_ptr() if qt else 0, x.size, code, eb, sf, qt,
                            out.data_ptr(), s)
         got = out.cpu().numpy()
         assert np.all(np.isfinite(got)), f"phase {phase}: a guard value leaked into the reconstruction"
@@ -353,7 +414,7 @@ def test_decompress_fuzz_synthetic_streams(ctx, dtype, qt):
             ac.copy_(torch.from_numpy(acv))
         out = torch.empty(n, dtype=tdt, device="cuda")
         d_bins, d_dc, d_qt = _dev(bins), _dev(dcv), (_dev(qtab) if qt else None)  # (kept alive across the call)
-        ctx.decompress_dev(d_bins.data_ptr(), d_dc.data_ptr(), ac.data_ptr() if n_out else 0, d_qt.data_ptr() if qt else 0,
+        ctx.decompress_dev(d_bins.data_ptr(), d_dc.data_ptr(), ac.data_ptr() if n_out else 0, n_out, d_qt.data_ptr() if qt else 0,
                            n, code, eb, sf, qt, out.data_ptr(), s)
         got = out.cpu().numpy()
         assert np.all(np.isfinite(got)), f"case {case}: a guard value leaked (n={n}, outliers={n_out}, phase={phase})"

@@ -66,7 +66,7 @@ def test_dct_tail_lengths(ctx, dtype, dn):
 def test_compress_parity_signal(ctx, dtype, qt, eb):
     x = _signal(64 * 3000 + 37, dtype)
     rep = parity.check_compress(ctx, x, eb, qt)
-    assert rep["tie_fraction"] < (1e-6 if dtype == np.float64 else 5e-2), rep
+    assert rep["tie_fraction"] <= (1e-6 if dtype == np.float64 else 2e-3), rep
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -126,8 +126,69 @@ def test_cesm_config_c1(ctx):
 def test_cesm_config_c2_qt_float(ctx):
     """configs[1]: 1800x3600 float, QT mode, compress + decompress round trip."""
     x = fields.cesm_like(dtype=np.float32)
-    parity.check_compress(ctx, x, 1e-3, True)
+    rep = parity.check_compress(ctx, x, 1e-3, True)
+    assert rep["tie_fraction"] <= 1e-3, rep
     parity.check_decompress(ctx, x, 1e-3, True)
+    print("c2", rep)
+
+
+@pytest.mark.parametrize("qt", [False, True])
+@pytest.mark.parametrize("eb", [1e-3, 1e-4, 1e-5])
+def test_hurricane_config_c3_error_bound_sweep(ctx, eb, qt):
+    """configs[2]: Hurricane-shaped 100x500x500 float field at the three error bounds the reference's harness sweeps
+    (tests/test-dctz.sh:13-56), full size, EC and QT, against the oracle: p ~ 5 / 20 / 75 % outliers -- the last one
+    is the dense-tile regime (more than FAST_MAX outliers per tile in the decoder)."""
+    x = fields.hurricane_like()
+    rep = parity.check_compress(ctx, x, eb, qt)
+    p = rep["n_outliers"] / x.size
+    print(f"c3 eb={eb:g} {'qt' if qt else 'ec'}: p={p:.4f} ties={rep['ties']} ({rep['tie_fraction']:.2e}) set_diff={rep['outlier_set_diff']}")
+    assert rep["tie_fraction"] <= (1e-3 if eb >= 1e-3 else 4e-3), rep  # the bin shrinks with eb, the float DCT error does not
+    assert (0.01 < p < 0.15) if eb == 1e-3 else (p > 0.1 if eb == 1e-4 else p > 0.5), p
+    parity.check_decompress(ctx, x, eb, qt)
+
+
+def test_nyx_config_c4_full_size(ctx):
+    """configs[3]: NYX-shaped 512^3 double field (fields.nyx_like, 1 GiB, ~20 % outliers), EC, eb 1E-3 -- the whole
+    field through compress and decompress against the oracle."""
+    x = fields.nyx_like()
+    rep = parity.check_compress(ctx, x, 1e-3, False)
+    print("c4", {k: rep[k] for k in ("ties", "tie_fraction", "n_outliers", "outlier_set_diff")})
+    assert rep["ties"] <= 64 and rep["n_outliers"] > x.size // 20, rep
+    parity.check_decompress(ctx, x, 1e-3, False)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_qt_outliers_are_never_dropped(ctx, dtype):
+    """dctz-comp-lib.c:494-506: a rescaled QT outlier that falls back inside the bin range is not stored although its bin
+    id stays 255 (the decoder would lose its place).  That needs qtable[j] >= 168 while |c_j| <= 113 for data scaled
+    into (1, 10].  The worst case the arithmetic admits: the smallest error bound (1E-6), a table entry
+    driven to its maximum by a block alternating +-10, and outliers a hair outside the range at the same positions --
+    plus coefficients planted exactly ON the range limits, where the fast quantiser and an exact comparison may
+    disagree.  Every marker must own a stored value (checked by compare_compress) and the round trip must stay in step."""
+    from scipy.fft import idct
+
+    eb = 1e-6
+    nblk = 4096
+    rng = np.random.default_rng(23)
+    c = np.zeros((nblk, 64))
+    c[:, 0] = 40.0                                  # block mean 5: max|x| in (1,10] -> sf = 1
+    lim = 255 * eb
+    j = 1 + np.arange(nblk) % 63
+    c[np.arange(nblk), j] = rng.choice([-1.0, 1.0], nblk) * lim * (1 + rng.choice([0.0, 1e-7, 1e-3, 3e-2], nblk))  # on / just outside the limit
+    x = idct(c, type=2, norm="ortho", axis=-1)
+    x[:64] = 5.0 + 4.99 * np.where(np.arange(64) % 2 == 0, 1.0, -1.0)  # +-: the largest AC coefficients a scaled block can have
+    x = x.reshape(-1).astype(dtype)
+    assert reflib.oracle_stat(x)["sf"] == 1.0
+    g = ctx.compress_core(x, eb, qt=True)
+    assert g["info"]["n_qt_dropped"] == 0 and float(np.max(g["qtable"][1:])) > 30.0
+    pos = np.arange(x.size) % 64
+    assert int(((g["bin_index"] == 255) & (pos != 0)).sum()) == g["ac"].size
+    lo, hi = np.float32(-255 * eb), np.float32(255 * eb)
+    assert np.all((g["ac"] < lo) | (g["ac"] > hi)), "a stored QT outlier lies inside the bin range"
+    if dtype == np.float64:  # (float: a bin of 2E-6 is below the resolution of a float coefficient near 40 -- everything is a tie)
+        parity.check_compress(ctx, x, eb, True)
+    r = ctx.decompress_core(g["bin_index"], g["dc"], g["ac"], x.size, dtype, eb, g["sf"], qt=True, qtable=g["qtable"])
+    assert float(np.max(np.abs(r.astype(np.float64) - x.astype(np.float64)))) < 1e-3  # in step: a lost place would show as O(1) errors
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

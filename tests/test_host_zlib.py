@@ -60,3 +60,20 @@ def test_parallel_ratio_is_close_to_serial_and_threads_env_is_honoured():
             "d = _bin_index_like(5 << 20, seed=7); assert _deflate(d) == zlib.compress(d, -1); print('same')" % ROOT)
     p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DCTZ_ZLIB_THREADS="1"), capture_output=True, text=True)
     assert p.returncode == 0 and "same" in p.stdout, p.stderr
+
+
+@pytest.mark.parametrize("n,piece", [(0, 0), (1000, 300), ((1 << 21) + 1, 1 << 20), (5 * (1 << 20) + 12345, 700001), (16 << 20, 16 << 20),
+                                     (24 << 20, (16 << 20))])
+def test_streamed_deflate_is_byte_identical(n, piece):
+    """dctz_compress deflates the sections while they arrive from the GPU in pieces (zpipe): the stream must be the one
+    deflate_sections produces from the complete array, whatever the piece size."""
+    lib = _lib()
+    lib.dctz_host_deflate_streamed.restype = C.c_size_t
+    lib.dctz_host_deflate_streamed.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
+    data = _bin_index_like(n, seed=11)
+    cap = n + n // 8 + 4096
+    out = C.create_string_buffer(cap)
+    src = C.create_string_buffer(data, len(data)) if data else C.create_string_buffer(1)
+    m = lib.dctz_host_deflate_streamed(src, n, out, cap, piece)
+    assert m > 0 and out.raw[:m] == _deflate(data)
+    assert zlib.decompress(out.raw[:m]) == data

@@ -65,6 +65,13 @@ def _worker(rank, world, port, n, qfile):
         q[0] = 100.0 + rank
         q = slabs.all_reduce_qtable(q, rank, world)
         assert q[0].item() == 100.0 + world - 1 and torch.all(q[1:] == float(world))
+        # a field of two blocks: ranks beyond the data hold nothing, entry 0 must come from the last rank WITH data
+        src = slabs.last_rank_with_data(100, world)
+        assert src == 1 and slabs.partition(100, world)[src][1] == 36
+        q = torch.full((64,), float(rank + 1), dtype=torch.float64)
+        q[0] = 100.0 + rank
+        q = slabs.all_reduce_qtable(q, rank, world, src_last=src)
+        assert q[0].item() == 101.0
         # outlier segments are concatenated in rank order: exchange counts only to place them (host side)
         counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(counts, torch.tensor([count // 7], dtype=torch.int64))
