@@ -283,6 +283,17 @@ struct TileSeq {
   }
 };
 
+// A shared-memory buffer that TMA refills may only be re-armed once every lane's READS of it have COMPLETED -- not merely
+// been issued: a generic-proxy load still queued in the memory pipeline is not ordered against an async-proxy write
+// (__syncwarp orders issue, not completion).  With the load/store unit backed up by thousands of scattered outlier
+// stores and the next tile hot in L2 the refill did overtake such loads (float fields at small error bounds: blocks
+// transformed from a mix of two tiles).  `probe` is an OR over (a word of) every value loaded from the buffer: the
+// vote cannot issue before all of them have arrived in every lane's registers, and the caller makes the TMA issue
+// depend on its result (it is true unless all 32 probes hit one magic value at once).
+__device__ __forceinline__ bool reads_have_landed(unsigned probe) {
+  return __ballot_sync(0xFFFFFFFFu, probe == 0x7F4A7C15u) != 0xFFFFFFFFu;
+}
+
 // inclusive warp scan of one small count per lane
 __device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, int lane) {
 #pragma unroll

@@ -869,7 +869,7 @@ static int upload(dctz_gpu_ctx *ctx, void *d_dst, const void *h_src, size_t byte
     const void *src = (const char *)h_src + off;
     const int s = (int)(c % NSTAGE);
     if (!pinned) {
-      if (c >= (size_t)NSTAGE) CU(cudaEventSynchronize(ctx->stage_ev[s]));  // the slot's previous content is on the device
+      CU(cudaEventSynchronize(ctx->stage_ev[s]));  // the slot's previous content (this upload's or an earlier one's) is on the device
       pool_memcpy(ctx->pool, ctx->stage[s], src, len);
       src = ctx->stage[s];
     }

@@ -500,38 +500,24 @@ template <typename T, bool QT> struct CompressCfg {
 // its last CTA checks that it lies in the decade the scaling factor was derived from; if not, info->status =
 // DCTZ_GPU_ESTALE and the outputs are to be discarded.  `verify_lower` = 0 leaves the lower limit to the caller
 // (a slab of a larger field need not contain the global maximum).
-template <typename T, bool QT, bool VERIFY>
-__global__ void __launch_bounds__(CompressCfg<T, QT>::THREADS, CompressCfg<T, QT>::CTAS_PER_SM)
-k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_full, const DevParams *__restrict__ params,
-           QuantConsts<T> qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
-           unsigned *__restrict__ counts,                     // outliers per warp tile
-           float *__restrict__ ac_slots,                      // EC: outlier scratch, TILE_SLOT entries per tile, packed
-           T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
-           typename BitsOf<T>::U *qmax_bits,                  // QT: 64 per-position maxima (bit patterns): filled by k_qt_max, unused here
-           T *qtable0,                                        // QT: entry 0 of the same table: the last full block's DC
-           TileControl *ctl, Info *info, FusedScan fused, int verify_lower, unsigned batch) {
+// The tile loop of the compress kernels: one warp, tiles handed out by `seq` (TileSeq: dynamic tickets; RangeSeq: the
+// CTA's own contiguous range in the single-launch kernel), `phase` = the parity of the warp's mbarrier.
+template <typename T, bool QT, bool VERIFY, class Seq>
+__device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsigned long long nblk_full, const DevParams *params,
+                                               const QuantConsts<T> &qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
+                                               unsigned *__restrict__ counts, float *__restrict__ ac_slots, T *__restrict__ raw_slots,
+                                               uint8_t *__restrict__ j_slots, T *qtable0, unsigned char *wsm, unsigned mb, Seq &seq,
+                                               int lane, typename BitsOf<T>::U &seen_max, unsigned &phase) {
   typedef typename ArithOf<T>::type A;
   typedef CompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
   typedef typename BitsOf<T>::U U;
   constexpr unsigned FULL = 0xFFFFFFFFu;
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char *wsm = smem + warp * Cfg::WARP_BYTES;
   const unsigned tile_s = smem_u32(wsm);
   unsigned char *binbuf = wsm + Cfg::OFF_BINS;
-  const unsigned mb = smem_u32(&s_mbar[warp]);
   const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
-
-  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
-  __syncthreads();  // the only CTA-wide barrier before the epilogue
-
   Quantizer<T> qz;
   qz.init(params, qc);
-  U seen_max = 0;  // VERIFY: largest |x| bit pattern of this thread's blocks
 
   auto rows_of = [&](unsigned t) -> unsigned {
     const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
@@ -541,20 +527,18 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     if (lane == 0) {
       mbar_expect_tx(mb, L::BYTES);  // rows beyond the field are zero-filled and still counted
 #pragma unroll
-      for (int q = 0; q < L::SLABS; q++) tma_load_2d(tile_s + q * L::SLAB_BYTES, &tmap_in, q * 128, (int)(t * WTILE), mb);
+      for (int q = 0; q < L::SLABS; q++) tma_load_2d(tile_s + q * L::SLAB_BYTES, tmap_in, q * 128, (int)(t * WTILE), mb);
     }
   };
-  TileSeq seq;
-  seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
   unsigned cur = seq.advance(lane);
   if (cur < ntiles) issue_tile(cur);
   unsigned nxt = seq.advance(lane);
-  unsigned phase = 0;
 
   while (cur < ntiles) {
     mbar_wait(mb, phase);
     phase ^= 1u;
     T x[BLK];
+    unsigned probe = 0;
 #pragma unroll
     for (int q = 0; q < L::SLABS; q++) {
 #pragma unroll
@@ -563,10 +547,12 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
         const T *e = reinterpret_cast<const T *>(&v);
 #pragma unroll
         for (int k = 0; k < L::PER_CHUNK; k++) x[(q * 8 + c) * L::PER_CHUNK + k] = e[k];
+        probe |= v.x ^ v.w;
       }
     }
-    __syncwarp();                        // every lane holds its row in registers
-    if (nxt < ntiles) issue_tile(nxt);   // refill the tile buffer; overlaps everything below
+    // every lane HOLDS its row in registers (reads_have_landed: completed, not just issued) before the buffer is refilled
+    __syncwarp();
+    if (reads_have_landed(probe) && nxt < ntiles) issue_tile(nxt);  // overlaps everything below
 
     const unsigned rows = rows_of(cur);
     const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
@@ -684,6 +670,41 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     cur = nxt;
     nxt = seq.advance(lane);
   }
+
+}
+
+template <typename T, bool QT, bool VERIFY>
+__global__ void __launch_bounds__(CompressCfg<T, QT>::THREADS, CompressCfg<T, QT>::CTAS_PER_SM)
+k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_full, const DevParams *__restrict__ params,
+           QuantConsts<T> qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
+           unsigned *__restrict__ counts,                     // outliers per warp tile
+           float *__restrict__ ac_slots,                      // EC: outlier scratch, TILE_SLOT entries per tile, packed
+           T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
+           typename BitsOf<T>::U *qmax_bits,                  // QT: 64 per-position maxima (bit patterns): filled by k_qt_max, unused here
+           T *qtable0,                                        // QT: entry 0 of the same table: the last full block's DC
+           TileControl *ctl, Info *info, FusedScan fused, int verify_lower, unsigned batch) {
+  typedef typename ArithOf<T>::type A;
+  typedef CompressCfg<T, QT> Cfg;
+  typedef WarpTile<T> L;
+  typedef typename BitsOf<T>::U U;
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char *wsm = smem + warp * Cfg::WARP_BYTES;
+  const unsigned mb = smem_u32(&s_mbar[warp]);
+
+  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
+  __syncthreads();  // the only CTA-wide barrier before the epilogue
+
+  U seen_max = 0;  // VERIFY: largest |x| bit pattern of this thread's blocks
+  unsigned phase = 0;
+  TileSeq seq;
+  seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
+  compress_tiles<T, QT, VERIFY>(&tmap_in, nblk_full, params, qc, bins, dc_out, counts, ac_slots, raw_slots, j_slots, qtable0, wsm, mb, seq, lane,
+                                seen_max, phase);
 
   // ---- epilogue ----
   bulk_wait_all();
@@ -1487,10 +1508,20 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
         }
       }
     }
-    __syncwarp();  // bin ids, DC and the stage are consumed by every lane
+    // bin ids, DC and the stage are consumed by every lane: their loads have COMPLETED (reads_have_landed), the next
+    // tile's copies may overwrite the buffers
+    unsigned probe = w[0] ^ w[15];
+    if constexpr (sizeof(T) == 8) {
+#pragma unroll
+      for (int j = 0; j < BLK; j++) probe |= (unsigned)__double2hiint((double)x[j]) ^ (unsigned)__double2loint((double)x[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BLK; j++) probe |= (unsigned)__float_as_int((float)x[j]);
+    }
     Ragged rag;
     rag.v = 0.f; rag.idx = -1;
-    if (nxt < ntiles) rag = issue_tile(nxt, ext_nxt);  // overlaps the inverse transform and the stores
+    __syncwarp();
+    if (reads_have_landed(probe) && nxt < ntiles) rag = issue_tile(nxt, ext_nxt);  // overlaps the inverse transform and the stores
 
     // ---- orthonormal DCT-III (dct.c:115-205) ----
     dct64_inverse<A>(x);
