@@ -26,7 +26,7 @@
 #include <vector>
 
 #include "../../include/dctz_gpu.h"
-#include "kernels.cuh"
+#include "fused.cuh"
 
 using namespace dctz;
 
@@ -177,6 +177,15 @@ struct dctz_gpu_ctx {
   DevBuf in, bins, dc, ac, qt, qtraw, out;
   double *d_dfrag[2] = {nullptr, nullptr};  // DMMA A-fragments of the DCT matrix (forward, inverse)
   int occ[2][2][2] = {};  // resident CTAs/SM per [kernel][datatype][qt]
+  // single-launch kernels for small fields (fused.cuh)
+  int occ_fused[2][2][2] = {};
+  size_t fused_max_bytes = (size_t)256 << 20;  // fields up to this size take the single-launch path (DCTZ_FUSED_MAX_MB, 0 = never)
+  int coop = 0;                                // cooperative launches supported
+  unsigned long long *d_barrier = nullptr;     // [0] compress, [1] decompress: grid-barrier arrival counters (monotonic)
+  unsigned long long barrier_base[2] = {0, 0}; // what the counters will have reached when the next launch starts
+  unsigned long long *d_cta_totals = nullptr;  // outliers per CTA (two halves: compress, decompress)
+  unsigned long long *d_qmax_scratch = nullptr;  // QT: 64 per-position maxima (bit patterns)
+  DevBuf tile_off;                             // decompress: offset of every tile's run inside its CTA's range
 };
 
 // ------------------------------------------------------------------------------------------
@@ -289,7 +298,7 @@ extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void *small[] = {ctx->d_partials, ctx->d_done, ctx->d_stats3, ctx->d_params, ctx->d_info, ctx->d_ctl,
+  void *small[] = {ctx->d_barrier, ctx->d_cta_totals, ctx->d_qmax_scratch, ctx->tile_off.p, ctx->d_partials, ctx->d_done, ctx->d_stats3, ctx->d_params, ctx->d_info, ctx->d_ctl,
                    ctx->d_nconsumed, ctx->d_mismatch, ctx->d_qpartials, ctx->d_stats_host3, (void *)ctx->tb.thr_d, (void *)ctx->tb.sf_d,
                    (void *)ctx->tb.thr_f, (void *)ctx->tb.sf_f};
   for (void *p : small) if (p) cudaFree(p);
@@ -375,6 +384,20 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   ctx->occ[1][1][1] = kernel_occupancy(k_decompress<double, true>, DecompressCfg<double, true>::THREADS, DecompressCfg<double, true>::SMEM);
   ctx->occ[1][0][0] = kernel_occupancy(k_decompress<float, false>, DecompressCfg<float, false>::THREADS, DecompressCfg<float, false>::SMEM);
   ctx->occ[1][0][1] = kernel_occupancy(k_decompress<float, true>, DecompressCfg<float, true>::THREADS, DecompressCfg<float, true>::SMEM);
+  ctx->occ_fused[0][1][0] = kernel_occupancy(k_compress_fused<double, false>, CompressCfg<double, false>::THREADS, CompressCfg<double, false>::SMEM);
+  ctx->occ_fused[0][1][1] = kernel_occupancy(k_compress_fused<double, true>, CompressCfg<double, true>::THREADS, CompressCfg<double, true>::SMEM);
+  ctx->occ_fused[0][0][0] = kernel_occupancy(k_compress_fused<float, false>, CompressCfg<float, false>::THREADS, CompressCfg<float, false>::SMEM);
+  ctx->occ_fused[0][0][1] = kernel_occupancy(k_compress_fused<float, true>, CompressCfg<float, true>::THREADS, CompressCfg<float, true>::SMEM);
+  ctx->occ_fused[1][1][0] = kernel_occupancy(k_decompress_fused<double, false>, DecompressCfg<double, false>::THREADS, DecompressCfg<double, false>::SMEM);
+  ctx->occ_fused[1][1][1] = kernel_occupancy(k_decompress_fused<double, true>, DecompressCfg<double, true>::THREADS, DecompressCfg<double, true>::SMEM);
+  ctx->occ_fused[1][0][0] = kernel_occupancy(k_decompress_fused<float, false>, DecompressCfg<float, false>::THREADS, DecompressCfg<float, false>::SMEM);
+  ctx->occ_fused[1][0][1] = kernel_occupancy(k_decompress_fused<float, true>, DecompressCfg<float, true>::THREADS, DecompressCfg<float, true>::SMEM);
+  CU(cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, device));
+  CU(cudaMalloc(&ctx->d_barrier, 2 * sizeof(unsigned long long)));
+  CU(cudaMemset(ctx->d_barrier, 0, 2 * sizeof(unsigned long long)));
+  CU(cudaMalloc(&ctx->d_cta_totals, 2 * (size_t)ctx->sm_count * 4 * sizeof(unsigned long long)));
+  CU(cudaMalloc(&ctx->d_qmax_scratch, BLK * sizeof(unsigned long long)));
+  if (const char *e = getenv("DCTZ_FUSED_MAX_MB")) ctx->fused_max_bytes = (size_t)atol(e) << 20;
   for (int a = 0; a < 2; a++)
     for (int b = 0; b < 2; b++)
       for (int c = 0; c < 2; c++)
@@ -700,12 +723,83 @@ extern "C" int dctz_gpu_qt_finish_dev(dctz_gpu_ctx *ctx, int datatype, double eb
   return launch_qt_finish<float>(ctx, eb, (const float *)d_qtable_raw, (float *)d_qtable, d_ac, (Info *)d_info, st);
 }
 
+// Single-launch path (fused.cuh): whole fields of full blocks up to fused_max_bytes, all CTAs co-resident.
+static int fused_grid(const dctz_gpu_ctx *ctx, int kernel, size_t N, size_t es, int mode_qt) {
+  static const bool dbg = getenv("DCTZ_DEBUG") != nullptr;
+  if (dbg)
+    fprintf(stderr, "fused_grid: kernel %d N %zu es %zu qt %d coop %d max_bytes %zu occ %d\n", kernel, N, es, mode_qt, ctx->coop, ctx->fused_max_bytes,
+            ctx->occ_fused[kernel][es == 8][mode_qt ? 1 : 0]);
+  if (!ctx->coop || N % BLK || N == 0 || N * es > ctx->fused_max_bytes) return 0;
+  const size_t ntiles = (N / BLK + WTILE - 1) / WTILE;
+  const size_t resident = (size_t)ctx->sm_count * ctx->occ_fused[kernel][es == 8][mode_qt ? 1 : 0];
+  if (resident == 0) return 0;
+  const size_t grid = ntiles < resident ? ntiles : resident;
+  if ((ntiles + grid - 1) / grid > FUSED_MAX_TILES_PER_CTA) return 0;
+  return (int)grid;
+}
+
+template <typename T, bool QT>
+static int launch_compress_fused(dctz_gpu_ctx *ctx, int grid, const T *d_in, size_t N, double eb, uint8_t *d_bins, float *d_dc, float *d_ac,
+                                 void *d_qtable, void *d_qtable_raw, Info *d_info, cudaStream_t st) {
+  typedef CompressCfg<T, QT> Cfg;
+  typedef typename BitsOf<T>::U U;
+  unsigned long long nblk_full = N / BLK;
+  const size_t ntiles = (nblk_full + WTILE - 1) / WTILE;
+  QuantConsts<T> qc = make_quant<T>(eb);
+  QtConsts<T> qk = make_qt<T>(eb);
+  ScanBufs sb;
+  TRY(scan_bufs(ctx, ntiles, &sb));
+  float *ac_slots = nullptr;
+  T *raw = nullptr;
+  uint8_t *jpos = nullptr;
+  if (QT) {
+    TRY(grow(ctx, ctx->qt_raw, ntiles * TILE_SLOT * sizeof(T)));
+    TRY(grow(ctx, ctx->qt_j, ntiles * TILE_SLOT));
+    raw = (T *)ctx->qt_raw.p;
+    jpos = (uint8_t *)ctx->qt_j.p;
+    ctx->qt_entries = 0;  // nothing is left for dctz_gpu_qt_finish_dev: the kernel rescales itself
+  } else {
+    TRY(grow(ctx, ctx->slots, ntiles * TILE_SLOT * sizeof(float)));
+    ac_slots = (float *)ctx->slots.p;
+  }
+  CUtensorMap tmap;
+  TRY(make_tile_map(ctx, &tmap, d_in, BLK * sizeof(T), nblk_full));
+  SfTables tb = ctx->tb;
+  tb.qmax_words = 0;
+  T *q_out = (T *)d_qtable, *q_raw = (T *)d_qtable_raw;
+  U *qmax = (U *)ctx->d_qmax_scratch;
+  StatPartial *partials = ctx->d_partials;
+  unsigned long long *totals = ctx->d_cta_totals, *bar = ctx->d_barrier;
+  unsigned long long base = ctx->barrier_base[0];
+  DevParams *params = ctx->d_params;
+  unsigned *counts = sb.counts;
+  void *args[] = {&tmap, &d_in, &nblk_full, &qc, &qk, &d_bins, &d_dc, &counts, &ac_slots, &raw, &jpos, &d_ac, &q_out, &q_raw, &qmax,
+                  &partials, &totals, &tb, &params, &d_info, &bar, &base};
+  CU(cudaLaunchCooperativeKernel((const void *)k_compress_fused<T, QT>, dim3(grid), dim3(Cfg::THREADS), args, Cfg::SMEM, st));
+  ctx->barrier_base[0] += 2ull * (unsigned long long)grid;
+  ctx->launches++;
+  return DCTZ_GPU_OK;
+}
+
+static int compress_fused_dispatch(dctz_gpu_ctx *ctx, int grid, const void *d_in, size_t N, int datatype, double eb, int mode_qt, uint8_t *d_bins,
+                                   float *d_dc, float *d_ac, void *d_qtable, void *d_qtable_raw, Info *d_info, cudaStream_t st) {
+  if (datatype == DCTZ_GPU_DOUBLE) {
+    if (mode_qt) return launch_compress_fused<double, true>(ctx, grid, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable, d_qtable_raw, d_info, st);
+    return launch_compress_fused<double, false>(ctx, grid, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable, d_qtable_raw, d_info, st);
+  }
+  if (mode_qt) return launch_compress_fused<float, true>(ctx, grid, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable, d_qtable_raw, d_info, st);
+  return launch_compress_fused<float, false>(ctx, grid, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable, d_qtable_raw, d_info, st);
+}
+
 extern "C" int dctz_gpu_compress_field_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt,
                                            uint8_t *d_bins, float *d_dc, float *d_ac, void *d_qtable, void *d_qtable_raw,
                                            dctz_gpu_info *d_info, void *stream) {
   TRY(check_compress_args(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, d_info));
+  if (mode_qt && !d_qtable) return fail(ctx, DCTZ_GPU_EINVAL, "compress_field: QT mode needs d_qtable");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (const int grid = fused_grid(ctx, 0, N, datatype == DCTZ_GPU_DOUBLE ? 8 : 4, mode_qt))  // small field: one launch for everything
+    return compress_fused_dispatch(ctx, grid, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable, d_qtable_raw, (Info *)d_info, st);
   void *qz = mode_qt ? d_qtable_raw : nullptr;
   if (datatype == DCTZ_GPU_DOUBLE) TRY(launch_stats<double>(ctx, (const double *)d_in, N, ctx->d_stats3, 1, N, qz, (Info *)d_info, st));
   else TRY(launch_stats<float>(ctx, (const float *)d_in, N, ctx->d_stats3, 1, N, qz, (Info *)d_info, st));
@@ -727,6 +821,26 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
   // gen_bins: bin_width = error_bound*2*BRSF (binning.c:16); gen_bins_f receives the bound as float (binning.c:32-36)
   const T bw = (sizeof(T) == 8) ? (T)(eb * 2 * 1.0) : (T)(float)((float)eb * 2 * 1.0);
   const T sfT = (T)sf;
+  if (const int fgrid = fused_grid(ctx, 1, N, sizeof(T), QT)) {  // small field of full blocks: count + dequantise + IDCT in ONE launch
+    unsigned long long nb = nblk_full;
+    const size_t ntiles = (nblk_full + WTILE - 1) / WTILE;
+    ScanBufs sb;
+    TRY(scan_bufs(ctx, ntiles, &sb));
+    TRY(grow(ctx, ctx->tile_off, ntiles * sizeof(unsigned)));
+    CUtensorMap tmap;
+    TRY(make_tile_map(ctx, &tmap, d_out, BLK * sizeof(T), nblk_full));
+    T bw_ = bw, sf_ = sfT;
+    QtConsts<T> qk_ = qk;
+    unsigned *counts = sb.counts, *toff = (unsigned *)ctx->tile_off.p;
+    unsigned long long *totals = ctx->d_cta_totals + (size_t)ctx->sm_count * 4, *bar = ctx->d_barrier + 1;
+    unsigned long long base = ctx->barrier_base[1], lim = ac_limit;
+    int dca = aligned16(d_dc) ? 1 : 0;
+    void *args[] = {&d_bins, &d_dc, &d_ac, &d_qtable, &nb, &bw_, &sf_, &qk_, &tmap, &counts, &toff, &totals, &lim, &d_corrupt, &dca, &bar, &base};
+    CU(cudaLaunchCooperativeKernel((const void *)k_decompress_fused<T, QT>, dim3(fgrid), dim3(Cfg::THREADS), args, Cfg::SMEM, st));
+    ctx->barrier_base[1] += (unsigned long long)fgrid;
+    ctx->launches++;
+    return DCTZ_GPU_OK;
+  }
   if (nblk_full) {
     const size_t ntiles = (nblk_full + WTILE - 1) / WTILE;
     if (ntiles > 0xFFFFF000ull) return fail(ctx, DCTZ_GPU_EINVAL, "slab too large: %zu tiles", ntiles);
@@ -980,7 +1094,7 @@ static int compress_core_impl(dctz_gpu_ctx *ctx, const void *in, size_t N, size_
     TRY(dctz_gpu_compress_dev(ctx, ctx->in.p, N, N, datatype, eb, mode_qt, ctx->d_stats3, 1, 1, (uint8_t *)ctx->bins.p, (float *)ctx->dc.p,
                               (float *)ctx->ac.p, ctx->qtraw.p, d_info, st));
     if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, ctx->qtraw.p, ctx->qt.p, (float *)ctx->ac.p, d_info, st));
-  } else if (nchunks == 1) {  // one upload, then the single-field path (small fields: one fused launch)
+  } else if (nchunks == 1 || fused_grid(ctx, 0, N, es, mode_qt)) {  // one upload, then the single-field path (small fields: ONE launch)
     TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr));
     TRY(dctz_gpu_compress_field_dev(ctx, ctx->in.p, N, datatype, eb, mode_qt, (uint8_t *)ctx->bins.p, (float *)ctx->dc.p,
                                     (float *)ctx->ac.p, ctx->qt.p, ctx->qtraw.p, d_info, st));

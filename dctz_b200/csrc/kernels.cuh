@@ -1228,77 +1228,59 @@ template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
 template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
 template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
 
-template <typename T, bool QT>
-__global__ void __launch_bounds__(DecompressCfg<T, QT>::THREADS, DecompressCfg<T, QT>::CTAS_PER_SM)
-k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, const float *__restrict__ ac_in,
-             const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
-             const __grid_constant__ CUtensorMap tmap_out, const unsigned *__restrict__ counts,
-             const unsigned long long *__restrict__ group_prefix, const unsigned long long *__restrict__ chunk_prefix,
-             const unsigned long long *__restrict__ n_outliers_total, unsigned long long n_limit, TileControl *ctl,
-             unsigned *corrupt_flag, int dc_aligned16, unsigned batch) {
-  typedef typename ArithOf<T>::type A;
-  typedef DecompressCfg<T, QT> Cfg;
-  typedef WarpTile<T> L;
-  constexpr unsigned FULL = 0xFFFFFFFFu;
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
-  __shared__ T s_qt[QT ? BLK : 1];
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(16) T center[256];  // static: its address is an immediate of the lookups
-  unsigned char *wsm = smem + warp * Cfg::WARP_BYTES;
-  // EC: a tile's outliers are turned into coefficients (converted to T, times sf) ONCE, cooperatively and
-  // conflict-free, before the lanes pick them up -- the per-coefficient work of a lane is then a select between two
-  // shared-memory addresses (pick_coefficient).  double: the converted values need 8 bytes each, so the prefetched
-  // floats are put in the upper half of the stage and expanded in place from the bottom.  Tiles with more than
-  // FAST_MAX outliers (double) and QT tiles (whose outliers are rescaled with a per-position table entry,
-  // dctz-decomp-lib.c:404-409) take the per-lane conversion path.
-  constexpr bool WIDE = (sizeof(T) == 8);
-  constexpr unsigned FAST_MAX = (unsigned)Cfg::FAST_MAX;
-  float *stage = reinterpret_cast<float *>(wsm + Cfg::OFF_STAGE);
-  unsigned char *binbuf = wsm + Cfg::OFF_BINS;
-  float *dcbuf = reinterpret_cast<float *>(wsm + Cfg::OFF_DC);
-  const unsigned mb = smem_u32(&s_mbar[warp]);
-  const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
-
-  // bin centres: gen_bins / gen_bins_f (binning.c:19-22, 39-42): centre = (int multiple) * bin_width.  The de-scale
-  // (x * sf, dctz-decomp-lib.c:494-511) is folded into the coefficients -- the inverse transform is linear, the
-  // result moves by ~1 ulp -- so the table holds centre * sf.
-  for (int i = threadIdx.x; i < 256; i += Cfg::THREADS) center[i] = mul_rn<T>(mul_rn<T>((T)center_multiple((unsigned)i), bin_width), sf);
-  if (QT && threadIdx.x < BLK) s_qt[threadIdx.x] = qtable[threadIdx.x];
-  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
-  __syncthreads();  // the only CTA-wide barrier before the epilogue
-
-  auto rows_of = [&](unsigned t) -> unsigned {
-    const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
-    return left < (unsigned long long)WTILE ? (unsigned)left : (unsigned)WTILE;
-  };
-  // Outlier extent of a tile (warp-uniform): offset of its first outlier = scanned group prefix + the counts of
-  // the earlier tiles of its group; its size is the tile's count from k_count_bins.  The loads (extent_load) and the
-  // warp reduction that consumes them (extent_finish) are a whole iteration apart, so their latency is never waited for.
-  struct Extent { unsigned long long base; unsigned total; bool bad; };  // bad: the run would leave the caller's AC_exact array
-  struct ExtentRaw { unsigned long long gp, cp; unsigned c; unsigned k; };  // loaded values, untouched until extent_finish
-  auto extent_load = [&](unsigned t) -> ExtentRaw {
+// Outlier extent of a tile (warp-uniform): where its run starts in AC_exact and how long it is.  The loads (load) and
+// the warp reduction that consumes them (finish) are a whole iteration apart, so their latency is never waited for.
+struct Extent { unsigned long long base; unsigned total; bool bad; };  // bad: the run would leave the caller's AC_exact array
+struct ExtentRaw { unsigned long long gp, cp; unsigned c; unsigned k; };  // loaded values, untouched until finish()
+// Extents from the scan of the pre-pass (k_count_bins + k_scan_groups): offset of the first outlier = scanned group prefix
+// + the counts of the earlier tiles of its group; the size is the tile's count.
+struct ScannedExtents {
+  const unsigned *__restrict__ counts;
+  const unsigned long long *__restrict__ group_prefix, *__restrict__ chunk_prefix;
+  unsigned long long n_limit;
+  unsigned *corrupt_flag;
+  __device__ __forceinline__ ExtentRaw load(unsigned t, int lane) const {
     ExtentRaw r;
     r.k = t & 31u;
     r.c = ((unsigned)lane <= r.k) ? __ldg(counts + (t & ~31u) + lane) : 0u;  // lanes < k: earlier tiles of the group; lane k: the tile
     r.gp = __ldg(group_prefix + (t >> 5));
-    r.cp = __ldg(chunk_prefix + (t >> 15));  // prefix_of_group(), its addition left to extent_finish
+    r.cp = __ldg(chunk_prefix + (t >> 15));  // prefix_of_group(), its addition left to finish()
     return r;
-  };
-  auto extent_finish = [&](const ExtentRaw &r) -> Extent {
+  }
+  __device__ __forceinline__ Extent finish(const ExtentRaw &r, int lane) const {
     Extent e;
-    e.total = __shfl_sync(FULL, r.c, (int)r.k);
+    e.total = __shfl_sync(0xFFFFFFFFu, r.c, (int)r.k);
     unsigned before = ((unsigned)lane < r.k) ? r.c : 0u;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(FULL, before, o);
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
     e.base = r.gp + r.cp + before;
     // A stream whose bin indices mark more outliers than AC_exact holds (n_limit: its length as the caller states it)
     // is corrupt: such a tile decodes without its outliers and the launch is flagged; nothing is read out of bounds.
     e.bad = e.base + e.total > n_limit;
     if (e.bad) { e.total = 0u; *corrupt_flag = 1u; }
     return e;
+  }
+};
+
+// The tile loop of the decompress kernels: one warp, tiles handed out by `seq`, outlier extents by `ext`.
+template <typename T, bool QT, class Seq, class Ext>
+__device__ __forceinline__ void decompress_tiles(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, const float *__restrict__ ac_in,
+                                                 unsigned long long nblk_full, T sf, const QtConsts<T> &qk, const CUtensorMap *tmap_out,
+                                                 unsigned long long n_ac /* end of the readable part of AC_exact */, int dc_aligned16,
+                                                 unsigned char *wsm, unsigned mb, const T *center, const T *s_qt, Seq &seq, const Ext &ext,
+                                                 int lane, unsigned &phase) {
+  typedef typename ArithOf<T>::type A;
+  typedef DecompressCfg<T, QT> Cfg;
+  typedef WarpTile<T> L;
+  constexpr bool WIDE = (sizeof(T) == 8);
+  constexpr unsigned FAST_MAX = (unsigned)Cfg::FAST_MAX;
+  float *stage = reinterpret_cast<float *>(wsm + Cfg::OFF_STAGE);
+  unsigned char *binbuf = wsm + Cfg::OFF_BINS;
+  float *dcbuf = reinterpret_cast<float *>(wsm + Cfg::OFF_DC);
+  const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
+  auto rows_of = [&](unsigned t) -> unsigned {
+    const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
+    return left < (unsigned long long)WTILE ? (unsigned)left : (unsigned)WTILE;
   };
   // Stage layout: the stage mirrors the 16-byte granules of AC_exact that hold the tile's run: outlier i lives at
   // stage[fofs + lead + i], lead = (elements between the previous 16-byte boundary and the run's first element), so ONE
@@ -1306,8 +1288,6 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   // and ignored).  Only where the superset would leave the array -- before AC_exact[0] when the array itself is not
   // 16-byte aligned, or past the last outlier of the field -- the copy is clipped to whole granules inside the array
   // and the at most 3 + 3 ragged elements are fetched by plain loads.
-  const unsigned long long n_scan = __ldg(n_outliers_total);
-  const unsigned long long n_ac = n_scan < n_limit ? n_scan : n_limit;  // end of the readable part of AC_exact
   struct Plan { unsigned lead, kend, fofs; bool fits, prefetch; };  // warp-uniform, a function of the extent alone
   auto plan_of = [&](const Extent &e) -> Plan {
     Plan p;
@@ -1354,22 +1334,19 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   // Tiles are known three ahead (there is no ordering between tiles): `nxt` and its outlier extent are known when an
   // iteration starts, so all of its loads are issued as soon as the current tile's inputs are consumed; the counts
   // behind the extent of the tile after it (`nn`) are loaded at the top of the iteration and reduced at its end.
-  TileSeq seq;
-  seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
   unsigned cur = seq.advance(lane);
   unsigned nxt = seq.advance(lane);
   unsigned nn = seq.advance(lane);
   Extent ext_cur, ext_nxt;
   ext_cur.base = 0; ext_cur.total = 0; ext_cur.bad = false;
   ext_nxt = ext_cur;
-  if (cur < ntiles) { ext_cur = extent_finish(extent_load(cur)); park_ragged(issue_tile(cur, ext_cur)); }
-  if (nxt < ntiles) ext_nxt = extent_finish(extent_load(nxt));
-  unsigned phase = 0;
+  if (cur < ntiles) { ext_cur = ext.finish(ext.load(cur, lane), lane); park_ragged(issue_tile(cur, ext_cur)); }
+  if (nxt < ntiles) ext_nxt = ext.finish(ext.load(nxt, lane), lane);
 
   while (cur < ntiles) {
     ExtentRaw raw_nn;
     raw_nn.gp = 0; raw_nn.cp = 0; raw_nn.c = 0; raw_nn.k = 0;
-    if (nn < ntiles) raw_nn = extent_load(nn);  // loads in flight for the whole iteration
+    if (nn < ntiles) raw_nn = ext.load(nn, lane);  // loads in flight for the whole iteration
     const unsigned rows = rows_of(cur);
     const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
     const bool active = (unsigned)lane < rows;
@@ -1544,7 +1521,7 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     __syncwarp();
     if (lane == 0) {
 #pragma unroll
-      for (int q = 0; q < L::SLABS; q++) tma_store_2d(&tmap_out, q * 128, (int)(cur * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES);
+      for (int q = 0; q < L::SLABS; q++) tma_store_2d(tmap_out, q * 128, (int)(cur * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES);
       bulk_commit();
     }
     park_ragged(rag);
@@ -1554,9 +1531,52 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     raw_nn.c = pin_here(raw_nn.c);
     raw_nn.gp = pin_here(raw_nn.gp);
     raw_nn.cp = pin_here(raw_nn.cp);
-    ext_nxt = extent_finish(raw_nn);
+    ext_nxt = ext.finish(raw_nn, lane);
     nn = seq.advance(lane);
   }
+}
+
+template <typename T, bool QT>
+__global__ void __launch_bounds__(DecompressCfg<T, QT>::THREADS, DecompressCfg<T, QT>::CTAS_PER_SM)
+k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, const float *__restrict__ ac_in,
+             const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
+             const __grid_constant__ CUtensorMap tmap_out, const unsigned *__restrict__ counts,
+             const unsigned long long *__restrict__ group_prefix, const unsigned long long *__restrict__ chunk_prefix,
+             const unsigned long long *__restrict__ n_outliers_total, unsigned long long n_limit, TileControl *ctl,
+             unsigned *corrupt_flag, int dc_aligned16, unsigned batch) {
+  typedef DecompressCfg<T, QT> Cfg;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
+  __shared__ T s_qt[QT ? BLK : 1];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(16) T center[256];  // static: its address is an immediate of the lookups
+  unsigned char *wsm = smem + warp * Cfg::WARP_BYTES;
+  // (decompress_tiles) EC: a tile's outliers are turned into coefficients (converted to T, times sf) ONCE, cooperatively and
+  // conflict-free, before the lanes pick them up -- the per-coefficient work of a lane is then a select between two
+  // shared-memory addresses (pick_coefficient).  double: the converted values need 8 bytes each, so the prefetched
+  // floats are put in the upper half of the stage and expanded in place from the bottom.  Tiles with more than
+  // FAST_MAX outliers (double) and QT tiles (whose outliers are rescaled with a per-position table entry,
+  // dctz-decomp-lib.c:404-409) take the per-lane conversion path.
+  const unsigned mb = smem_u32(&s_mbar[warp]);
+
+  // bin centres: gen_bins / gen_bins_f (binning.c:19-22, 39-42): centre = (int multiple) * bin_width.  The de-scale
+  // (x * sf, dctz-decomp-lib.c:494-511) is folded into the coefficients -- the inverse transform is linear, the
+  // result moves by ~1 ulp -- so the table holds centre * sf.
+  for (int i = threadIdx.x; i < 256; i += Cfg::THREADS) center[i] = mul_rn<T>(mul_rn<T>((T)center_multiple((unsigned)i), bin_width), sf);
+  if (QT && threadIdx.x < BLK) s_qt[threadIdx.x] = qtable[threadIdx.x];
+  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
+  __syncthreads();  // the only CTA-wide barrier before the epilogue
+
+  const unsigned long long n_scan = __ldg(n_outliers_total);
+  ScannedExtents ext;
+  ext.counts = counts; ext.group_prefix = group_prefix; ext.chunk_prefix = chunk_prefix; ext.n_limit = n_limit; ext.corrupt_flag = corrupt_flag;
+  TileSeq seq;
+  seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
+  unsigned phase = 0;
+  decompress_tiles<T, QT>(bins, dc_in, ac_in, nblk_full, sf, qk, &tmap_out, n_scan < n_limit ? n_scan : n_limit, dc_aligned16, wsm, mb, center, s_qt,
+                          seq, ext, lane, phase);
   bulk_wait_all();
   // every warp still has one look-ahead ticket request outstanding (TileSeq::advance): its result is consumed here, so
   // the increment has been performed before this thread's fence and therefore before the last CTA resets the counter
