@@ -22,7 +22,7 @@ EXPORTS = [
     "dctz_gpu_stats_dev", "dctz_gpu_compress_dev", "dctz_gpu_compress_known_stats_dev", "dctz_gpu_qt_finish_dev", "dctz_gpu_compress_field_dev",
     "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_dct64_dev", "dctz_gpu_fill_hash_field",
     "dctz_gpu_sf_from_max", "dctz_gpu_selftest_division", "dctz_gpu_launch_count", "dctz_gpu_compress_core_cb",
-    "dctz_gpu_set_timing", "dctz_gpu_last_call_stats",
+    "dctz_gpu_set_timing", "dctz_gpu_last_call_stats", "dctz_gpu_fused_phase_times", "dctz_gpu_compress_slab_comm",
 ]
 
 
@@ -83,6 +83,7 @@ def load_library():
         "dctz_gpu_launch_count": (u64, [vp]),
         "dctz_gpu_compress_core_cb": (i32, [vp, vp, sz, i32, dbl, i32, vp, vp, vp, vp, vp, vp, C.POINTER(GpuInfo), vp, vp]),
         "dctz_gpu_set_timing": (i32, [vp, i32]),
+        "dctz_gpu_fused_phase_times": (i32, [vp, i32, C.POINTER(dbl)]),
         "dctz_gpu_last_call_stats": (i32, [vp, C.POINTER(dbl), C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
@@ -177,6 +178,13 @@ class Context:
 
     def set_timing(self, on):
         return self._lib.dctz_gpu_set_timing(self._h, int(bool(on)))
+
+    def fused_phase_times(self, kernel):
+        """[(earliest, latest)] per phase stamp of the last single-launch kernel (0 compress, 1 decompress), microseconds"""
+        t = (C.c_double * 16)()
+        self._check(self._lib.dctz_gpu_fused_phase_times(self._h, int(kernel), t))
+        n = 6 if kernel == 0 else 4
+        return [(t[2 * k], t[2 * k + 1]) for k in range(n)]
 
     def last_call_stats(self):
         """stage timers (ms) and PCIe bytes of the last host-buffer call"""

@@ -8,6 +8,7 @@
 // There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -186,6 +187,8 @@ struct dctz_gpu_ctx {
   unsigned long long *d_cta_totals = nullptr;  // outliers per CTA (two halves: compress, decompress)
   unsigned long long *d_qmax_scratch = nullptr;  // QT: 64 per-position maxima (bit patterns)
   DevBuf tile_off;                             // decompress: offset of every tile's run inside its CTA's range
+  unsigned long long *d_dbg = nullptr;         // phase timestamps of the last single-launch kernels: [2][sm_count * 4][8]
+  int dbg_grid[2] = {0, 0};
 };
 
 // ------------------------------------------------------------------------------------------
@@ -298,7 +301,7 @@ extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void *small[] = {ctx->d_barrier, ctx->d_cta_totals, ctx->d_qmax_scratch, ctx->tile_off.p, ctx->d_partials, ctx->d_done, ctx->d_stats3, ctx->d_params, ctx->d_info, ctx->d_ctl,
+  void *small[] = {ctx->d_dbg, ctx->d_barrier, ctx->d_cta_totals, ctx->d_qmax_scratch, ctx->tile_off.p, ctx->d_partials, ctx->d_done, ctx->d_stats3, ctx->d_params, ctx->d_info, ctx->d_ctl,
                    ctx->d_nconsumed, ctx->d_mismatch, ctx->d_qpartials, ctx->d_stats_host3, (void *)ctx->tb.thr_d, (void *)ctx->tb.sf_d,
                    (void *)ctx->tb.thr_f, (void *)ctx->tb.sf_f};
   for (void *p : small) if (p) cudaFree(p);
@@ -397,6 +400,7 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   CU(cudaMemset(ctx->d_barrier, 0, 2 * sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_cta_totals, 2 * (size_t)ctx->sm_count * 4 * sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_qmax_scratch, BLK * sizeof(unsigned long long)));
+  CU(cudaMalloc(&ctx->d_dbg, 2 * (size_t)ctx->sm_count * 4 * 8 * sizeof(unsigned long long)));
   if (const char *e = getenv("DCTZ_FUSED_MAX_MB")) ctx->fused_max_bytes = (size_t)atol(e) << 20;
   for (int a = 0; a < 2; a++)
     for (int b = 0; b < 2; b++)
@@ -455,13 +459,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 static EncodeTiledFn g_encode = nullptr;
 
 static int make_tile_map(dctz_gpu_ctx *ctx, CUtensorMap *map, const void *base, size_t row_bytes, unsigned long long nrows) {
-  if (!g_encode) {
+  static std::once_flag once;
+  std::call_once(once, [] {
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
-      return fail(ctx, DCTZ_GPU_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    g_encode = (EncodeTiledFn)fn;
-  }
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) g_encode = (EncodeTiledFn)fn;
+  });
+  if (!g_encode) return fail(ctx, DCTZ_GPU_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)nrows};
   const cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
   const cuuint32_t box[2] = {128u, (cuuint32_t)WTILE};
@@ -773,8 +777,10 @@ static int launch_compress_fused(dctz_gpu_ctx *ctx, int grid, const T *d_in, siz
   unsigned long long base = ctx->barrier_base[0];
   DevParams *params = ctx->d_params;
   unsigned *counts = sb.counts;
+  unsigned long long *dbg = ctx->d_dbg;
+  ctx->dbg_grid[0] = grid;
   void *args[] = {&tmap, &d_in, &nblk_full, &qc, &qk, &d_bins, &d_dc, &counts, &ac_slots, &raw, &jpos, &d_ac, &q_out, &q_raw, &qmax,
-                  &partials, &totals, &tb, &params, &d_info, &bar, &base};
+                  &partials, &totals, &tb, &params, &d_info, &bar, &base, &dbg};
   CU(cudaLaunchCooperativeKernel((const void *)k_compress_fused<T, QT>, dim3(grid), dim3(Cfg::THREADS), args, Cfg::SMEM, st));
   ctx->barrier_base[0] += 2ull * (unsigned long long)grid;
   ctx->launches++;
@@ -789,6 +795,71 @@ static int compress_fused_dispatch(dctz_gpu_ctx *ctx, int grid, const void *d_in
   }
   if (mode_qt) return launch_compress_fused<float, true>(ctx, grid, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable, d_qtable_raw, d_info, st);
   return launch_compress_fused<float, false>(ctx, grid, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable, d_qtable_raw, d_info, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU slabs from C: the ONE exchange the path needs, inside the library, for callers that have an
+// NCCL communicator (one process or thread per GPU, e.g. under MPI) and no Python around it.  NCCL is resolved at run
+// time from the process (the caller created its communicator with some libnccl: that one is used) or from
+// libnccl.so.2; the library does not link it.  Only the handful of enum values of nccl.h that the calls need are
+// restated here (stable since NCCL 2.0).
+// ------------------------------------------------------------------------------------------
+typedef int (*NcclAllGatherFn)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*NcclAllReduceFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*NcclBroadcastFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*NcclErrFn)(int);
+static struct { NcclAllGatherFn all_gather; NcclAllReduceFn all_reduce; NcclBroadcastFn broadcast; NcclErrFn err; } g_nccl = {};
+constexpr int kNcclFloat = 7, kNcclDouble = 8, kNcclMax = 2;  // ncclFloat32, ncclFloat64, ncclMax (nccl.h)
+
+static int load_nccl(dctz_gpu_ctx *ctx) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *h = RTLD_DEFAULT;
+    if (!dlsym(h, "ncclAllGather")) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      g_nccl.all_gather = (NcclAllGatherFn)dlsym(h, "ncclAllGather");
+      g_nccl.all_reduce = (NcclAllReduceFn)dlsym(h, "ncclAllReduce");
+      g_nccl.broadcast = (NcclBroadcastFn)dlsym(h, "ncclBroadcast");
+      g_nccl.err = (NcclErrFn)dlsym(h, "ncclGetErrorString");
+    }
+  });
+  if (!g_nccl.all_gather || !g_nccl.all_reduce || !g_nccl.broadcast) return fail(ctx, DCTZ_GPU_ENODEV, "NCCL is not available in this process (libnccl.so.2)");
+  return DCTZ_GPU_OK;
+}
+#define NCCL(call)                                                                                                     \
+  do {                                                                                                                 \
+    const int r_ = (call);                                                                                             \
+    if (r_ != 0) return fail(ctx, DCTZ_GPU_ECUDA, "%s: %s", #call, g_nccl.err ? g_nccl.err(r_) : "NCCL error");        \
+  } while (0)
+
+extern "C" int dctz_gpu_compress_slab_comm(dctz_gpu_ctx *ctx, void *nccl_comm, int rank, int nranks, int last_rank_with_data,
+                                           const void *d_in, size_t N, size_t N_total, int datatype, double eb, int mode_qt, uint8_t *d_bins,
+                                           float *d_dc, float *d_ac, void *d_qtable, void *d_qtable_raw, dctz_gpu_info *d_info, void *stream) {
+  TRY(check_compress_args(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, d_info));
+  if (!nccl_comm || nranks < 1 || rank < 0 || rank >= nranks || last_rank_with_data < 0 || last_rank_with_data >= nranks || N_total < N)
+    return fail(ctx, DCTZ_GPU_EINVAL, "compress_slab_comm: bad communicator / rank arguments");
+  if (mode_qt && !d_qtable) return fail(ctx, DCTZ_GPU_EINVAL, "compress_slab_comm: QT mode needs d_qtable");
+  TRY(load_nccl(ctx));
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = datatype == DCTZ_GPU_DOUBLE ? 8 : 4;
+  TRY(grow(ctx, ctx->chunk_stats, (size_t)nranks * 3 * sizeof(double) + BLK * 8));
+  double *d_all = (double *)ctx->chunk_stats.p;
+  // statistics of the slab -> all-gather of {max, min, sum} (24 bytes per rank) -> every rank merges them in rank order
+  TRY(dctz_gpu_stats_dev(ctx, d_in, N, datatype, ctx->d_stats3, st));
+  NCCL(g_nccl.all_gather(ctx->d_stats3, d_all, 3, kNcclDouble, nccl_comm, st));
+  TRY(dctz_gpu_compress_dev(ctx, d_in, N, N_total, datatype, eb, mode_qt, d_all, nranks, rank == 0, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st));
+  if (mode_qt) {
+    // per-position maxima: MAX over the ranks; entry 0 (the DC of the field's last block, dctz-comp-lib.c:355-360) comes from
+    // the last rank that holds data -- saved aside, reduced with the rest, broadcast, put back
+    char *keep = (char *)(d_all + 3 * (size_t)nranks);
+    CU(cudaMemcpyAsync(keep, d_qtable_raw, es, cudaMemcpyDeviceToDevice, st));
+    NCCL(g_nccl.all_reduce(d_qtable_raw, d_qtable_raw, BLK, es == 8 ? kNcclDouble : kNcclFloat, kNcclMax, nccl_comm, st));
+    NCCL(g_nccl.broadcast(keep, keep, 1, es == 8 ? kNcclDouble : kNcclFloat, last_rank_with_data, nccl_comm, st));
+    CU(cudaMemcpyAsync(d_qtable_raw, keep, es, cudaMemcpyDeviceToDevice, st));
+    TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, d_qtable_raw, d_qtable, d_ac, d_info, st));
+  }
+  return DCTZ_GPU_OK;
 }
 
 extern "C" int dctz_gpu_compress_field_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt,
@@ -835,7 +906,9 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
     unsigned long long *totals = ctx->d_cta_totals + (size_t)ctx->sm_count * 4, *bar = ctx->d_barrier + 1;
     unsigned long long base = ctx->barrier_base[1], lim = ac_limit;
     int dca = aligned16(d_dc) ? 1 : 0;
-    void *args[] = {&d_bins, &d_dc, &d_ac, &d_qtable, &nb, &bw_, &sf_, &qk_, &tmap, &counts, &toff, &totals, &lim, &d_corrupt, &dca, &bar, &base};
+    unsigned long long *dbg = ctx->d_dbg + (size_t)ctx->sm_count * 4 * 8;
+    ctx->dbg_grid[1] = fgrid;
+    void *args[] = {&d_bins, &d_dc, &d_ac, &d_qtable, &nb, &bw_, &sf_, &qk_, &tmap, &counts, &toff, &totals, &lim, &d_corrupt, &dca, &bar, &base, &dbg};
     CU(cudaLaunchCooperativeKernel((const void *)k_decompress_fused<T, QT>, dim3(fgrid), dim3(Cfg::THREADS), args, Cfg::SMEM, st));
     ctx->barrier_base[1] += (unsigned long long)fgrid;
     ctx->launches++;
@@ -1188,6 +1261,28 @@ extern "C" int dctz_gpu_compress_core_with_stats(dctz_gpu_ctx *ctx, const void *
   if (!stats3 || N_total < N) return fail(ctx, DCTZ_GPU_EINVAL, "compress_core_with_stats: bad statistics arguments");
   return compress_core_impl(ctx, in, N, N_total, stats3, first_piece, datatype, eb, mode_qt, scaled_out, bin_index, DC, AC_exact, qtable,
                             qtable_raw, info, nullptr, nullptr);
+}
+
+// Phase boundaries of the last single-launch kernel (kernel 0 = compress, 1 = decompress), synchronous: for every stamp
+// k (fused.cuh) the earliest and the latest CTA, in microseconds after the earliest CTA's start: out[2k], out[2k+1].
+extern "C" int dctz_gpu_fused_phase_times(dctz_gpu_ctx *ctx, int kernel, double out_us[16]) {
+  if (!ctx || kernel < 0 || kernel > 1 || !out_us) return fail(ctx, DCTZ_GPU_EINVAL, "fused_phase_times: bad arguments");
+  const int grid = ctx->dbg_grid[kernel];
+  if (grid <= 0) return fail(ctx, DCTZ_GPU_EINVAL, "fused_phase_times: no single-launch kernel has run");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  std::vector<unsigned long long> h((size_t)grid * 8);
+  CU(cudaMemcpy(h.data(), ctx->d_dbg + (size_t)kernel * ctx->sm_count * 4 * 8, h.size() * 8, cudaMemcpyDeviceToHost));
+  unsigned long long t0 = ~0ull;
+  for (int b = 0; b < grid; b++) t0 = h[8 * b] < t0 ? h[8 * b] : t0;
+  const int nstamp = kernel == 0 ? 6 : 4;
+  for (int k = 0; k < 8; k++) {
+    unsigned long long lo = ~0ull, hi = 0;
+    for (int b = 0; b < grid && k < nstamp; b++) { const unsigned long long v = h[8 * b + k]; lo = v < lo ? v : lo; hi = v > hi ? v : hi; }
+    out_us[2 * k] = k < nstamp ? (double)(lo - t0) / 1e3 : 0.0;
+    out_us[2 * k + 1] = k < nstamp ? (double)(hi - t0) / 1e3 : 0.0;
+  }
+  return DCTZ_GPU_OK;
 }
 
 extern "C" int dctz_gpu_set_timing(dctz_gpu_ctx *ctx, int on) {

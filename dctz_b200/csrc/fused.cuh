@@ -60,6 +60,16 @@ __device__ __forceinline__ void grid_arrive_only(unsigned long long *counter) {
   if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;\n" ::"l"(counter) : "memory");
 }
 
+// Phase timestamps (ns, %globaltimer) of every CTA of a single-launch kernel: dbg[8 * blockIdx.x + k]; read back by
+// dctz_gpu_fused_phase_times (profiles/: where the microseconds of a small field go).
+__device__ __forceinline__ void stamp(unsigned long long *dbg, int k) {
+  if (dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    dbg[8 * blockIdx.x + k] = t;
+  }
+}
+
 constexpr unsigned FUSED_MAX_TILES_PER_CTA = 2048;  // the per-CTA scratch (counts + offsets) lives in the idle tile buffers
 
 // exclusive scan of s_cnt[0..nt) into s_off by warp 0; returns the total in every lane of warp 0
@@ -98,7 +108,7 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
                  QtConsts<T> qk, uint8_t *__restrict__ bins, float *__restrict__ dc_out, unsigned *counts, float *ac_slots, T *raw_slots,
                  uint8_t *j_slots, float *__restrict__ ac_out, T *qtable_out, T *qtable_raw, typename BitsOf<T>::U *qmax_scratch,
                  StatPartial *partials, unsigned long long *cta_totals, SfTables tb, DevParams *params_out, Info *info,
-                 unsigned long long *barrier, unsigned long long barrier_base) {
+                 unsigned long long *barrier, unsigned long long barrier_base, unsigned long long *dbg) {
   typedef CompressCfg<T, QT> Cfg;
   typedef typename BitsOf<T>::U U;
   constexpr int VEC = 16 / (int)sizeof(T);
@@ -122,32 +132,60 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
   if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
   if (QT && blockIdx.x == 0 && threadIdx.x < BLK) qmax_scratch[threadIdx.x] = 0;  // ordered before every use by the first barrier
 
-  // ---- phase 1: statistics of the CTA's own range (util.c:12-44), eight 128-bit loads in flight per thread ----
+  stamp(dbg, 0);
+  // ---- phase 1: statistics of the CTA's own range (util.c:12-44).  Every warp streams chunks of one tile buffer's size
+  //      through its own buffer with TMA bulk copies (one instruction per 16 / 8 KB instead of a thousand LDG.128; 8-12
+  //      warps per SM keep > 100 KB in flight), the next chunk requested as soon as the current one is in registers ----
+  unsigned phase = 0;  // parity of the warp's mbarrier, carried on into the compress loop
+  __syncthreads();     // (the mbarriers are initialised)
   {
+    typedef WarpTile<T> L;
+    constexpr unsigned CH = (unsigned)L::BYTES;
+    constexpr int NV = (int)(CH / 16 / 32);  // 128-bit vectors per lane and chunk
     const unsigned long long e0 = (unsigned long long)t0 * (WTILE * BLK);
     unsigned long long e1 = (unsigned long long)t1 * (WTILE * BLK);
     if (e1 > nblk_full * BLK) e1 = nblk_full * BLK;
-    const uint4 *p = reinterpret_cast<const uint4 *>(in + e0);
-    const unsigned nvec = (unsigned)((e1 - e0) / VEC);
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(in + e0);
+    const unsigned long long bytes = (e1 - e0) * sizeof(T);  // a multiple of 64 elements: of 16 bytes
+    const unsigned nchunks = (unsigned)((bytes + CH - 1) / CH);
+    auto len_of = [&](unsigned c) -> unsigned { const unsigned long long left = bytes - (unsigned long long)c * CH; return left < CH ? (unsigned)left : CH; };
+    auto issue = [&](unsigned c) {
+      if (lane == 0) { mbar_expect_tx(mb, len_of(c)); bulk_g2s(smem_u32(wsm), src + (unsigned long long)c * CH, len_of(c), mb); }
+    };
     unsigned long long umax = 0ull, umin = ~0ull;
     double s0 = 0.0, s1 = 0.0;
-    for (unsigned i0 = threadIdx.x; i0 < nvec; i0 += Cfg::THREADS * 8) {
-      uint4 v[8];
+    unsigned c = (unsigned)warp;
+    if (c < nchunks) issue(c);
+    while (c < nchunks) {
+      mbar_wait(mb, phase);
+      phase ^= 1u;
+      const unsigned nv = len_of(c) / 16;
+      const uint4 *buf = reinterpret_cast<const uint4 *>(wsm);
+      unsigned probe = 0;
 #pragma unroll
-      for (int u = 0; u < 8; u++) { const unsigned i = i0 + u * Cfg::THREADS; v[u] = i < nvec ? __ldg(p + i) : make_uint4(0u, 0u, 0u, 0u); }
+      for (int h = 0; h < 2; h++) {  // two batches bound the registers
+        uint4 v[NV / 2];
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        if (i0 + u * Cfg::THREADS < nvec) {
-          const T *e = reinterpret_cast<const T *>(&v[u]);
+        for (int u = 0; u < NV / 2; u++) { const unsigned i = (unsigned)(h * (NV / 2) + u) * 32u + lane; v[u] = i < nv ? buf[i] : make_uint4(0u, 0u, 0u, 0u); }
 #pragma unroll
-          for (int q = 0; q < VEC; q++) {
-            const unsigned long long a = AbsBits<T>::get(e[q]);
-            umax = a > umax ? a : umax;
-            umin = a < umin ? a : umin;
-            if (q & 1) s1 += (double)e[q]; else s0 += (double)e[q];
+        for (int u = 0; u < NV / 2; u++) {
+          probe |= v[u].x ^ v[u].w;
+          if ((unsigned)(h * (NV / 2) + u) * 32u + lane < nv) {
+            const T *e = reinterpret_cast<const T *>(&v[u]);
+#pragma unroll
+            for (int q = 0; q < VEC; q++) {
+              const unsigned long long a = AbsBits<T>::get(e[q]);
+              umax = a > umax ? a : umax;
+              umin = a < umin ? a : umin;
+              if (q & 1) s1 += (double)e[q]; else s0 += (double)e[q];
+            }
           }
         }
       }
+      const unsigned cn = c + Cfg::WARPS;
+      __syncwarp();
+      if (reads_have_landed(probe) && cn < nchunks) issue(cn);
+      c = cn;
     }
     double sum = s0 + s1;
 #pragma unroll
@@ -169,7 +207,9 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
       partials[blockIdx.x] = r;
     }
   }
+  stamp(dbg, 1);
   grid_barrier(barrier, barrier_base + gridDim.x);
+  stamp(dbg, 2);
 
   // ---- phase 2: every CTA reduces the partials in index order (deterministic) and derives sf for itself ----
   if (warp == 0) {
@@ -208,7 +248,6 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
     RangeSeq seq;
     seq.init_down(t0, t1, warp, Cfg::WARPS);
     U seen = 0;
-    unsigned phase = 0;
     compress_tiles<T, QT, false>(&tmap_in, nblk_full, &s_params, qc, bins, dc_out, counts, ac_slots, raw_slots, j_slots, qtable_raw, wsm, mb, seq,
                                  lane, seen, phase);
   }
@@ -249,7 +288,9 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
     __syncthreads();
     if (threadIdx.x >= 1 && threadIdx.x < BLK && s_max[threadIdx.x] != 0) atomicMax(&qmax_scratch[threadIdx.x], s_max[threadIdx.x]);
   }
+  stamp(dbg, 3);
   grid_barrier(barrier, barrier_base + 2ull * gridDim.x);
+  stamp(dbg, 4);
 
   // ---- phase 4: the CTA's outliers go to their final place (dctz-comp-lib.c:478-544) ----
   if (warp == 0) {
@@ -318,6 +359,7 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
     }
   }
   if (QT && dropped) atomicAdd(&info->n_qt_dropped, (unsigned long long)dropped);
+  stamp(dbg, 5);
 }
 
 // Extents of the single-launch decompress kernel: the tile's count and its offset inside the CTA's range (both written
@@ -350,7 +392,7 @@ k_decompress_fused(const uint8_t *__restrict__ bins, const float *__restrict__ d
                    const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
                    const __grid_constant__ CUtensorMap tmap_out, unsigned *counts, unsigned *tile_off, unsigned long long *cta_totals,
                    unsigned long long n_limit, unsigned *corrupt_flag, int dc_aligned16, unsigned long long *barrier,
-                   unsigned long long barrier_base) {
+                   unsigned long long barrier_base, unsigned long long *dbg) {
   typedef DecompressCfg<T, QT> Cfg;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
@@ -370,6 +412,7 @@ k_decompress_fused(const uint8_t *__restrict__ bins, const float *__restrict__ d
   if (QT && threadIdx.x < BLK) s_qt[threadIdx.x] = qtable[threadIdx.x];
   if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
 
+  stamp(dbg, 0);
   // ---- phase 1: 255 markers at positions j >= 1 of the CTA's own tiles (a warp per tile, two tiles per trip) ----
   unsigned *s_cnt = reinterpret_cast<unsigned *>(smem);  // the tile buffers are idle until the barrier
   unsigned *s_off = s_cnt + FUSED_MAX_TILES_PER_CTA;
@@ -416,7 +459,9 @@ k_decompress_fused(const uint8_t *__restrict__ bins, const float *__restrict__ d
   }
   __syncthreads();
   for (unsigned i = threadIdx.x; i < nt; i += Cfg::THREADS) tile_off[t0 + i] = s_off[i];
+  stamp(dbg, 1);
   grid_barrier(barrier, barrier_base + gridDim.x);
+  stamp(dbg, 2);
 
   // ---- phase 2: dequantise + inverse DCT + de-scale of the CTA's own tiles ----
   if (warp == 0) {
@@ -434,6 +479,8 @@ k_decompress_fused(const uint8_t *__restrict__ bins, const float *__restrict__ d
   decompress_tiles<T, QT>(bins, dc_in, ac_in, nblk_full, sf, qk, &tmap_out, n_scan < n_limit ? n_scan : n_limit, dc_aligned16, wsm, mb, center, s_qt,
                           seq, ext, lane, phase);
   bulk_wait_all();
+  __syncthreads();
+  stamp(dbg, 3);
 }
 
 }  // namespace dctz

@@ -179,6 +179,19 @@ int dctz_gpu_compress_known_stats_dev(dctz_gpu_ctx *ctx, const void *d_in, size_
 int dctz_gpu_qt_finish_dev(dctz_gpu_ctx *ctx, int datatype, double error_bound, const void *d_qtable_raw,
                            void *d_qtable, float *d_AC_exact, dctz_gpu_info *d_info, void *stream);
 
+/* Phases 1+2(+3) of ONE RANK of a multi-GPU job, with the exchange between them done inside the library over the
+ * caller's NCCL communicator (`nccl_comm` is an ncclComm_t passed as void*): statistics -> ncclAllGather of
+ * {max, min, sum} (24 bytes per rank) -> compress [-> QT: ncclAllReduce(max) of the 64-entry table, entry 0
+ * broadcast from `last_rank_with_data` (the rank whose slab ends the field) -> rescale].  Everything is enqueued
+ * on `stream`; the call does not synchronise with the host.  Every rank calls it with its own slab (N > 0; slabs
+ * are contiguous runs of whole blocks in rank order, only the last may end with a partial block) -- this is what
+ * a C / MPI caller uses where bench.py uses torch.distributed.  NCCL is looked up in the process at run time
+ * (DCTZ_GPU_ENODEV if there is none); the library does not link it.                                    */
+int dctz_gpu_compress_slab_comm(dctz_gpu_ctx *ctx, void *nccl_comm, int rank, int nranks, int last_rank_with_data,
+                                const void *d_in, size_t N, size_t N_total, int datatype, double error_bound,
+                                int mode_qt, uint8_t *d_bin_index, float *d_DC, float *d_AC_exact, void *d_qtable,
+                                void *d_qtable_raw, dctz_gpu_info *d_info, void *stream);
+
 /* Convenience: phases 1+2(+3) for a whole field on one GPU, nothing leaves the device.          */
 int dctz_gpu_compress_field_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype,
                                 double error_bound, int mode_qt, uint8_t *d_bin_index, float *d_DC,
@@ -234,6 +247,11 @@ uint64_t dctz_gpu_launch_count(const dctz_gpu_ctx *ctx);
  * [2] transform kernels (CUDA events, only with timing on), [3] wall clock until the kernels were done,
  * [4] wall clock of the downloads + host-side scaling; and the PCIe bytes the call moved.          */
 int dctz_gpu_set_timing(dctz_gpu_ctx *ctx, int on);
+/* Where the microseconds of a small field go: phase boundaries of the last single-launch kernel (kernel 0 =
+ * compress: start, statistics done, past barrier 1, compress done, past barrier 2, end; 1 = decompress: start,
+ * markers counted, past the barrier, end).  For stamp k the earliest CTA is out_us[2k], the latest out_us[2k+1],
+ * in microseconds after the first CTA started.  Synchronises the device.                              */
+int dctz_gpu_fused_phase_times(dctz_gpu_ctx *ctx, int kernel, double out_us[16]);
 int dctz_gpu_last_call_stats(const dctz_gpu_ctx *ctx, double times_ms[8], uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
 #ifdef __cplusplus
