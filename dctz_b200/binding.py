@@ -23,6 +23,7 @@ EXPORTS = [
     "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_dct64_dev", "dctz_gpu_fill_hash_field",
     "dctz_gpu_sf_from_max", "dctz_gpu_selftest_division", "dctz_gpu_launch_count", "dctz_gpu_compress_core_cb",
     "dctz_gpu_set_timing", "dctz_gpu_last_call_stats", "dctz_gpu_fused_phase_times", "dctz_gpu_compress_slab_comm",
+    "dctz_gpu_sample_dev", "dctz_gpu_compress_spec_dev", "dctz_gpu_compress_spec_finish_dev",
 ]
 
 
@@ -72,6 +73,9 @@ def load_library():
         "dctz_gpu_compress_dev": (i32, [vp, vp, sz, sz, i32, dbl, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "dctz_gpu_compress_known_stats_dev": (i32, [vp, vp, sz, sz, i32, dbl, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "dctz_gpu_qt_finish_dev": (i32, [vp, i32, dbl, vp, vp, vp, vp, vp]),
+        "dctz_gpu_sample_dev": (i32, [vp, vp, sz, i32, vp, vp]),
+        "dctz_gpu_compress_spec_dev": (i32, [vp, vp, sz, sz, i32, dbl, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "dctz_gpu_compress_spec_finish_dev": (i32, [vp, vp, sz, sz, i32, dbl, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "dctz_gpu_compress_field_dev": (i32, [vp, vp, sz, i32, dbl, i32, vp, vp, vp, vp, vp, vp, vp]),
         "dctz_gpu_decompress_dev": (i32, [vp, vp, vp, vp, u64, vp, sz, i32, dbl, dbl, i32, vp, vp, vp]),
         "dctz_gpu_scale_dev": (i32, [vp, vp, sz, i32, dbl, i32, vp]),
@@ -293,10 +297,26 @@ class Context:
 
     def compress_known_stats_dev(self, d_in, n, n_total, code, eb, qt, d_stats_all, nranks, first_slab, d_bins, d_dc, d_ac,
                                  d_qtable_raw, d_info, stream=0):
-        """compress_dev with caller-supplied statistics that the kernel verifies (info.status = -6 if stale)"""
+        """whole field with a caller-supplied belief about its statistics: one read of the input, a wrong belief is corrected
+        on the device (info.n_exact_path = 1)"""
         self._check(self._lib.dctz_gpu_compress_known_stats_dev(self._h, d_in, n, n_total, code, float(eb), int(bool(qt)), d_stats_all,
                                                                 int(nranks), int(bool(first_slab)), d_bins, d_dc, d_ac,
                                                                 d_qtable_raw or None, d_info, stream or None))
+
+    def sample_dev(self, d_in, n, code, d_belief3, stream=0):
+        """single-read path, step 1: max|x| over a 0.4 % sample (+ the exact tail block) -> d_belief3"""
+        self._check(self._lib.dctz_gpu_sample_dev(self._h, d_in, n, code, d_belief3, stream or None))
+
+    def compress_spec_dev(self, d_in, n, n_total, code, eb, qt, d_belief_all, nranks, first_slab, d_bins, d_dc, d_ac, d_qtable_raw, d_info, d_true3,
+                          stream=0):
+        """step 3: compress with the believed scaling factor, gathering the slab's true statistics -> d_true3"""
+        self._check(self._lib.dctz_gpu_compress_spec_dev(self._h, d_in, n, n_total, code, float(eb), int(bool(qt)), d_belief_all, int(nranks),
+                                                         int(bool(first_slab)), d_bins, d_dc, d_ac, d_qtable_raw or None, d_info, d_true3, stream or None))
+
+    def compress_spec_finish_dev(self, d_in, n, n_total, code, eb, qt, d_true_all, nranks, first_slab, d_bins, d_dc, d_ac, d_qtable_raw, d_info, stream=0):
+        """step 5: verdict from the true statistics (re-compress only if the belief was wrong), outlier scan + gather"""
+        self._check(self._lib.dctz_gpu_compress_spec_finish_dev(self._h, d_in, n, n_total, code, float(eb), int(bool(qt)), d_true_all, int(nranks),
+                                                                int(bool(first_slab)), d_bins, d_dc, d_ac, d_qtable_raw or None, d_info, stream or None))
 
     def qt_finish_dev(self, code, eb, d_qtable_raw, d_qtable, d_ac, d_info, stream=0):
         self._check(self._lib.dctz_gpu_qt_finish_dev(self._h, code, float(eb), d_qtable_raw, d_qtable, d_ac, d_info, stream or None))

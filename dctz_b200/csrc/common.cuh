@@ -228,6 +228,8 @@ struct TileControl {
   unsigned long long max_bits;  // VERIFY variant of K2: largest |x| bit pattern seen so far
   unsigned corrupt;  // K3: set when the bin indices mark more outliers than the caller's AC_exact array holds
   unsigned pad_;
+  unsigned long long min_bits;  // VERIFY: smallest |x| bit pattern (kept at ~0 between launches)
+  double belief_sf;             // the scaling factor the VERIFY launch compressed with (read by the REDO launch)
 };
 
 // Keep the first USE of a long-latency result (a ticket atomic, a prefetched global load) where the source puts it:

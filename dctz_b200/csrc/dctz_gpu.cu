@@ -182,11 +182,16 @@ struct dctz_gpu_ctx {
   int occ_fused[2][2][2] = {};
   size_t fused_max_bytes = (size_t)256 << 20;  // fields up to this size take the single-launch path (DCTZ_FUSED_MAX_MB, 0 = never)
   int coop = 0;                                // cooperative launches supported
+  int single_read = 1;                         // whole fields take the single-read (sample + verify) path (DCTZ_SINGLE_READ=0: two passes)
   unsigned long long *d_barrier = nullptr;     // [0] compress, [1] decompress: grid-barrier arrival counters (monotonic)
   unsigned long long barrier_base[2] = {0, 0}; // what the counters will have reached when the next launch starts
   unsigned long long *d_cta_totals = nullptr;  // outliers per CTA (two halves: compress, decompress)
   unsigned long long *d_qmax_scratch = nullptr;  // QT: 64 per-position maxima (bit patterns)
   DevBuf tile_off;                             // decompress: offset of every tile's run inside its CTA's range
+  double *d_tail3 = nullptr;                   // exact {max, min, sum} of the partial tail block (k_sample)
+  double *d_spec3 = nullptr;                   // [0..2] belief, [3..5] true statistics of the single-read path (whole fields)
+  unsigned long long *d_sample_bits = nullptr; // k_sample: running maximum (bit pattern)
+  DevBuf tile_sums;                            // per-tile sums + per-4096-tile partials (MODE_BELIEF)
   unsigned long long *d_dbg = nullptr;         // phase timestamps of the last single-launch kernels: [2][sm_count * 4][8]
   int dbg_grid[2] = {0, 0};
 };
@@ -301,7 +306,7 @@ extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void *small[] = {ctx->d_dbg, ctx->d_barrier, ctx->d_cta_totals, ctx->d_qmax_scratch, ctx->tile_off.p, ctx->d_partials, ctx->d_done, ctx->d_stats3, ctx->d_params, ctx->d_info, ctx->d_ctl,
+  void *small[] = {ctx->d_tail3, ctx->d_spec3, ctx->d_sample_bits, ctx->tile_sums.p, ctx->d_dbg, ctx->d_barrier, ctx->d_cta_totals, ctx->d_qmax_scratch, ctx->tile_off.p, ctx->d_partials, ctx->d_done, ctx->d_stats3, ctx->d_params, ctx->d_info, ctx->d_ctl,
                    ctx->d_nconsumed, ctx->d_mismatch, ctx->d_qpartials, ctx->d_stats_host3, (void *)ctx->tb.thr_d, (void *)ctx->tb.sf_d,
                    (void *)ctx->tb.thr_f, (void *)ctx->tb.sf_f};
   for (void *p : small) if (p) cudaFree(p);
@@ -350,13 +355,21 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   for (cudaEvent_t &e : ctx->ev_time) CU(cudaEventCreate(&e));
   ctx->stat_grid = ctx->sm_count * 8;
   CU(cudaMalloc(&ctx->d_partials, sizeof(StatPartial) * ctx->stat_grid));
-  CU(cudaMalloc(&ctx->d_done, 5 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups, [2] k_quality, [3] k_count_bins, [4] k_qt_max
-  CU(cudaMemset(ctx->d_done, 0, 5 * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->d_done, 8 * sizeof(unsigned)));  // [0] k_stats, [1] k_scan_groups, [2] k_quality, [3] k_count_bins, [4] k_qt_max, [5] k_sample, [6] k_reduce_tile_sums
+  CU(cudaMemset(ctx->d_done, 0, 8 * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->d_tail3, 3 * sizeof(double)));
+  CU(cudaMalloc(&ctx->d_spec3, 6 * sizeof(double)));
+  CU(cudaMalloc(&ctx->d_sample_bits, sizeof(unsigned long long)));
+  CU(cudaMemset(ctx->d_sample_bits, 0, sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_stats3, 3 * sizeof(double)));
   CU(cudaMalloc(&ctx->d_params, sizeof(DevParams)));
   CU(cudaMalloc(&ctx->d_info, sizeof(Info)));
   CU(cudaMalloc(&ctx->d_ctl, 2 * sizeof(TileControl)));
   CU(cudaMemset(ctx->d_ctl, 0, 2 * sizeof(TileControl)));
+  {
+    const unsigned long long ones = ~0ull;  // the running minimum of |x| (bit pattern) rests at all ones
+    CU(cudaMemcpy(&ctx->d_ctl[0].min_bits, &ones, sizeof ones, cudaMemcpyHostToDevice));
+  }
   CU(cudaMalloc(&ctx->d_nconsumed, sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_mismatch, sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_qpartials, sizeof(QualityPartial) * (ctx->stat_grid + 1)));
@@ -402,6 +415,7 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   CU(cudaMalloc(&ctx->d_qmax_scratch, BLK * sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_dbg, 2 * (size_t)ctx->sm_count * 4 * 8 * sizeof(unsigned long long)));
   if (const char *e = getenv("DCTZ_FUSED_MAX_MB")) ctx->fused_max_bytes = (size_t)atol(e) << 20;
+  if (const char *e = getenv("DCTZ_SINGLE_READ")) ctx->single_read = atoi(e) != 0;
   for (int a = 0; a < 2; a++)
     for (int b = 0; b < 2; b++)
       for (int c = 0; c < 2; c++)
@@ -570,9 +584,19 @@ extern "C" int dctz_gpu_stats_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N,
 // ------------------------------------------------------------------------------------------
 // phase 2: fused compress
 // ------------------------------------------------------------------------------------------
+struct StatArgs {  // where a compress launch takes its scaling factor from (kernels.cuh: StatSource)
+  const double *d_stats_all;
+  int nranks, first_slab, mode;
+  size_t n_total;
+  double *d_true3;  // MODE_BELIEF: receives the slab's true {max, min, sum}
+};
+
+// MODE_STATS:  [k_compress] -> [k_qt_max] -> [tail] -> scan -> gather           (true statistics known: the two-pass path)
+// MODE_BELIEF: [k_compress<VERIFY>] -> k_reduce_tile_sums                       (first half of the single-read path)
+// MODE_REDO:   [k_compress, leaves at once unless the belief was wrong] -> [k_qt_max] -> [tail] -> scan -> gather
 template <typename T, bool QT>
-static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb, uint8_t *d_bins, float *d_dc, float *d_ac,
-                           void *d_qtable_raw, Info *d_info, cudaStream_t st, int verify = 0, int verify_lower = 0) {
+static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb, const StatArgs &sa, uint8_t *d_bins, float *d_dc, float *d_ac,
+                           void *d_qtable_raw, Info *d_info, cudaStream_t st) {
   typedef CompressCfg<T, QT> Cfg;
   typedef typename BitsOf<T>::U U;
   const unsigned long long nblk_full = N / BLK;
@@ -599,6 +623,17 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     TRY(grow(ctx, ctx->slots, n_entries * TILE_SLOT * sizeof(float)));
     ac_slots = (float *)ctx->slots.p;
   }
+  StatSource src;
+  src.stats_all = sa.d_stats_all; src.nranks = sa.nranks; src.first_slab = sa.first_slab; src.is_double = sizeof(T) == 8; src.mode = sa.mode;
+  src.n_total = (unsigned long long)sa.n_total; src.first_elem = d_in; src.tb = ctx->tb;
+  src.tb.qmax_words = (int)(BLK * sizeof(T) / 8);
+  src.params = ctx->d_params;
+  src.qmax_zero = QT ? (unsigned long long *)d_qtable_raw : nullptr;
+  src.tile_sums = nullptr; src.true3 = sa.d_true3; src.tail3 = rem ? ctx->d_tail3 : nullptr;
+  if (sa.mode == MODE_BELIEF) {
+    TRY(grow(ctx, ctx->tile_sums, (ntiles + (ntiles + 4095) / 4096 + 8) * sizeof(double)));
+    src.tile_sums = (double *)ctx->tile_sums.p;
+  }
   if (nblk_full) {
     const size_t resident = (size_t)ctx->sm_count * ctx->occ[0][sizeof(T) == 8][QT];
     const size_t ctas = (ntiles + Cfg::WARPS - 1) / Cfg::WARPS;
@@ -607,18 +642,25 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     TRY(make_tile_map(ctx, &tmap, d_in, BLK * sizeof(T), nblk_full));
     fused.out = sb.out;
     fused.total = &d_info->n_outliers;
-    fused.n_entries = (rem == 0 && (n_entries + 31) / 32 <= 1024) ? (unsigned)n_entries : 0u;  // small field: the last CTA scans
+    // small field, true statistics: the last CTA scans (one launch less); the single-read modes scan after the REDO launch
+    fused.n_entries = (sa.mode == MODE_STATS && rem == 0 && (n_entries + 31) / 32 <= 1024) ? (unsigned)n_entries : 0u;
     const unsigned batch = tile_batch(ntiles, (size_t)grid * Cfg::WARPS);
-    if (verify)
-      k_compress<T, QT, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts,
-                                                                     ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0],
-                                                                     d_info, fused, verify_lower, batch);
+    if (sa.mode == MODE_BELIEF)
+      k_compress<T, QT, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, src, qc, d_bins, d_dc, sb.counts, ac_slots, raw, jpos,
+                                                                     (T *)d_qtable_raw, &ctx->d_ctl[0], d_info, fused, batch);
     else
-      k_compress<T, QT, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, ctx->d_params, qc, d_bins, d_dc, sb.counts,
-                                                                      ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, &ctx->d_ctl[0],
-                                                                      d_info, fused, 0, batch);
+      k_compress<T, QT, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, src, qc, d_bins, d_dc, sb.counts, ac_slots, raw, jpos,
+                                                                      (T *)d_qtable_raw, &ctx->d_ctl[0], d_info, fused, batch);
     ctx->launches++;
     CU(cudaGetLastError());
+    if (sa.mode == MODE_BELIEF) {
+      double *cta_sums = (double *)ctx->tile_sums.p + ntiles;
+      k_reduce_tile_sums<<<(unsigned)((ntiles + 4095) / 4096), 256, 0, st>>>((const double *)ctx->tile_sums.p, (unsigned)ntiles, cta_sums, ctx->d_done + 6,
+                                                                            rem ? ctx->d_tail3 : nullptr, sa.d_true3);
+      ctx->launches++;
+      CU(cudaGetLastError());
+      return DCTZ_GPU_OK;
+    }
     if (QT) {  // per-position maxima of the parked (unscaled) outliers, scaled by the kernel's last CTA (before the tail
                // block adds its own, scaled, values)
       const size_t groups = (ntiles + 31) / 32;
@@ -626,10 +668,15 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
       k_qt_max<T><<<gq, 256, 0, st>>>(sb.counts, (unsigned)ntiles, raw, jpos, (U *)d_qtable_raw, ctx->d_params, ctx->d_done + 4);
       ctx->launches++;
     }
+  } else {  // a field of one partial block: nothing for k_compress to do, the parameters come from the one-thread kernel
+    if (sa.mode == MODE_BELIEF) return fail(ctx, DCTZ_GPU_EINVAL, "internal: the single-read path needs at least one full block");
+    k_finalize<<<1, 32, 0, st>>>(sa.d_stats_all, sa.nranks, (unsigned long long)sa.n_total, sizeof(T) == 8, d_in, sa.first_slab, src.tb, ctx->d_params, d_info,
+                                 src.qmax_zero);
+    ctx->launches++;
   }
   if (rem) {
     k_tail_compress<T, QT><<<1, 32, 0, st>>>(d_in + nblk_full * BLK, rem, nblk_full, (unsigned)ntiles, ctx->d_params, qc, d_bins, d_dc,
-                                             sb.counts, ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, d_info, verify, verify_lower);
+                                             sb.counts, ac_slots, raw, jpos, (U *)d_qtable_raw, (T *)d_qtable_raw, d_info);
     ctx->launches++;
     CU(cudaGetLastError());
   }
@@ -647,15 +694,14 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
   return DCTZ_GPU_OK;
 }
 
-static int compress_dispatch(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt, uint8_t *d_bins,
-                             float *d_dc, float *d_ac, void *d_qtable_raw, Info *d_info, cudaStream_t st, int verify = 0,
-                             int verify_lower = 0) {
+static int compress_dispatch(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt, const StatArgs &sa, uint8_t *d_bins,
+                             float *d_dc, float *d_ac, void *d_qtable_raw, Info *d_info, cudaStream_t st) {
   if (datatype == DCTZ_GPU_DOUBLE) {
-    if (mode_qt) return launch_compress<double, true>(ctx, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st, verify, verify_lower);
-    return launch_compress<double, false>(ctx, (const double *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st, verify, verify_lower);
+    if (mode_qt) return launch_compress<double, true>(ctx, (const double *)d_in, N, eb, sa, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
+    return launch_compress<double, false>(ctx, (const double *)d_in, N, eb, sa, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
   }
-  if (mode_qt) return launch_compress<float, true>(ctx, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st, verify, verify_lower);
-  return launch_compress<float, false>(ctx, (const float *)d_in, N, eb, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st, verify, verify_lower);
+  if (mode_qt) return launch_compress<float, true>(ctx, (const float *)d_in, N, eb, sa, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
+  return launch_compress<float, false>(ctx, (const float *)d_in, N, eb, sa, d_bins, d_dc, d_ac, d_qtable_raw, d_info, st);
 }
 
 static int check_compress_args(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double eb, int mode_qt,
@@ -670,34 +716,70 @@ static int check_compress_args(dctz_gpu_ctx *ctx, const void *d_in, size_t N, in
 
 static int compress_dev_impl(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb, int mode_qt,
                              const double *d_stats_all, int nranks, int first_slab, uint8_t *d_bins, float *d_dc, float *d_ac,
-                             void *d_qtable_raw, dctz_gpu_info *d_info, void *stream, int verify) {
+                             void *d_qtable_raw, dctz_gpu_info *d_info, void *stream, int mode, double *d_true3) {
   TRY(check_compress_args(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, d_info));
   if (!d_stats_all || nranks < 1 || N_total < N) return fail(ctx, DCTZ_GPU_EINVAL, "compress: bad statistics arguments");
+  if (mode == MODE_BELIEF && (!d_true3 || N < (size_t)BLK)) return fail(ctx, DCTZ_GPU_EINVAL, "compress_spec: needs d_true3 and at least one full block");
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  SfTables tb = ctx->tb;
-  tb.qmax_words = (int)(BLK * (datatype == DCTZ_GPU_DOUBLE ? 8 : 4) / 8);
-  k_finalize<<<1, 32, 0, st>>>(d_stats_all, nranks, (unsigned long long)N_total, datatype == DCTZ_GPU_DOUBLE, d_in, first_slab, tb,
-                               ctx->d_params, (Info *)d_info, mode_qt ? (unsigned long long *)d_qtable_raw : nullptr);
-  ctx->launches++;
-  CU(cudaGetLastError());
-  // a slab of a larger field need not hold the global maximum: only a single-slab call can check the lower limit
-  return compress_dispatch(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, (Info *)d_info, st, verify,
-                           verify && N_total == N);
+  StatArgs sa;
+  sa.d_stats_all = d_stats_all; sa.nranks = nranks; sa.first_slab = first_slab; sa.mode = mode; sa.n_total = N_total; sa.d_true3 = d_true3;
+  return compress_dispatch(ctx, d_in, N, datatype, eb, mode_qt, sa, d_bins, d_dc, d_ac, d_qtable_raw, (Info *)d_info, (cudaStream_t)stream);
 }
 
 extern "C" int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb,
                                      int mode_qt, const double *d_stats_all, int nranks, int first_slab, uint8_t *d_bins,
                                      float *d_dc, float *d_ac, void *d_qtable_raw, dctz_gpu_info *d_info, void *stream) {
   return compress_dev_impl(ctx, d_in, N, N_total, datatype, eb, mode_qt, d_stats_all, nranks, first_slab, d_bins, d_dc, d_ac, d_qtable_raw,
-                           d_info, stream, 0);
+                           d_info, stream, MODE_STATS, nullptr);
 }
 
+// ---- the single-read path: belief (sample) -> compress while gathering the true statistics -> verdict / redo ----
+template <typename T> static int launch_sample(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double *d_belief3, cudaStream_t st) {
+  const size_t nsamp = (N * sizeof(T) / 16 + SAMPLE_STRIDE_VECS - 1) / SAMPLE_STRIDE_VECS;
+  const size_t want = (nsamp + 256 * 4 - 1) / (256 * 4);
+  const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? (want ? want : 1) : (size_t)ctx->sm_count * 8);
+  k_sample<T><<<grid, 256, 0, st>>>(d_in, N, ctx->d_sample_bits, ctx->d_done + 5, d_belief3, ctx->d_tail3);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return DCTZ_GPU_OK;
+}
+
+extern "C" int dctz_gpu_sample_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double *d_belief3, void *stream) {
+  TRY(check_common(ctx, datatype, 1.0));
+  if (!d_in || !d_belief3 || N == 0) return fail(ctx, DCTZ_GPU_EINVAL, "sample: NULL pointer or N == 0");
+  if (!aligned16(d_in)) return fail(ctx, DCTZ_GPU_EINVAL, "sample: input must be 16-byte aligned");
+  CU(cudaSetDevice(ctx->device));
+  if (datatype == DCTZ_GPU_DOUBLE) return launch_sample<double>(ctx, (const double *)d_in, N, d_belief3, (cudaStream_t)stream);
+  return launch_sample<float>(ctx, (const float *)d_in, N, d_belief3, (cudaStream_t)stream);
+}
+
+extern "C" int dctz_gpu_compress_spec_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb, int mode_qt,
+                                          const double *d_belief_all, int nranks, int first_slab, uint8_t *d_bins, float *d_dc, float *d_ac,
+                                          void *d_qtable_raw, dctz_gpu_info *d_info, double *d_true3, void *stream) {
+  return compress_dev_impl(ctx, d_in, N, N_total, datatype, eb, mode_qt, d_belief_all, nranks, first_slab, d_bins, d_dc, d_ac, d_qtable_raw, d_info,
+                           stream, MODE_BELIEF, d_true3);
+}
+
+extern "C" int dctz_gpu_compress_spec_finish_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb, int mode_qt,
+                                                 const double *d_true_all, int nranks, int first_slab, uint8_t *d_bins, float *d_dc, float *d_ac,
+                                                 void *d_qtable_raw, dctz_gpu_info *d_info, void *stream) {
+  return compress_dev_impl(ctx, d_in, N, N_total, datatype, eb, mode_qt, d_true_all, nranks, first_slab, d_bins, d_dc, d_ac, d_qtable_raw, d_info,
+                           stream, MODE_REDO, nullptr);
+}
+
+// One slab (or a whole field) with a caller-supplied belief about its statistics: compress_spec + finish in one call.
 extern "C" int dctz_gpu_compress_known_stats_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype, double eb,
                                                  int mode_qt, const double *d_stats_all, int nranks, int first_slab, uint8_t *d_bins,
                                                  float *d_dc, float *d_ac, void *d_qtable_raw, dctz_gpu_info *d_info, void *stream) {
-  return compress_dev_impl(ctx, d_in, N, N_total, datatype, eb, mode_qt, d_stats_all, nranks, first_slab, d_bins, d_dc, d_ac, d_qtable_raw,
-                           d_info, stream, 1);
+  if (nranks != 1 || N_total != N) return fail(ctx, DCTZ_GPU_EINVAL, "compress_known_stats: whole fields only (slabs: sample / compress_spec / compress_spec_finish)");
+  if (N < (size_t)BLK)  // nothing to speculate on: the two-pass path
+    return fail(ctx, DCTZ_GPU_EINVAL, "compress_known_stats: needs at least one full block");
+  // the partial tail block's exact statistics come from the sampling kernel (its belief output is not used)
+  TRY(dctz_gpu_sample_dev(ctx, d_in, N, datatype, ctx->d_spec3, stream));
+  TRY(compress_dev_impl(ctx, d_in, N, N_total, datatype, eb, mode_qt, d_stats_all, 1, first_slab, d_bins, d_dc, d_ac, d_qtable_raw, d_info, stream,
+                        MODE_BELIEF, ctx->d_spec3 + 3));
+  return compress_dev_impl(ctx, d_in, N, N_total, datatype, eb, mode_qt, ctx->d_spec3 + 3, 1, first_slab, d_bins, d_dc, d_ac, d_qtable_raw, d_info, stream,
+                           MODE_REDO, nullptr);
 }
 
 template <typename T>
@@ -782,7 +864,7 @@ static int launch_compress_fused(dctz_gpu_ctx *ctx, int grid, const T *d_in, siz
   void *args[] = {&tmap, &d_in, &nblk_full, &qc, &qk, &d_bins, &d_dc, &counts, &ac_slots, &raw, &jpos, &d_ac, &q_out, &q_raw, &qmax,
                   &partials, &totals, &tb, &params, &d_info, &bar, &base, &dbg};
   CU(cudaLaunchCooperativeKernel((const void *)k_compress_fused<T, QT>, dim3(grid), dim3(Cfg::THREADS), args, Cfg::SMEM, st));
-  ctx->barrier_base[0] += 2ull * (unsigned long long)grid;
+  ctx->barrier_base[0] += (unsigned long long)FUSED_COMPRESS_BARRIERS * (unsigned long long)grid;
   ctx->launches++;
   return DCTZ_GPU_OK;
 }
@@ -871,10 +953,17 @@ extern "C" int dctz_gpu_compress_field_dev(dctz_gpu_ctx *ctx, const void *d_in, 
   cudaStream_t st = (cudaStream_t)stream;
   if (const int grid = fused_grid(ctx, 0, N, datatype == DCTZ_GPU_DOUBLE ? 8 : 4, mode_qt))  // small field: one launch for everything
     return compress_fused_dispatch(ctx, grid, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable, d_qtable_raw, (Info *)d_info, st);
-  void *qz = mode_qt ? d_qtable_raw : nullptr;
-  if (datatype == DCTZ_GPU_DOUBLE) TRY(launch_stats<double>(ctx, (const double *)d_in, N, ctx->d_stats3, 1, N, qz, (Info *)d_info, st));
-  else TRY(launch_stats<float>(ctx, (const float *)d_in, N, ctx->d_stats3, 1, N, qz, (Info *)d_info, st));
-  TRY(compress_dispatch(ctx, d_in, N, datatype, eb, mode_qt, d_bins, d_dc, d_ac, d_qtable_raw, (Info *)d_info, st));
+  if (N >= (size_t)BLK && ctx->single_read) {
+    // SINGLE-READ path: the scaling factor only depends on the decade of max|x| (util.c:28), and a sample of 0.4 % of the
+    // slab almost always finds it.  sample -> compress with that belief while gathering the true statistics -> a gate
+    // launch that leaves at once when the belief held (else the slab is compressed again with the right factor).
+    TRY(dctz_gpu_sample_dev(ctx, d_in, N, datatype, ctx->d_spec3, stream));
+    TRY(dctz_gpu_compress_spec_dev(ctx, d_in, N, N, datatype, eb, mode_qt, ctx->d_spec3, 1, 1, d_bins, d_dc, d_ac, d_qtable_raw, d_info, ctx->d_spec3 + 3, stream));
+    TRY(dctz_gpu_compress_spec_finish_dev(ctx, d_in, N, N, datatype, eb, mode_qt, ctx->d_spec3 + 3, 1, 1, d_bins, d_dc, d_ac, d_qtable_raw, d_info, stream));
+  } else {  // two passes: statistics, then compress
+    TRY(dctz_gpu_stats_dev(ctx, d_in, N, datatype, ctx->d_stats3, stream));
+    TRY(dctz_gpu_compress_dev(ctx, d_in, N, N, datatype, eb, mode_qt, ctx->d_stats3, 1, 1, d_bins, d_dc, d_ac, d_qtable_raw, d_info, stream));
+  }
   if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, d_qtable_raw, d_qtable, d_ac, d_info, stream));
   return DCTZ_GPU_OK;
 }

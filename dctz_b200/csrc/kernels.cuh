@@ -273,6 +273,7 @@ __device__ __forceinline__ void finalize_params(const double *stats_all, int nra
     p->sf_d = sf; p->inv_sf_d = 0.0;
   }
   if (!(sf > 0.0)) status = -5;
+  if (!(sum - sum == 0.0)) status = -5;  // a NaN or an infinity among the data (the single-read path takes max|x| with FP max, which skips NaN)
   p->status = status;
   info->sf = sf; info->mean = mean; info->max_abs = mx; info->min_abs = mn; info->sum = sum;
   info->n_outliers = 0; info->n_edge = 0; info->n_exact_path = 0; info->n_qt_dropped = 0;
@@ -500,6 +501,19 @@ template <typename T, bool QT> struct CompressCfg {
 // its last CTA checks that it lies in the decade the scaling factor was derived from; if not, info->status =
 // DCTZ_GPU_ESTALE and the outputs are to be discarded.  `verify_lower` = 0 leaves the lower limit to the caller
 // (a slab of a larger field need not contain the global maximum).
+__device__ __forceinline__ double fabs_t(double v) { return fabs(v); }
+__device__ __forceinline__ float fabs_t(float v) { return fabsf(v); }
+__device__ __forceinline__ double fmax_t(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float fmax_t(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double fmin_t(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float fmin_t(float a, float b) { return fminf(a, b); }
+
+// VERIFY: what a thread has seen of the slab's true statistics while compressing with a BELIEF about them.
+template <typename T> struct VerifyStat {
+  T *slot;             // this thread's {max, min} of |x| over its blocks so far, in SHARED memory (the tile loop has no register to spare)
+  double *tile_sums;   // per-tile sum of x (global scratch), reduced in tile order afterwards: deterministic
+};
+
 // The tile loop of the compress kernels: one warp, tiles handed out by `seq` (TileSeq: dynamic tickets; RangeSeq: the
 // CTA's own contiguous range in the single-launch kernel), `phase` = the parity of the warp's mbarrier.
 template <typename T, bool QT, bool VERIFY, class Seq>
@@ -507,7 +521,7 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
                                                const QuantConsts<T> &qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
                                                unsigned *__restrict__ counts, float *__restrict__ ac_slots, T *__restrict__ raw_slots,
                                                uint8_t *__restrict__ j_slots, T *qtable0, unsigned char *wsm, unsigned mb, Seq &seq,
-                                               int lane, typename BitsOf<T>::U &seen_max, unsigned &phase) {
+                                               int lane, VerifyStat<T> &vstat, unsigned &phase) {
   typedef typename ArithOf<T>::type A;
   typedef CompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -559,8 +573,23 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
     const bool active = (unsigned)lane < rows;
     // (rows beyond the field arrive zero-filled: they quantise to bin 0 and are never stored)
     if constexpr (VERIFY) {
+      // the statistics pass folded into this one (util.c:12-44): max|x|, min|x| as FP max/min (one instruction per
+      // element; a NaN/inf shows in the sum), the tile's sum reduced over the warp in a fixed order -> deterministic
+      T bs = (T)0, bmax = (T)0, bmin = fabs_t(x[0]);
 #pragma unroll
-      for (int j = 0; j < BLK; j++) { const U a = BitsOf<T>::abs_bits(x[j]); seen_max = a > seen_max ? a : seen_max; }
+      for (int j = 0; j < BLK; j++) {  // one min/max instruction with an |x| operand each
+        bmax = fmax_t(bmax, fabs_t(x[j]));
+        bmin = fmin_t(bmin, fabs_t(x[j]));
+        bs += x[j];
+      }
+      if (active) {  // (rows beyond the field arrive zero-filled: they must not lower the minimum)
+        vstat.slot[0] = fmax_t(vstat.slot[0], bmax);
+        vstat.slot[1] = fmin_t(vstat.slot[1], bmin);
+      }
+      double ts = active ? (double)bs : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(FULL, ts, o);
+      if (lane == 0) vstat.tile_sums[cur] = ts;
     }
 
     // ---- orthonormal DCT-II (dct.c:55-103) of the unscaled block; x / sf is folded into the quantiser ----
@@ -673,23 +702,45 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
 
 }
 
+// Where the scaling factor of a launch comes from.  k_compress derives the parameters in its own prologue (every CTA for
+// itself, identically; CTA 0 publishes them and the result block): no separate one-thread launch in front of it.
+//   MODE_STATS   stats_all are the TRUE statistics of the field (one triple per rank, merged in rank order)
+//   MODE_BELIEF  stats_all are a BELIEF (a sample, the previous time step): the VERIFY instantiation compresses with the
+//                scaling factor they give and gathers the true max / min / per-tile sums of the slab on the way
+//   MODE_REDO    stats_all are the true statistics gathered by a MODE_BELIEF launch: if they give the scaling factor that
+//                launch used, every CTA leaves at once (the normal case: the input has been read ONCE); otherwise the
+//                slab is compressed again with the right one
+enum { MODE_STATS = 0, MODE_BELIEF = 1, MODE_REDO = 2 };
+struct StatSource {
+  const double *stats_all;
+  int nranks, first_slab, is_double, mode;
+  unsigned long long n_total;
+  const void *first_elem;       // element 0 of the field (only read by the first slab: util.c:21-25 skips it in the sum)
+  SfTables tb;
+  DevParams *params;            // published by CTA 0 (the tail kernel and the QT gather read it)
+  unsigned long long *qmax_zero;  // QT: the per-position maxima to clear
+  double *tile_sums;            // MODE_BELIEF: per-tile sums
+  double *true3;                // MODE_BELIEF: {max, min, -} of this slab's full blocks, merged with tail3 (the sum is added by k_reduce_tile_sums)
+  const double *tail3;          // MODE_BELIEF: exact {max, min, sum} of the partial tail block (from k_sample), or NULL
+};
+
 template <typename T, bool QT, bool VERIFY>
 __global__ void __launch_bounds__(CompressCfg<T, QT>::THREADS, CompressCfg<T, QT>::CTAS_PER_SM)
-k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_full, const DevParams *__restrict__ params,
+k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_full, StatSource src,
            QuantConsts<T> qc, uint8_t *__restrict__ bins, float *__restrict__ dc_out,
            unsigned *__restrict__ counts,                     // outliers per warp tile
            float *__restrict__ ac_slots,                      // EC: outlier scratch, TILE_SLOT entries per tile, packed
            T *__restrict__ raw_slots, uint8_t *__restrict__ j_slots,  // QT: raw outliers + their position j, same layout
-           typename BitsOf<T>::U *qmax_bits,                  // QT: 64 per-position maxima (bit patterns): filled by k_qt_max, unused here
-           T *qtable0,                                        // QT: entry 0 of the same table: the last full block's DC
-           TileControl *ctl, Info *info, FusedScan fused, int verify_lower, unsigned batch) {
-  typedef typename ArithOf<T>::type A;
+           T *qtable0,                                        // QT: entry 0 of the table: the last full block's DC
+           TileControl *ctl, Info *info, FusedScan fused, unsigned batch) {
   typedef CompressCfg<T, QT> Cfg;
-  typedef WarpTile<T> L;
   typedef typename BitsOf<T>::U U;
   constexpr unsigned FULL = 0xFFFFFFFFu;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
+  __shared__ DevParams s_params;
+  __shared__ Info s_info;
+  __shared__ int s_skip;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -697,23 +748,60 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
   const unsigned mb = smem_u32(&s_mbar[warp]);
 
   if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
+  if (threadIdx.x == 0) {  // sf and the quantiser's divisor, from the merged statistics (util.c:28/42)
+    double fv = 0.0;
+    if (src.first_slab) fv = src.is_double ? __ldg((const double *)src.first_elem) : (double)__ldg((const float *)src.first_elem);
+    finalize_params(src.stats_all, src.nranks, src.n_total, src.is_double, fv, src.first_slab, src.tb, &s_params, &s_info,
+                    (blockIdx.x == 0 && src.mode != MODE_REDO) ? src.qmax_zero : nullptr);
+    int skip = 0;
+    if (src.mode == MODE_REDO) {
+      skip = (s_params.status == 0 && s_params.sf_d == *reinterpret_cast<volatile double *>(&ctl->belief_sf)) ? 1 : 0;
+      if (!skip) s_info.n_exact_path = 1;  // the belief was wrong: the slab is compressed a second time
+    }
+    if (s_params.status != 0) skip = 1;  // degenerate statistics (max|x| = 0 / inf / NaN): nothing to compress, the status says why
+    s_skip = skip;
+    if (blockIdx.x == 0) {
+      if (src.mode == MODE_BELIEF) ctl->belief_sf = s_params.sf_d;
+      *src.params = s_params;
+      *info = s_info;
+    }
+  }
   __syncthreads();  // the only CTA-wide barrier before the epilogue
+  if (s_skip) return;
 
-  U seen_max = 0;  // VERIFY: largest |x| bit pattern of this thread's blocks
+  __shared__ T s_vstat[VERIFY ? 2 * Cfg::THREADS : 2];
+  VerifyStat<T> vstat;
+  vstat.slot = &s_vstat[VERIFY ? 2 * threadIdx.x : 0];
+  if (VERIFY) {
+    vstat.slot[0] = (T)0;
+    vstat.slot[1] = sizeof(T) == 8 ? (T)__longlong_as_double(0x7FF0000000000000ll) : (T)__int_as_float(0x7F800000);
+  }
+  vstat.tile_sums = src.tile_sums;
   unsigned phase = 0;
   TileSeq seq;
   seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
-  compress_tiles<T, QT, VERIFY>(&tmap_in, nblk_full, params, qc, bins, dc_out, counts, ac_slots, raw_slots, j_slots, qtable0, wsm, mb, seq, lane,
-                                seen_max, phase);
+  compress_tiles<T, QT, VERIFY>(&tmap_in, nblk_full, &s_params, qc, bins, dc_out, counts, ac_slots, raw_slots, j_slots, qtable0, wsm, mb, seq, lane,
+                                vstat, phase);
 
   // ---- epilogue ----
   bulk_wait_all();
   __syncthreads();
   __shared__ bool s_last;
   if constexpr (VERIFY) {
+    U bmax = BitsOf<T>::abs_bits(vstat.slot[0]), bmin = BitsOf<T>::abs_bits(vstat.slot[1]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const U m = __shfl_xor_sync(FULL, seen_max, o); seen_max = m > seen_max ? m : seen_max; }
-    if (lane == 0) atomicMax(&ctl->max_bits, (unsigned long long)seen_max);
+    for (int o = 16; o > 0; o >>= 1) {
+      const U m1 = __shfl_xor_sync(FULL, bmax, o), m2 = __shfl_xor_sync(FULL, bmin, o);
+      bmax = m1 > bmax ? m1 : bmax;
+      bmin = m2 < bmin ? m2 : bmin;
+    }
+    if (lane == 0) {
+      // widened to the double's bit pattern so that slabs of either type share the two 64-bit words
+      const double dmax = (double)(sizeof(T) == 8 ? __longlong_as_double((long long)(unsigned long long)bmax) : (double)__int_as_float((int)(unsigned)bmax));
+      const double dmin = (double)(sizeof(T) == 8 ? __longlong_as_double((long long)(unsigned long long)bmin) : (double)__int_as_float((int)(unsigned)bmin));
+      atomicMax(&ctl->max_bits, (unsigned long long)__double_as_longlong(dmax));
+      atomicMin(&ctl->min_bits, (unsigned long long)__double_as_longlong(dmin));
+    }
   }
   __threadfence();  // this thread's counts are visible device-wide before the CTA signs off
   __syncthreads();
@@ -725,13 +813,11 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
       ctl->done = 0u;
       if constexpr (VERIFY) {
         __threadfence();
-        const unsigned long long mb = atomicExch(&ctl->max_bits, 0ull);
-        const double mx = sizeof(T) == 8 ? __longlong_as_double((long long)mb) : (double)__int_as_float((int)(unsigned)mb);
-        info->max_abs = mx;  // the true maximum of this slab
-        if (!(mx < params->decade_hi) || (verify_lower && !(mx >= params->decade_lo))) {
-          info->status = -6;  // DCTZ_GPU_ESTALE
-          info->n_exact_path = 1;
-        }
+        double mx = __longlong_as_double((long long)atomicExch(&ctl->max_bits, 0ull));
+        double mn = __longlong_as_double((long long)atomicExch(&ctl->min_bits, ~0ull));
+        if (src.tail3) { mx = fmax(mx, src.tail3[0]); mn = fmin(mn, src.tail3[1]); }
+        src.true3[0] = mx;  // the slab's true extremes; the sum follows from k_reduce_tile_sums
+        src.true3[1] = mn;
       }
     }
   }
@@ -740,6 +826,85 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     __threadfence();
     cta_scan_small(counts, fused);
   }
+}
+
+// MODE_BELIEF, second half: the slab's sum from the per-tile sums, in tile order whatever the tiles' owners were
+// (deterministic): CTA c adds tiles [4096 c, 4096 c + 4096) with a fixed tree, the last CTA adds the CTA sums in order.
+__global__ void __launch_bounds__(256) k_reduce_tile_sums(const double *__restrict__ tile_sums, unsigned ntiles, double *cta_sums,
+                                                          unsigned *done_counter, const double *tail3, double *true3) {
+  __shared__ double s_w[8];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned first = blockIdx.x * 4096u;
+  double s = 0.0;
+  for (unsigned i = first + threadIdx.x; i < first + 4096u && i < ntiles; i += 256u) s += __ldcg(tile_sums + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0) s_w[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += s_w[w];
+    cta_sums[blockIdx.x] = t;
+    __threadfence();
+    s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  double t = 0.0;
+  for (unsigned c = 0; c < gridDim.x; c++) t += __ldcg(cta_sums + c);
+  if (tail3) t += tail3[2];
+  true3[2] = t;
+  *done_counter = 0u;
+}
+
+// The BELIEF: max|x| over a sample of the slab -- one 16-byte vector of every 4 KB (0.4 % of the bytes) -- plus the
+// exact {max, min, sum} of the partial tail block, which the tile loop never sees.  belief3 = {max, max, 0}: only the
+// decade of the maximum matters (util.c:28), the true statistics replace it after the compress pass.
+constexpr unsigned SAMPLE_STRIDE_VECS = 256;  // 16-byte vectors between two samples (4 KB)
+template <typename T>
+__global__ void __launch_bounds__(256) k_sample(const T *__restrict__ in, size_t n, unsigned long long *max_bits, unsigned *done_counter,
+                                                double *belief3, double *tail3) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const size_t nfull = (n / BLK) * BLK, nvec = nfull / VEC, nsamp = (nvec + SAMPLE_STRIDE_VECS - 1) / SAMPLE_STRIDE_VECS;
+  const uint4 *p = reinterpret_cast<const uint4 *>(in);
+  T vmax = (T)0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nsamp; i0 += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const size_t i = i0 + u * stride; v[u] = i < nsamp ? __ldg(p + i * SAMPLE_STRIDE_VECS) : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const T *e = reinterpret_cast<const T *>(&v[u]);
+#pragma unroll
+      for (int q = 0; q < VEC; q++) { const T a = e[q] < (T)0 ? -e[q] : e[q]; vmax = a > vmax ? a : vmax; }
+    }
+  }
+  double m = (double)vmax;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(max_bits, (unsigned long long)__double_as_longlong(m));
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  double mx = __longlong_as_double((long long)atomicExch(max_bits, 0ull));
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  double tmax = 0.0, tmin = inf, tsum = 0.0;
+  for (size_t k = nfull; k < n; k++) {  // the partial tail block, exactly
+    const double v = (double)in[k], a = fabs(v);
+    tmax = fmax(tmax, a); tmin = fmin(tmin, a); tsum += v;
+  }
+  tail3[0] = tmax; tail3[1] = tmin; tail3[2] = tsum;
+  mx = fmax(mx, tmax);
+  if (!(mx > 0.0) || !(mx < inf)) mx = 1.0;  // a sample of zeros (or a NaN): any belief will do, the true statistics decide afterwards
+  belief3[0] = mx; belief3[1] = mx; belief3[2] = 0.0;
+  *done_counter = 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -795,22 +960,11 @@ __global__ void __launch_bounds__(32) k_tail_compress(const T *__restrict__ in /
                                                       const DevParams *params, QuantConsts<T> qc, uint8_t *bins,
                                                       float *dc_out, unsigned *counts, float *ac_slots,
                                                       T *raw_slots, uint8_t *j_slots, typename BitsOf<T>::U *qmax_bits,
-                                                      T *qtable0, Info *info, int verify, int verify_lower) {
+                                                      T *qtable0, Info *info) {
   __shared__ double xs[BLK];
   const int lane = threadIdx.x;
+  if (params->status != 0) return;  // degenerate statistics: nothing is compressed
   const T sf = (sizeof(T) == 8) ? (T)params->sf_d : (T)params->sf_f;
-  if (verify) {  // the caller's statistics are a belief: the tail's values count towards the true maximum too
-    double m = 0.0;
-    for (int n = lane; n < rem; n += 32) m = fmax(m, fabs((double)in[n]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-    if (lane == 0) {
-      const double mx = fmax(m, info->max_abs);  // the main kernel stored the maximum of the full blocks (none: the caller's)
-      if (blk_index != 0) info->max_abs = mx; else info->max_abs = m;
-      const double t = blk_index != 0 ? mx : m;
-      if (!(t < params->decade_hi) || (verify_lower && !(t >= params->decade_lo))) { info->status = -6; info->n_exact_path = 1; }
-    }
-  }
   for (int n = lane; n < rem; n += 32) {
     T v = in[n];
     if (sf != (T)1) v = v / sf;  // IEEE division (no fast-math)

@@ -50,7 +50,7 @@ extern "C" {
 #define DCTZ_GPU_EINVAL (-3)    /* bad argument (eb < 1e-6 like dctz-comp-lib.c:135, alignment, ...) */
 #define DCTZ_GPU_ENOMEM (-4)
 #define DCTZ_GPU_EDEGENERATE (-5) /* max|x| is 0, inf or NaN: the reference computes sf = 0/NaN (util.c:28) */
-#define DCTZ_GPU_ESTALE (-6)      /* compress_known_stats: the data's true max|x| gives another scaling factor */
+#define DCTZ_GPU_ESTALE (-6)      /* (no longer returned: a wrong belief about the statistics is corrected on the device) */
 #define DCTZ_GPU_ECORRUPT (-7)    /* decompress_core: bin_index marks more outliers than AC_exact holds */
 
 #define DCTZ_GPU_BLK 64    /* BLK_SZ, dctz.h:28 */
@@ -69,7 +69,8 @@ typedef struct dctz_gpu_info {
   uint64_t n_edge;     /* partial tail block only: coefficients at ordinal 255 although item <= range_max
                           (the reference indexes conv_tbl[255] out of bounds there); every path stores
                           such a coefficient as an outlier, the tail kernel also counts it */
-  uint64_t n_exact_path; /* 1 if compress_known_stats found the statistics stale (status ESTALE), else 0     */
+  uint64_t n_exact_path; /* single-read path: 1 if the belief gave the wrong scaling factor and the slab was
+                            compressed a second time, else 0                                                 */
   uint64_t n_qt_dropped; /* QT diagnostic, always 0: rescaled outliers that fell back inside the bin range
                             (dctz-comp-lib.c:494-506 would drop them; unreachable)        */
   int32_t status;      /* 0, or DCTZ_GPU_EDEGENERATE                                                */
@@ -159,15 +160,32 @@ int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t 
                           int first_slab, uint8_t *d_bin_index, float *d_DC, float *d_AC_exact,
                           void *d_qtable_raw, dctz_gpu_info *d_info, void *stream);
 
-/* Phase 2 WITHOUT phase 1: the statistics in d_stats_all are the caller's belief -- the previous time step of a
- * simulation, a sample, an analytic bound -- not a pass over this data.  Same arguments and outputs as
- * dctz_gpu_compress_dev, one read of the input instead of two.  While compressing, the kernel tracks the true
- * max|x| of the slab and verifies that it lies in the decade the scaling factor was derived from
- * (sf = 10^(ceil(log10 max)-1), util.c:28): on success d_info->max_abs is the slab's true maximum and the result is
- * exactly what phases 1+2 would have produced (d_info->sum / mean are the caller's); otherwise d_info->status =
- * DCTZ_GPU_ESTALE, the outputs are to be discarded and the caller runs dctz_gpu_stats_dev + dctz_gpu_compress_dev.
- * With several ranks only "max < upper limit" is checked per slab; that the GLOBAL maximum reaches the decade's
- * lower limit is the caller's check on the exchanged d_info->max_abs values.                            */
+/* ---- the SINGLE-READ path: the input is read once instead of twice -------------------------------------------
+ * The scaling factor only depends on the DECADE of max|x| (sf = 10^(ceil(log10 max)-1), util.c:28), and a sample of
+ * 0.4 % of a slab almost always finds it.  So: (1) sample_dev takes max|x| over one 16-byte vector of every 4 KB (and
+ * the exact statistics of a partial tail block) -> d_belief3; (2) [all-gather the beliefs of all ranks];
+ * (3) compress_spec_dev compresses with the scaling factor the beliefs give and gathers the slab's TRUE {max|x|,
+ * min|x|, sum} on the way (FP max/min per element, per-tile sums reduced in tile order: deterministic) -> d_true3;
+ * (4) [all-gather the true statistics]; (5) compress_spec_finish_dev derives the scaling factor from them: if it is the
+ * one step 3 used -- the normal case -- its gate launch leaves at once and only the outlier scan + gather run; if not,
+ * the slab is compressed again with the right factor (d_info->n_exact_path = 1).  Either way the outputs are exactly
+ * those of stats_dev + compress_dev.  Same argument meanings as dctz_gpu_compress_dev; N >= 64.  In QT mode call
+ * dctz_gpu_qt_finish_dev afterwards as usual.  dctz_gpu_compress_field_dev uses this path for whole fields
+ * (DCTZ_SINGLE_READ=0 in the environment at context creation selects the two-pass path).                      */
+int dctz_gpu_sample_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, int datatype, double *d_belief3, void *stream);
+int dctz_gpu_compress_spec_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype,
+                               double error_bound, int mode_qt, const double *d_belief_all, int nranks, int first_slab,
+                               uint8_t *d_bin_index, float *d_DC, float *d_AC_exact, void *d_qtable_raw,
+                               dctz_gpu_info *d_info, double *d_true3, void *stream);
+int dctz_gpu_compress_spec_finish_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype,
+                                      double error_bound, int mode_qt, const double *d_true_all, int nranks,
+                                      int first_slab, uint8_t *d_bin_index, float *d_DC, float *d_AC_exact,
+                                      void *d_qtable_raw, dctz_gpu_info *d_info, void *stream);
+
+/* The same with a belief supplied by the CALLER (the previous time step of a simulation, an analytic bound) instead
+ * of a sample: steps 3 + 5 for a whole field (nranks must be 1, N_total == N, N >= 64).  d_stats_all = the believed
+ * {max|x|, min|x|, sum}; only the maximum matters.  The result is always that of the two-pass path; a wrong belief
+ * costs a second compress pass (d_info->n_exact_path = 1).                                                    */
 int dctz_gpu_compress_known_stats_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t N, size_t N_total, int datatype,
                                       double error_bound, int mode_qt, const double *d_stats_all, int nranks,
                                       int first_slab, uint8_t *d_bin_index, float *d_DC, float *d_AC_exact,

@@ -287,9 +287,10 @@ def test_more_elements_than_int32(ctx):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_compress_with_known_statistics_is_verified(ctx, dtype):
-    """dctz_gpu_compress_known_stats_dev: one read of the input, scaling factor from the caller's statistics (here:
-    the previous 'time step'), verified against the true max|x| while compressing."""
+def test_compress_with_known_statistics_is_corrected_on_the_device(ctx, dtype):
+    """dctz_gpu_compress_known_stats_dev: one read of the input, scaling factor from the caller's belief (here: the
+    previous 'time step'); the true statistics are gathered while compressing and a wrong belief costs a second
+    compress pass on the device -- the result is always the two-pass one."""
     code = DOUBLE if dtype == np.float64 else FLOAT
     s = torch.cuda.current_stream().cuda_stream
     x_prev = (fields.small_cases(dtype)["tail32"]).astype(dtype)            # max ~ 7.03 -> sf = 1
@@ -298,35 +299,120 @@ def test_compress_with_known_statistics_is_verified(ctx, dtype):
     stats = torch.zeros(3, dtype=torch.float64, device="cuda")
     ctx.stats_dev(d_prev.data_ptr(), n, code, stats.data_ptr(), s)
 
-    def run(x, n_total=None):
+    def run(x):
         d = _dev(x)
         o = dict(bins=torch.empty(n, dtype=torch.uint8, device="cuda"), dc=torch.empty((n + 63) // 64, dtype=torch.float32, device="cuda"),
                  ac=torch.empty(n, dtype=torch.float32, device="cuda"), info=torch.zeros(binding.INFO_BYTES, dtype=torch.uint8, device="cuda"))
-        ctx.compress_known_stats_dev(d.data_ptr(), n, n_total or n, code, 1e-3, False, stats.data_ptr(), 1, True, o["bins"].data_ptr(),
+        ctx.compress_known_stats_dev(d.data_ptr(), n, n, code, 1e-3, False, stats.data_ptr(), 1, True, o["bins"].data_ptr(),
                                      o["dc"].data_ptr(), o["ac"].data_ptr(), 0, o["info"].data_ptr(), s)
         torch.cuda.synchronize()
         o["i"] = _info(o["info"])
         return o
 
-    # (a) the next time step stays in the same decade: verified, and bit-identical to the two-pass result
+    def same_as_two_pass(o, x, redone):
+        want = ctx.compress_core(x, 1e-3)
+        i = o["i"]
+        assert i["status"] == 0 and i["n_exact_path"] == redone and i["sf"] == want["sf"], (i, want["sf"])
+        assert i["max_abs"] == float(np.max(np.abs(x))) and i["min_abs"] == float(np.min(np.abs(x)))  # the TRUE extremes, not the caller's
+        assert abs(i["sum"] - want["info"]["sum"]) <= 1e-9 * float(np.sum(np.abs(x.astype(np.float64)))) * (1 if dtype == np.float64 else 1e4)
+        k = i["n_outliers"]
+        assert np.array_equal(o["bins"].cpu().numpy(), want["bin_index"]) and np.array_equal(o["dc"].cpu().numpy(), want["dc"])
+        assert k == want["ac"].size and np.array_equal(o["ac"][:k].cpu().numpy(), want["ac"])
+
+    # (a) the next time step stays in the same decade: one pass, bit-identical to the two-pass result
     x_next = (x_prev * dtype(1.01)).astype(dtype)
-    o = run(x_next)
-    want = ctx.compress_core(x_next, 1e-3)
-    assert o["i"]["status"] == 0 and o["i"]["n_exact_path"] == 0 and o["i"]["sf"] == want["sf"]
-    assert o["i"]["max_abs"] == float(np.max(np.abs(x_next)))  # the TRUE maximum, not the caller's
-    k = o["i"]["n_outliers"]
-    assert np.array_equal(o["bins"].cpu().numpy(), want["bin_index"]) and np.array_equal(o["dc"].cpu().numpy(), want["dc"])
-    assert k == want["ac"].size and np.array_equal(o["ac"][:k].cpu().numpy(), want["ac"])
-    # (b) the field grew into the next decade: flagged
-    assert run((x_prev * dtype(20.0)).astype(dtype))["i"]["status"] == -6
-    # (c) it shrank below the decade: flagged for a whole field, left to the caller for a slab of a larger field
-    small = (x_prev * dtype(0.05)).astype(dtype)
-    assert run(small)["i"]["status"] == -6
-    assert run(small, n_total=4 * n)["i"]["status"] == 0
+    same_as_two_pass(run(x_next), x_next, 0)
+    # (b) the field grew into the next decade / (c) shrank below it: corrected by a second pass, same result
+    for factor in (20.0, 0.05):
+        xx = (x_prev * dtype(factor)).astype(dtype)
+        same_as_two_pass(run(xx), xx, 1)
     # (d) the maximum sits in the partial tail block only
     spike = x_next.copy()
     spike[-3] = dtype(55.0)
-    assert run(spike)["i"]["status"] == -6
+    same_as_two_pass(run(spike), spike, 1)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("qt", [False, True])
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_single_read_path_equals_two_pass(ctx, dtype, qt, world):
+    """sample -> [exchange] -> compress_spec -> [exchange] -> compress_spec_finish over 1..3 slabs (one context per
+    emulated rank) against stats -> compress of the whole field: same bytes, same statistics.  Fields: one whose
+    maximum every sample finds, one whose maximum is a single spike between the sample points of slab 1 (the belief is
+    a decade too low: every slab is compressed twice), one of zeros with one value (the belief degenerates)."""
+    import dctz_b200
+
+    code = DOUBLE if dtype == np.float64 else FLOAT
+    tdt = torch.float64 if code == DOUBLE else torch.float32
+    s = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(5)
+    n = 64 * 32 * 90 + 64 * 5 + 19
+    base = (3.0 + np.sin(np.arange(n) / 41.0) * 2.0 + 0.02 * rng.standard_normal(n))
+    spike = base.copy()
+    spike[n // 2 + 777] = 83.0          # not on a sampled vector (the samples are 16 bytes every 4 KB)
+    lonely = np.zeros(n)
+    lonely[12345] = -37.0
+    ranks = [dctz_b200.Context(0) for _ in range(world)]
+    try:
+        for name, field, redone in (("plain", base, 0), ("spike", spike, 1), ("lonely", lonely, 1)):
+            x = field.astype(dtype)
+            # reference: the two-pass device path on the whole field
+            ref = _two_pass(ctx, x, code, tdt, 1e-3, qt, s)
+            parts = slabs.partition(n, world)
+            xs = [_dev(x[a:a + c]) for a, c in parts]
+            belief_all = torch.zeros(3 * world, dtype=torch.float64, device="cuda")
+            true_all = torch.zeros(3 * world, dtype=torch.float64, device="cuda")
+            outs = []
+            for r, (a, c) in enumerate(parts):
+                ranks[r].sample_dev(xs[r].data_ptr(), c, code, belief_all[3 * r:].data_ptr(), s)
+            for r, (a, c) in enumerate(parts):
+                o = dict(bins=torch.empty(c, dtype=torch.uint8, device="cuda"), dc=torch.empty((c + 63) // 64, dtype=torch.float32, device="cuda"),
+                         ac=torch.empty(c, dtype=torch.float32, device="cuda"), qraw=torch.zeros(64, dtype=tdt, device="cuda"),
+                         qt=torch.zeros(64, dtype=tdt, device="cuda"), info=torch.zeros(binding.INFO_BYTES, dtype=torch.uint8, device="cuda"))
+                ranks[r].compress_spec_dev(xs[r].data_ptr(), c, n, code, 1e-3, qt, belief_all.data_ptr(), world, r == 0, o["bins"].data_ptr(), o["dc"].data_ptr(),
+                                           o["ac"].data_ptr(), o["qraw"].data_ptr(), o["info"].data_ptr(), true_all[3 * r:].data_ptr(), s)
+                outs.append(o)
+            for r, (a, c) in enumerate(parts):
+                o = outs[r]
+                ranks[r].compress_spec_finish_dev(xs[r].data_ptr(), c, n, code, 1e-3, qt, true_all.data_ptr(), world, r == 0, o["bins"].data_ptr(),
+                                                  o["dc"].data_ptr(), o["ac"].data_ptr(), o["qraw"].data_ptr(), o["info"].data_ptr(), s)
+            if qt:
+                g = torch.stack([o["qraw"] for o in outs]).max(dim=0).values
+                g[0] = outs[-1]["qraw"][0]
+                for r, o in enumerate(outs):
+                    o["qraw"].copy_(g)
+                    ranks[r].qt_finish_dev(code, 1e-3, o["qraw"].data_ptr(), o["qt"].data_ptr(), o["ac"].data_ptr(), o["info"].data_ptr(), s)
+            torch.cuda.synchronize()
+            infos = [_info(o["info"]) for o in outs]
+            assert all(i["status"] == 0 and i["sf"] == ref["i"]["sf"] and i["n_exact_path"] == redone for i in infos), (name, infos, ref["i"])
+            assert all(i["max_abs"] == ref["i"]["max_abs"] and i["min_abs"] == ref["i"]["min_abs"] for i in infos), (name, infos[0], ref["i"])
+            assert abs(infos[0]["sum"] - ref["i"]["sum"]) <= 1e-9 * max(1.0, float(np.sum(np.abs(x.astype(np.float64))))) * (1 if dtype == np.float64 else 1e4)
+            bins = np.concatenate([o["bins"].cpu().numpy() for o in outs])
+            dc = np.concatenate([o["dc"].cpu().numpy() for o in outs])
+            ac = np.concatenate([o["ac"][: i["n_outliers"]].cpu().numpy() for o, i in zip(outs, infos)])
+            assert np.array_equal(bins, ref["bins"]) and np.array_equal(dc, ref["dc"]) and np.array_equal(ac, ref["ac"]), name
+            if qt:
+                assert all(np.array_equal(o["qt"].cpu().numpy(), ref["qt"]) for o in outs), name
+    finally:
+        for rk in ranks:
+            rk.close()
+
+
+def _two_pass(ctx, x, code, tdt, eb, qt, s):
+    n = x.size
+    d = _dev(x)
+    st = torch.zeros(3, dtype=torch.float64, device="cuda")
+    o = dict(bins=torch.empty(n, dtype=torch.uint8, device="cuda"), dc=torch.empty((n + 63) // 64, dtype=torch.float32, device="cuda"),
+             ac=torch.empty(n, dtype=torch.float32, device="cuda"), qraw=torch.zeros(64, dtype=tdt, device="cuda"), qt=torch.zeros(64, dtype=tdt, device="cuda"),
+             info=torch.zeros(binding.INFO_BYTES, dtype=torch.uint8, device="cuda"))
+    ctx.stats_dev(d.data_ptr(), n, code, st.data_ptr(), s)
+    ctx.compress_dev(d.data_ptr(), n, n, code, eb, qt, st.data_ptr(), 1, True, o["bins"].data_ptr(), o["dc"].data_ptr(), o["ac"].data_ptr(), o["qraw"].data_ptr(),
+                     o["info"].data_ptr(), s)
+    if qt:
+        ctx.qt_finish_dev(code, eb, o["qraw"].data_ptr(), o["qt"].data_ptr(), o["ac"].data_ptr(), o["info"].data_ptr(), s)
+    torch.cuda.synchronize()
+    i = _info(o["info"])
+    return dict(i=i, bins=o["bins"].cpu().numpy(), dc=o["dc"].cpu().numpy(), ac=o["ac"][: i["n_outliers"]].cpu().numpy(), qt=o["qt"].cpu().numpy())
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])

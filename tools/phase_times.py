@@ -44,7 +44,7 @@ for name, make, code, qt, eb in (("c1", lambda: fields.cesm_like(), DOUBLE, Fals
         pd = ctx.fused_phase_times(1)
         rows.append((pc, pd))
     pc, pd = rows[-1]
-    print(name, "compress stamps (earliest, latest CTA) us:", [(round(a, 1), round(b, 1)) for a, b in pc])
+    print(name, "compress stamps [start, sampled, past barrier 1, compressed, past barrier 2, end] (earliest, latest CTA) us:", [(round(a, 1), round(b, 1)) for a, b in pc])
     print(name, "decompress stamps us:", [(round(a, 1), round(b, 1)) for a, b in pd])
     out[name] = dict(compress=pc, decompress=pd)
 json.dump(out, open("gpurun_out/phase_times.json", "w"))
