@@ -359,8 +359,8 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   CU(cudaMemset(ctx->d_done, 0, 8 * sizeof(unsigned)));
   CU(cudaMalloc(&ctx->d_tail3, 3 * sizeof(double)));
   CU(cudaMalloc(&ctx->d_spec3, 6 * sizeof(double)));
-  CU(cudaMalloc(&ctx->d_sample_bits, sizeof(unsigned long long)));
-  CU(cudaMemset(ctx->d_sample_bits, 0, sizeof(unsigned long long)));
+  CU(cudaMalloc(&ctx->d_sample_bits, 4 * sizeof(unsigned long long)));  // [0] k_sample's running maximum, [1] extreme high words, [2..3] exact extremes
+  CU(cudaMemset(ctx->d_sample_bits, 0, 4 * sizeof(unsigned long long)));
   CU(cudaMalloc(&ctx->d_stats3, 3 * sizeof(double)));
   CU(cudaMalloc(&ctx->d_params, sizeof(DevParams)));
   CU(cudaMalloc(&ctx->d_info, sizeof(Info)));
@@ -629,10 +629,12 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
   src.tb.qmax_words = (int)(BLK * sizeof(T) / 8);
   src.params = ctx->d_params;
   src.qmax_zero = QT ? (unsigned long long *)d_qtable_raw : nullptr;
-  src.tile_sums = nullptr; src.true3 = sa.d_true3; src.tail3 = rem ? ctx->d_tail3 : nullptr;
-  if (sa.mode == MODE_BELIEF) {
-    TRY(grow(ctx, ctx->tile_sums, (ntiles + (ntiles + 4095) / 4096 + 8) * sizeof(double)));
+  src.tile_sums = nullptr; src.tile_ext = nullptr;
+  const size_t nred = (ntiles + 4095) / 4096;  // CTAs of k_reduce_tiles
+  if (sa.mode == MODE_BELIEF) {  // scratch: [tile sums][CTA sums][tile extremes][CTA extremes]
+    TRY(grow(ctx, ctx->tile_sums, (ntiles + nred + 8) * sizeof(double) + (ntiles + nred + 8) * sizeof(uint2)));
     src.tile_sums = (double *)ctx->tile_sums.p;
+    src.tile_ext = (uint2 *)((double *)ctx->tile_sums.p + ntiles + nred + 8);
   }
   if (nblk_full) {
     const size_t resident = (size_t)ctx->sm_count * ctx->occ[0][sizeof(T) == 8][QT];
@@ -653,11 +655,22 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
                                                                       (T *)d_qtable_raw, &ctx->d_ctl[0], d_info, fused, batch);
     ctx->launches++;
     CU(cudaGetLastError());
-    if (sa.mode == MODE_BELIEF) {
-      double *cta_sums = (double *)ctx->tile_sums.p + ntiles;
-      k_reduce_tile_sums<<<(unsigned)((ntiles + 4095) / 4096), 256, 0, st>>>((const double *)ctx->tile_sums.p, (unsigned)ntiles, cta_sums, ctx->d_done + 6,
-                                                                            rem ? ctx->d_tail3 : nullptr, sa.d_true3);
+    if (sa.mode == MODE_BELIEF) {  // the slab's true statistics from the per-tile records
+      TileReduce tr;
+      tr.cta_sums = src.tile_sums + ntiles;
+      tr.cta_ext = src.tile_ext + ntiles;
+      tr.done = ctx->d_done + 6;
+      tr.hw = (unsigned *)(ctx->d_sample_bits + 1);
+      tr.ext_bits = ctx->d_sample_bits + 2;
+      const double *tail3 = rem ? ctx->d_tail3 : nullptr;
+      k_reduce_tiles<T><<<(unsigned)nred, 256, 0, st>>>(src.tile_sums, src.tile_ext, (unsigned)ntiles, tr, tail3, sa.d_true3);
       ctx->launches++;
+      if (sizeof(T) == 8) {
+        const size_t want = (ntiles + 7) / 8;
+        const int gr = (int)(want < (size_t)ctx->sm_count * 8 ? want : (size_t)ctx->sm_count * 8);
+        k_resolve_extremes<<<gr, 256, 0, st>>>((const double *)d_in, nblk_full, src.tile_ext, (unsigned)ntiles, tr, ctx->d_done + 7, tail3, sa.d_true3);
+        ctx->launches++;
+      }
       CU(cudaGetLastError());
       return DCTZ_GPU_OK;
     }
@@ -735,10 +748,15 @@ extern "C" int dctz_gpu_compress_dev(dctz_gpu_ctx *ctx, const void *d_in, size_t
 
 // ---- the single-read path: belief (sample) -> compress while gathering the true statistics -> verdict / redo ----
 template <typename T> static int launch_sample(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double *d_belief3, cudaStream_t st) {
-  const size_t nsamp = (N * sizeof(T) / 16 + SAMPLE_STRIDE_VECS - 1) / SAMPLE_STRIDE_VECS;
+  // one 16-byte vector of every 4 KB; large slabs: about 256 K samples in all (scattered 32-byte reads cost DRAM far more than
+  // their bytes, and the decade of the maximum is found long before that)
+  const size_t nvec = N * sizeof(T) / 16;
+  size_t stride = nvec >> 18;
+  if (stride < SAMPLE_STRIDE_VECS) stride = SAMPLE_STRIDE_VECS;
+  const size_t nsamp = (nvec + stride - 1) / stride;
   const size_t want = (nsamp + 256 * 4 - 1) / (256 * 4);
   const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? (want ? want : 1) : (size_t)ctx->sm_count * 8);
-  k_sample<T><<<grid, 256, 0, st>>>(d_in, N, ctx->d_sample_bits, ctx->d_done + 5, d_belief3, ctx->d_tail3);
+  k_sample<T><<<grid, 256, 0, st>>>(d_in, N, stride, ctx->d_sample_bits, ctx->d_done + 5, d_belief3, ctx->d_tail3);
   ctx->launches++;
   CU(cudaGetLastError());
   return DCTZ_GPU_OK;

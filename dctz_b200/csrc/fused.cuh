@@ -253,7 +253,7 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
     RangeSeq seq;
     seq.init_down(t0, t1, warp, Cfg::WARPS);
     VerifyStat<T> vs;
-    vs.slot = nullptr; vs.tile_sums = nullptr;
+    vs.tile_sums = nullptr; vs.tile_ext = nullptr;
     compress_tiles<T, QT, false>(&tmap_in, nblk_full, &s_params, qc, bins, dc_out, counts, ac_slots, raw_slots, j_slots, qtable_raw, wsm, mb, seq,
                                  lane, vs, phase);
   }

@@ -445,6 +445,30 @@ size_t dctz_host_deflate_streamed(const void *src, size_t n, void *dst, size_t c
   return out;
 }
 
+static double wall(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+static int env_on(const char *name) {
+  const char *e = getenv(name);
+  return e && *e && *e != '0';
+}
+
+typedef struct {
+  const void *qtable_raw, *bin_index, *ac;
+  size_t qbytes, n, ac_bytes;
+} dump_job;
+
+static void *dump_worker(void *arg) {
+  dump_job *d = (dump_job *)arg;
+  if (d->qtable_raw) dump("qtable.bin", d->qtable_raw, d->qbytes);
+  dump("bin_index.bin", d->bin_index, d->n);
+  dump("AC_exact.bin", d->ac, d->ac_bytes);
+  return NULL;
+}
+
 /* ---- stream assembly (dctz-comp-lib.c:583-846): side files, three deflates, header, concatenation ---- */
 static size_t assemble_stream(t_datatype dt, size_t n, double error_bound, const dctz_gpu_info *info, const t_bin_id *bin_index,
                               const float *DC, const float *AC_exact, const void *qtable, const void *qtable_raw, unsigned char *out,
@@ -456,11 +480,18 @@ static size_t assemble_stream(t_datatype dt, size_t n, double error_bound, const
   struct header h;
   size_t total;
   int i;
+  dump_job dj;
+  pthread_t dump_th;
+  int dumping = 0;
+  double t_a = wall(), t_b;
   if (info->n_outliers > 0xFFFFFFFFull) die("too many outliers for the stream header", NULL);
-  if (write_dumps && dumps_enabled()) { /* dctz-comp-lib.c:443-448, 583-595: side files the reference's scripts rename */
-    if (MODE_QT) dump("qtable.bin", qtable_raw, qbytes);
-    dump("bin_index.bin", bin_index, n);
-    dump("AC_exact.bin", AC_exact, (size_t)info->n_outliers * sizeof(float));
+  if (write_dumps && dumps_enabled()) { /* dctz-comp-lib.c:443-448, 583-595: side files the reference's scripts rename;
+                                           written by their own thread while the sections are deflated */
+    dj.qtable_raw = MODE_QT ? qtable_raw : NULL; dj.qbytes = qbytes;
+    dj.bin_index = bin_index; dj.n = n;
+    dj.ac = AC_exact; dj.ac_bytes = (size_t)info->n_outliers * sizeof(float);
+    dumping = !pthread_create(&dump_th, NULL, dump_worker, &dj);
+    if (!dumping) dump_worker(&dj);
   }
   memset(jobs, 0, sizeof jobs);
   jobs[0].src = bin_index; jobs[0].n_src = n;
@@ -491,21 +522,13 @@ static size_t assemble_stream(t_datatype dt, size_t n, double error_bound, const
     free(jobs[i].dst);
   }
   if (MODE_QT) memcpy(out, qtable, qbytes);
+  t_b = wall();
+  if (dumping) pthread_join(dump_th, NULL);
+  if (env_on("DCTZ_PROFILE")) fprintf(stderr, "dctz profile: deflate+assemble %.1f ms, waiting for the side files %.1f ms\n", 1e3 * (t_b - t_a), 1e3 * (wall() - t_b));
   return total;
 }
 
 /* ---- dctz_compress (dctz.h:126) ------------------------------------------------------------------ */
-static double wall(void) {
-  struct timespec t;
-  clock_gettime(CLOCK_MONOTONIC, &t);
-  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
-}
-
-static int env_on(const char *name) {
-  const char *e = getenv(name);
-  return e && *e && *e != '0';
-}
-
 typedef struct {
   zpipe *zp;
   const void *base[3];
@@ -575,6 +598,11 @@ int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error
   }
   if (rc != DCTZ_GPU_OK) die("GPU compress failed", dctz_gpu_last_error(g_ctx));
   t1 = wall();
+  if (env_on("DCTZ_PROFILE")) {
+    double ms[8];
+    dctz_gpu_last_call_stats(g_ctx, ms, NULL, NULL);
+    fprintf(stderr, "dctz profile: GPU call %.1f ms (upload + kernels %.1f ms, downloads + host scaling %.1f ms)\n", 1e3 * (t1 - t0), ms[3], ms[4]);
+  }
   if (env_on("DCTZ_DCT_FILE_DEBUG") && dumps_enabled()) dump_coefficients(var, n, DC, nblk);
   *outSize = assemble_stream(var->datatype, n, error_bound, &info, bin_index, DC, AC_exact, qtable, qtable_raw,
                              is_double ? (unsigned char *)var_z->buf.d : (unsigned char *)var_z->buf.f, 1, timing ? NULL : &zp);

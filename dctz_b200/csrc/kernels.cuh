@@ -222,6 +222,37 @@ template <typename T> __device__ __forceinline__ int sf_index(T mx, const T *thr
   while (lo > 0 && mx < thr[lo - 1]) lo--;
   return lo;
 }
+// The same index, its sf and the decade limits thr[idx-1], thr[idx] with ALL table loads issued at once: the guess from
+// the binary exponent is off by at most one, so the answer lies in a window of four entries -- one memory latency
+// instead of a chain of four (this runs on one thread in the prologue of every compress CTA).
+template <typename T> struct SfHit { int idx; T sf, lo, hi; };
+template <typename T> __device__ __forceinline__ SfHit<T> sf_window(T mx, const T *__restrict__ thr, const T *__restrict__ sfv, int n, int kmin, int e2) {
+  int g = (int)floorf((float)e2 * 0.30103f) - kmin;  // candidate index (smallest i with mx < thr[i]) is within g-1 .. g+1
+  g = g < 1 ? 1 : (g > n - 2 ? n - 2 : g);
+  T t[4], v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {  // thr[g-2 .. g+1] (guards at the table ends), sf[g-1 .. g+2]
+    const int i = g - 2 + k;
+    t[k] = (i >= 0 && i < n) ? __ldg(thr + i) : (i < 0 ? (T)0 : (T)__int_as_float(0x7F800000));
+    const int j = g - 1 + k;
+    v[k] = __ldg(sfv + (j < 0 ? 0 : (j > n ? n : j)));
+  }
+  SfHit<T> h;
+  if (mx < t[0] || !(mx < t[3])) {  // (never for a consistent table: fall back to the search)
+    h.idx = sf_index<T>(mx, thr, n, kmin, e2);
+    h.sf = sfv[h.idx];
+    h.lo = h.idx > 0 ? thr[h.idx - 1] : (T)0;
+    h.hi = h.idx < n ? thr[h.idx] : (T)0;
+    return h;
+  }
+  // smallest i in {g-1, g, g+1} with mx < thr[i]  (thr[g-2] <= mx < thr[g+1] here)
+  const int step = (mx < t[1]) ? 0 : ((mx < t[2]) ? 1 : 2);
+  h.idx = g - 1 + step;
+  h.sf = v[step];
+  h.lo = t[step];
+  h.hi = t[step + 1];
+  return h;
+}
 __device__ __forceinline__ double sf_lookup_d(double mx, const SfTables &tb) {
   return tb.sf_d[sf_index<double>(mx, tb.thr_d, tb.n_d, tb.kmin_d, ilogb(mx))];
 }
@@ -249,10 +280,10 @@ __device__ __forceinline__ void finalize_params(const double *stats_all, int nra
   p->decade_hi = __longlong_as_double(0x7FF0000000000000ll);
   if (is_double) {
     if (!status) {
-      const int idx = sf_index<double>(mx, tb.thr_d, tb.n_d, tb.kmin_d, ilogb(mx));
-      sf = tb.sf_d[idx];
-      p->decade_lo = idx > 0 ? tb.thr_d[idx - 1] : tb.min_d;
-      if (idx < tb.n_d) p->decade_hi = tb.thr_d[idx];
+      SfHit<double> h = sf_window<double>(mx, tb.thr_d, tb.sf_d, tb.n_d, tb.kmin_d, ilogb(mx));
+      sf = h.sf;
+      p->decade_lo = h.idx > 0 ? h.lo : tb.min_d;
+      if (h.idx < tb.n_d) p->decade_hi = h.hi;
     }
     mean = sum / (double)(long long)n_total;
     const Divisor<double> d = make_divisor(sf);
@@ -261,10 +292,10 @@ __device__ __forceinline__ void finalize_params(const double *stats_all, int nra
   } else {
     float sff = 1.0f;
     if (!status) {
-      const int idx = sf_index<float>((float)mx, tb.thr_f, tb.n_f, tb.kmin_f, ilogbf((float)mx));
-      sff = tb.sf_f[idx];
-      p->decade_lo = (double)(idx > 0 ? tb.thr_f[idx - 1] : tb.min_f);
-      if (idx < tb.n_f) p->decade_hi = (double)tb.thr_f[idx];
+      SfHit<float> h = sf_window<float>((float)mx, tb.thr_f, tb.sf_f, tb.n_f, tb.kmin_f, ilogbf((float)mx));
+      sff = h.sf;
+      p->decade_lo = (double)(h.idx > 0 ? h.lo : tb.min_f);
+      if (h.idx < tb.n_f) p->decade_hi = (double)h.hi;
     }
     sf = (double)sff;
     mean = (double)((float)sum / (float)(long long)n_total);
@@ -510,8 +541,8 @@ __device__ __forceinline__ float fmin_t(float a, float b) { return fminf(a, b); 
 
 // VERIFY: what a thread has seen of the slab's true statistics while compressing with a BELIEF about them.
 template <typename T> struct VerifyStat {
-  T *slot;             // this thread's {max, min} of |x| over its blocks so far, in SHARED memory (the tile loop has no register to spare)
-  double *tile_sums;   // per-tile sum of x (global scratch), reduced in tile order afterwards: deterministic
+  double *tile_sums;  // per-tile sum of x, reduced in tile order afterwards: deterministic
+  uint2 *tile_ext;    // per-tile {max, min} of the HIGH 32 bits of |x| (float: of all its bits, i.e. exact)
 };
 
 // The tile loop of the compress kernels: one warp, tiles handed out by `seq` (TileSeq: dynamic tickets; RangeSeq: the
@@ -551,6 +582,35 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
   while (cur < ntiles) {
     mbar_wait(mb, phase);
     phase ^= 1u;
+    if constexpr (VERIFY) {
+      // The statistics pass folded into this one (util.c:12-44).  max|x| / min|x| are taken on the HIGH WORD of the bit
+      // pattern (one integer max and min per element; for float that is the value, for double k_resolve_extremes settles
+      // the low words of the few candidates afterwards) -- in a pass of its own over the tile in shared memory, BEFORE the
+      // 64 values occupy the registers (folded into the load below it spilled).  The SUM is not taken here at all: it is
+      // 8 x the block's DC coefficient, which the transform delivers anyway.
+      unsigned hx2[2] = {0u, 0u}, hn2[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+      const unsigned long long left = nblk_full - (unsigned long long)cur * WTILE;
+      if ((unsigned long long)lane < left) {  // rows beyond the field arrive zero-filled: they must not lower the minimum
+#pragma unroll
+        for (int q = 0; q < L::SLABS; q++) {
+#pragma unroll
+          for (int c = 0; c < 8; c++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(wsm + L::chunk_offset(q, lane, c));
+            if constexpr (sizeof(T) == 8) {
+              const unsigned h0 = v.y & 0x7FFFFFFFu, h1 = v.w & 0x7FFFFFFFu;
+              hx2[c & 1] = max(hx2[c & 1], max(h0, h1));
+              hn2[c & 1] = min(hn2[c & 1], min(h0, h1));
+            } else {
+              const unsigned h0 = v.x & 0x7FFFFFFFu, h1 = v.y & 0x7FFFFFFFu, h2 = v.z & 0x7FFFFFFFu, h3 = v.w & 0x7FFFFFFFu;
+              hx2[c & 1] = max(hx2[c & 1], max(max(h0, h1), max(h2, h3)));
+              hn2[c & 1] = min(hn2[c & 1], min(min(h0, h1), min(h2, h3)));
+            }
+          }
+        }
+      }
+      const unsigned hmax = __reduce_max_sync(FULL, max(hx2[0], hx2[1])), hmin = __reduce_min_sync(FULL, min(hn2[0], hn2[1]));
+      if (lane == 0) vstat.tile_ext[cur] = make_uint2(hmax, hmin);
+    }
     T x[BLK];
     unsigned probe = 0;
 #pragma unroll
@@ -572,28 +632,15 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
     const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
     const bool active = (unsigned)lane < rows;
     // (rows beyond the field arrive zero-filled: they quantise to bin 0 and are never stored)
-    if constexpr (VERIFY) {
-      // the statistics pass folded into this one (util.c:12-44): max|x|, min|x| as FP max/min (one instruction per
-      // element; a NaN/inf shows in the sum), the tile's sum reduced over the warp in a fixed order -> deterministic
-      T bs = (T)0, bmax = (T)0, bmin = fabs_t(x[0]);
-#pragma unroll
-      for (int j = 0; j < BLK; j++) {  // one min/max instruction with an |x| operand each
-        bmax = fmax_t(bmax, fabs_t(x[j]));
-        bmin = fmin_t(bmin, fabs_t(x[j]));
-        bs += x[j];
-      }
-      if (active) {  // (rows beyond the field arrive zero-filled: they must not lower the minimum)
-        vstat.slot[0] = fmax_t(vstat.slot[0], bmax);
-        vstat.slot[1] = fmin_t(vstat.slot[1], bmin);
-      }
-      double ts = active ? (double)bs : 0.0;
+
+    // ---- orthonormal DCT-II (dct.c:55-103) of the unscaled block; x / sf is folded into the quantiser ----
+    dct64_forward<A>(x);
+    if constexpr (VERIFY) {  // sum of the block = sqrt(64) x its DC coefficient (orthonormal DCT-II); reduced over the warp in a fixed order
+      double ts = active ? 8.0 * (double)x[0] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(FULL, ts, o);
       if (lane == 0) vstat.tile_sums[cur] = ts;
     }
-
-    // ---- orthonormal DCT-II (dct.c:55-103) of the unscaled block; x / sf is folded into the quantiser ----
-    dct64_forward<A>(x);
 
     // ---- quantise (dctz-comp-lib.c:350-414); the ids go straight to the warp's bin-id buffer in shared
     //      memory (four at a time), which keeps 16 registers free and is where the bulk store reads them ----
@@ -720,8 +767,7 @@ struct StatSource {
   DevParams *params;            // published by CTA 0 (the tail kernel and the QT gather read it)
   unsigned long long *qmax_zero;  // QT: the per-position maxima to clear
   double *tile_sums;            // MODE_BELIEF: per-tile sums
-  double *true3;                // MODE_BELIEF: {max, min, -} of this slab's full blocks, merged with tail3 (the sum is added by k_reduce_tile_sums)
-  const double *tail3;          // MODE_BELIEF: exact {max, min, sum} of the partial tail block (from k_sample), or NULL
+  uint2 *tile_ext;              // MODE_BELIEF: per-tile extremes of the high word of |x|
 };
 
 template <typename T, bool QT, bool VERIFY>
@@ -734,8 +780,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
            T *qtable0,                                        // QT: entry 0 of the table: the last full block's DC
            TileControl *ctl, Info *info, FusedScan fused, unsigned batch) {
   typedef CompressCfg<T, QT> Cfg;
-  typedef typename BitsOf<T>::U U;
-  constexpr unsigned FULL = 0xFFFFFFFFu;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
   __shared__ DevParams s_params;
@@ -769,14 +813,9 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
   __syncthreads();  // the only CTA-wide barrier before the epilogue
   if (s_skip) return;
 
-  __shared__ T s_vstat[VERIFY ? 2 * Cfg::THREADS : 2];
   VerifyStat<T> vstat;
-  vstat.slot = &s_vstat[VERIFY ? 2 * threadIdx.x : 0];
-  if (VERIFY) {
-    vstat.slot[0] = (T)0;
-    vstat.slot[1] = sizeof(T) == 8 ? (T)__longlong_as_double(0x7FF0000000000000ll) : (T)__int_as_float(0x7F800000);
-  }
   vstat.tile_sums = src.tile_sums;
+  vstat.tile_ext = src.tile_ext;
   unsigned phase = 0;
   TileSeq seq;
   seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
@@ -787,22 +826,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
   bulk_wait_all();
   __syncthreads();
   __shared__ bool s_last;
-  if constexpr (VERIFY) {
-    U bmax = BitsOf<T>::abs_bits(vstat.slot[0]), bmin = BitsOf<T>::abs_bits(vstat.slot[1]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const U m1 = __shfl_xor_sync(FULL, bmax, o), m2 = __shfl_xor_sync(FULL, bmin, o);
-      bmax = m1 > bmax ? m1 : bmax;
-      bmin = m2 < bmin ? m2 : bmin;
-    }
-    if (lane == 0) {
-      // widened to the double's bit pattern so that slabs of either type share the two 64-bit words
-      const double dmax = (double)(sizeof(T) == 8 ? __longlong_as_double((long long)(unsigned long long)bmax) : (double)__int_as_float((int)(unsigned)bmax));
-      const double dmin = (double)(sizeof(T) == 8 ? __longlong_as_double((long long)(unsigned long long)bmin) : (double)__int_as_float((int)(unsigned)bmin));
-      atomicMax(&ctl->max_bits, (unsigned long long)__double_as_longlong(dmax));
-      atomicMin(&ctl->min_bits, (unsigned long long)__double_as_longlong(dmin));
-    }
-  }
   __threadfence();  // this thread's counts are visible device-wide before the CTA signs off
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -811,14 +834,6 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
     if (s_last) {
       ctl->ticket = 0u;
       ctl->done = 0u;
-      if constexpr (VERIFY) {
-        __threadfence();
-        double mx = __longlong_as_double((long long)atomicExch(&ctl->max_bits, 0ull));
-        double mn = __longlong_as_double((long long)atomicExch(&ctl->min_bits, ~0ull));
-        if (src.tail3) { mx = fmax(mx, src.tail3[0]); mn = fmin(mn, src.tail3[1]); }
-        src.true3[0] = mx;  // the slab's true extremes; the sum follows from k_reduce_tile_sums
-        src.true3[1] = mn;
-      }
     }
   }
   __syncthreads();
@@ -829,52 +844,133 @@ k_compress(const __grid_constant__ CUtensorMap tmap_in, unsigned long long nblk_
 }
 
 // MODE_BELIEF, second half: the slab's sum from the per-tile sums, in tile order whatever the tiles' owners were
-// (deterministic): CTA c adds tiles [4096 c, 4096 c + 4096) with a fixed tree, the last CTA adds the CTA sums in order.
-__global__ void __launch_bounds__(256) k_reduce_tile_sums(const double *__restrict__ tile_sums, unsigned ntiles, double *cta_sums,
-                                                          unsigned *done_counter, const double *tail3, double *true3) {
+// (deterministic): CTA c adds tiles [4096 c, 4096 c + 4096) with a fixed tree, the last CTA adds the CTA sums in order --
+// and the slab's extreme high words.  spec[0] = max high word, spec[1] = min high word; true3[2] = the sum (+ the tail's).
+// For float the high word is the value: true3[0..1] are final here.  For double k_resolve_extremes settles the low words.
+struct TileReduce { double *cta_sums; uint2 *cta_ext; unsigned *done; unsigned *hw; /* [2] */ unsigned long long *ext_bits; /* [2] exact |x| patterns */ };
+template <typename T>
+__global__ void __launch_bounds__(256) k_reduce_tiles(const double *__restrict__ tile_sums, const uint2 *__restrict__ tile_ext, unsigned ntiles, TileReduce r,
+                                                      const double *tail3, double *true3) {
   __shared__ double s_w[8];
+  __shared__ unsigned s_hx[8], s_hn[8];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned first = blockIdx.x * 4096u;
   double s = 0.0;
-  for (unsigned i = first + threadIdx.x; i < first + 4096u && i < ntiles; i += 256u) s += __ldcg(tile_sums + i);
+  unsigned hx = 0u, hn = 0xFFFFFFFFu;
+  for (unsigned i = first + threadIdx.x; i < first + 4096u && i < ntiles; i += 256u) {
+    s += __ldcg(tile_sums + i);
+    const uint2 e = __ldcg(tile_ext + i);
+    hx = max(hx, e.x);
+    hn = min(hn, e.y);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-  if (lane == 0) s_w[warp] = s;
+  hx = __reduce_max_sync(0xFFFFFFFFu, hx);
+  hn = __reduce_min_sync(0xFFFFFFFFu, hn);
+  if (lane == 0) { s_w[warp] = s; s_hx[warp] = hx; s_hn[warp] = hn; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < 8; w++) t += s_w[w];
-    cta_sums[blockIdx.x] = t;
+    unsigned x = 0u, n = 0xFFFFFFFFu;
+    for (int w = 0; w < 8; w++) { t += s_w[w]; x = max(x, s_hx[w]); n = min(n, s_hn[w]); }
+    r.cta_sums[blockIdx.x] = t;
+    r.cta_ext[blockIdx.x] = make_uint2(x, n);
     __threadfence();
-    s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+    s_last = (atomicAdd(r.done, 1u) == gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;
   __threadfence();
   double t = 0.0;
-  for (unsigned c = 0; c < gridDim.x; c++) t += __ldcg(cta_sums + c);
+  unsigned x = 0u, n = 0xFFFFFFFFu;
+  for (unsigned c = 0; c < gridDim.x; c++) {
+    t += __ldcg(r.cta_sums + c);
+    const uint2 e = __ldcg(r.cta_ext + c);
+    x = max(x, e.x);
+    n = min(n, e.y);
+  }
   if (tail3) t += tail3[2];
   true3[2] = t;
-  *done_counter = 0u;
+  if (sizeof(T) == 4) {  // float: the "high word" is the whole pattern -- exact
+    double mx = (double)__int_as_float((int)x), mn = (double)__int_as_float((int)n);
+    if (tail3) { mx = fmax(mx, tail3[0]); mn = fmin(mn, tail3[1]); }
+    true3[0] = mx; true3[1] = mn;
+  } else {
+    r.hw[0] = x; r.hw[1] = n;
+    r.ext_bits[0] = 0ull; r.ext_bits[1] = ~0ull;
+  }
+  *r.done = 0u;
+}
+
+// double: exact max|x| / min|x| among the elements whose high word equals the slab's extreme high word.  Only the tiles
+// that recorded that high word are read again (usually one or two; a constant field: all of them -- a second pass, as
+// the two-pass path always makes).  The last CTA merges the tail block and publishes true3[0..1].
+__global__ void __launch_bounds__(256) k_resolve_extremes(const double *__restrict__ in, unsigned long long nblk_full, const uint2 *__restrict__ tile_ext,
+                                                          unsigned ntiles, TileReduce r, unsigned *done2, const double *tail3, double *true3) {
+  const unsigned hx = __ldcg(r.hw), hn = __ldcg(r.hw + 1);
+  const int lane = threadIdx.x & 31;
+  const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long bmax = 0ull, bmin = ~0ull;
+  for (unsigned t0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; t0 < ntiles; t0 += wpg * 32u) {  // 32 tile records per warp and trip
+    const unsigned tl = t0 + (unsigned)lane;
+    uint2 e = make_uint2(0xFFFFFFFFu, 0u);
+    if (tl < ntiles) e = __ldcg(tile_ext + tl);
+    unsigned hit = __ballot_sync(0xFFFFFFFFu, tl < ntiles && (e.x == hx || e.y == hn));
+    while (hit) {  // re-read the (few) tiles that hold a candidate
+      const unsigned t = t0 + (unsigned)(__ffs(hit) - 1);
+      hit &= hit - 1u;
+      const unsigned long long first = (unsigned long long)t * (WTILE * BLK);
+      unsigned long long last = first + WTILE * BLK;
+      if (last > nblk_full * BLK) last = nblk_full * BLK;
+      for (unsigned long long i = first + lane; i < last; i += 32) {
+        const unsigned long long a = (unsigned long long)__double_as_longlong(__ldg(in + i)) & 0x7FFFFFFFFFFFFFFFull;
+        const unsigned h = (unsigned)(a >> 32);
+        if (h == hx) bmax = a > bmax ? a : bmax;
+        if (h == hn) bmin = a < bmin ? a : bmin;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long m1 = __shfl_xor_sync(0xFFFFFFFFu, bmax, o), m2 = __shfl_xor_sync(0xFFFFFFFFu, bmin, o);
+    bmax = m1 > bmax ? m1 : bmax;
+    bmin = m2 < bmin ? m2 : bmin;
+  }
+  if (lane == 0) {
+    if (bmax != 0ull) atomicMax(r.ext_bits, bmax);
+    if (bmin != ~0ull) atomicMin(r.ext_bits + 1, bmin);
+  }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done2, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  double mx = __longlong_as_double((long long)*reinterpret_cast<volatile unsigned long long *>(r.ext_bits));
+  double mn = __longlong_as_double((long long)*reinterpret_cast<volatile unsigned long long *>(r.ext_bits + 1));
+  if (tail3) { mx = fmax(mx, tail3[0]); mn = fmin(mn, tail3[1]); }
+  true3[0] = mx; true3[1] = mn;
+  *done2 = 0u;
 }
 
 // The BELIEF: max|x| over a sample of the slab -- one 16-byte vector of every 4 KB (0.4 % of the bytes) -- plus the
 // exact {max, min, sum} of the partial tail block, which the tile loop never sees.  belief3 = {max, max, 0}: only the
 // decade of the maximum matters (util.c:28), the true statistics replace it after the compress pass.
-constexpr unsigned SAMPLE_STRIDE_VECS = 256;  // 16-byte vectors between two samples (4 KB)
+constexpr unsigned SAMPLE_STRIDE_VECS = 256;  // at least this many 16-byte vectors between two samples (4 KB); large slabs: ~256 K samples in all
 template <typename T>
-__global__ void __launch_bounds__(256) k_sample(const T *__restrict__ in, size_t n, unsigned long long *max_bits, unsigned *done_counter,
+__global__ void __launch_bounds__(256) k_sample(const T *__restrict__ in, size_t n, size_t stride_vecs, unsigned long long *max_bits, unsigned *done_counter,
                                                 double *belief3, double *tail3) {
   constexpr int VEC = 16 / (int)sizeof(T);
-  const size_t nfull = (n / BLK) * BLK, nvec = nfull / VEC, nsamp = (nvec + SAMPLE_STRIDE_VECS - 1) / SAMPLE_STRIDE_VECS;
+  const size_t nfull = (n / BLK) * BLK, nvec = nfull / VEC, nsamp = (nvec + stride_vecs - 1) / stride_vecs;
   const uint4 *p = reinterpret_cast<const uint4 *>(in);
   T vmax = (T)0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nsamp; i0 += 4 * stride) {
     uint4 v[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) { const size_t i = i0 + u * stride; v[u] = i < nsamp ? __ldg(p + i * SAMPLE_STRIDE_VECS) : make_uint4(0u, 0u, 0u, 0u); }
+    for (int u = 0; u < 4; u++) { const size_t i = i0 + u * stride; v[u] = i < nsamp ? __ldg(p + i * stride_vecs) : make_uint4(0u, 0u, 0u, 0u); }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const T *e = reinterpret_cast<const T *>(&v[u]);

@@ -68,7 +68,8 @@ def test_single_launch_equals_streaming_path(ctx, streaming_ctx, dtype, qt, kind
         ia, ib = a["info"], b["info"]
         for key in ("sf", "max_abs", "min_abs", "n_outliers", "status", "n_qt_dropped"):
             assert ia[key] == ib[key], (n, key, ia[key], ib[key])
-        assert abs(ia["sum"] - ib["sum"]) <= 1e-9 * np.sum(np.abs(x.astype(np.float64))) + 1e-300
+        # (float data: the streaming path's single-read kernel adds a block's 64 values in float, like the reference's float sum)
+        assert abs(ia["sum"] - ib["sum"]) <= (1e-9 if dtype == np.float64 else 1e-5) * np.sum(np.abs(x.astype(np.float64))) + 1e-300
         # decompress: both paths on the same stream
         ra, lda = _launches(ctx, lambda: ctx.decompress_core(a["bin_index"], a["dc"], a["ac"], n, dtype, eb, a["sf"], qt=qt, qtable=a.get("qtable")))
         rb, ldb = _launches(streaming_ctx, lambda: streaming_ctx.decompress_core(a["bin_index"], a["dc"], a["ac"], n, dtype, eb, a["sf"], qt=qt,
