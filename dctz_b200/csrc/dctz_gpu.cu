@@ -548,6 +548,7 @@ template <typename T> static QtConsts<T> make_qt(double eb) {
   k.d_rmax = (T)(eb * DCTZ_GPU_NBINS);   // dctz-decomp-lib.c:373 / 378
   k.d_rmin = (T)(-eb * DCTZ_GPU_NBINS);  // :374 / 379
   k.den = eb * (sizeof(T) == 8 ? 10.0 : (double)10.0f);  // error_bound * qt_factor (:405, :450)
+  k.den_div = make_divisor(k.den);
   return k;
 }
 
@@ -914,9 +915,10 @@ constexpr int kNcclFloat = 7, kNcclDouble = 8, kNcclMax = 2;  // ncclFloat32, nc
 static int load_nccl(dctz_gpu_ctx *ctx) {
   static std::once_flag once;
   std::call_once(once, [] {
-    void *h = RTLD_DEFAULT;
-    if (!dlsym(h, "ncclAllGather")) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (h) {
+    void *h = RTLD_DEFAULT;  // (a null handle: "whatever the process has loaded")
+    bool ok = dlsym(h, "ncclAllGather") != nullptr;
+    if (!ok) { h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); ok = h != nullptr; }
+    if (ok) {
       g_nccl.all_gather = (NcclAllGatherFn)dlsym(h, "ncclAllGather");
       g_nccl.all_reduce = (NcclAllReduceFn)dlsym(h, "ncclAllReduce");
       g_nccl.broadcast = (NcclBroadcastFn)dlsym(h, "ncclBroadcast");

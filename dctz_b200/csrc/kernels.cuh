@@ -1265,6 +1265,7 @@ template <typename T> struct QtConsts {
   T rmin, rmax;     // compress-side range (dctz-comp-lib.c:274-275 / 279-280)
   T d_rmin, d_rmax; // decompress-side range (dctz-decomp-lib.c:373-374 / 378-379)
   double den;       // error_bound * qt_factor  (dctz-decomp-lib.c:405,450)
+  Divisor<double> den_div;  // exact division by it without the division instruction sequence (common.cuh)
 };
 
 // The branch is chosen by the SIGN of the coefficient, not by re-testing it against the range: the element IS an outlier
@@ -1465,13 +1466,13 @@ template <typename T> __device__ __forceinline__ unsigned id_offset(unsigned w, 
 
 __device__ __forceinline__ double qt_unscale_one(float acf, double q, const QtConsts<double> &k) {
   const double v = (double)acf;  // :402
-  if (v > 0) return __dmul_rn(__ddiv_rn(__dsub_rn(v, k.d_rmax), k.den), q);  // :405
-  return __dmul_rn(__ddiv_rn(__dsub_rn(v, k.d_rmin), k.den), q);             // :408
+  if (v > 0) return __dmul_rn(div_exact(__dsub_rn(v, k.d_rmax), k.den_div), q);  // :405 (IEEE quotient by den, see Divisor)
+  return __dmul_rn(div_exact(__dsub_rn(v, k.d_rmin), k.den_div), q);             // :408
 }
 __device__ __forceinline__ float qt_unscale_one(float acf, float q, const QtConsts<float> &k) {
   // :450-454 -- float subtraction, double division and product, stored to float
-  if (acf > 0) return (float)__dmul_rn(__ddiv_rn((double)__fsub_rn(acf, k.d_rmax), k.den), (double)q);
-  return (float)__dmul_rn(__ddiv_rn((double)__fsub_rn(acf, k.d_rmin), k.den), (double)q);
+  if (acf > 0) return (float)__dmul_rn(div_exact((double)__fsub_rn(acf, k.d_rmax), k.den_div), (double)q);
+  return (float)__dmul_rn(div_exact((double)__fsub_rn(acf, k.d_rmin), k.den_div), (double)q);
 }
 
 template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
