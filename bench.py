@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--cpu-log2", type=int, default=23, help="elements per process of the CPU reference sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / quality legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="independent fields in flight through the host-buffer API (host threads, a context each)")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs leg (c1..c4 beside the headline)")
     ap.add_argument("--f32", action="store_true", help="c5-slab only: cast the slab to float (single-precision path)")
     ap.add_argument("--qt", action="store_true", help="c5-slab: quantiser (QT) mode instead of error-bounded (EC); at N > 1 the qtable is reduced over NCCL")
@@ -638,43 +639,104 @@ def main_ours(args):
             raise SystemExit(f"bench.py: per-rank parity check failed: {quality_per_rank}")
 
     # ---- end to end through the host-buffer C-ABI (pinned host buffers, copies inside the timing) ----
+    # Every step uploads its input from page-locked host memory and brings the result back.  A compress call is upload-
+    # heavy and a decompress call download-heavy, and the link is full duplex: `lanes` host threads (a context and a set
+    # of host buffers each) keep that many independent fields in flight, the library's per-device link gates put them in
+    # step (one uploads while the other downloads).  `serial_value` is one field at a time, as in round 1.
     e2e = None
     if not args.no_e2e:
+        import threading
+
         ne = min(pieces[0][1], 1 << args.e2e_log2)
         nblk_e = (ne + 63) // 64
         np_dt = np.float64 if es == 8 else np.float32
-        hx = binding.PinnedArray((ne,), np_dt)
-        hout = binding.PinnedArray((ne,), np_dt)
-        hb = binding.PinnedArray((ne,), np.uint8)
-        hdc = binding.PinnedArray((nblk_e,), np.float32)
-        hac = binding.PinnedArray((ne,), np.float32)
-        hx.array[:] = x[:ne].cpu().numpy()
-        pre = dict(bin_index=hb.array, dc=hdc.array, ac_full=hac.array)
-        ksteps = max(1, min(args.steps, 5))
+        ksteps = max(1, min(args.steps, 8))
+        lanes = max(1, args.e2e_lanes)
 
-        def e2e_step():
-            g = ctx.compress_core(hx.array, EB, qt=qt, out=pre)
-            st_c = ctx.last_call_stats()
-            ctx.decompress_core(g["bin_index"], g["dc"], g["ac"], ne, np_dt, EB, g["sf"], qt=qt, qtable=g.get("qtable"), out=hout.array)
-            st_d = ctx.last_call_stats()
-            return g, st_c, st_d
+        class Lane:
+            def __init__(self, c):
+                self.ctx = c
+                self.hx = binding.PinnedArray((ne,), np_dt)
+                self.hout = binding.PinnedArray((ne,), np_dt)
+                self.hb = binding.PinnedArray((ne,), np.uint8)
+                self.hdc = binding.PinnedArray((nblk_e,), np.float32)
+                self.hac = binding.PinnedArray((ne,), np.float32)
+                self.pre = dict(bin_index=self.hb.array, dc=self.hdc.array, ac_full=self.hac.array)
+                self.err = None
+                self.trace = []
 
-        g, st_c, st_d = e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            g, st_c, st_d = e2e_step()
-        torch.cuda.synchronize()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = dict(value=world * ne * es * ksteps / 1e9 / float(te.item()), unit=UNIT,
-                   h2d_bytes_per_step=st_c["h2d_bytes"] + st_d["h2d_bytes"], d2h_bytes_per_step=st_c["d2h_bytes"] + st_d["d2h_bytes"],
-                   steps=ksteps, sample=f"first {ne} elements of the rank's slab per step, pinned host buffers, "
-                                        f"dctz_gpu_compress_core + dctz_gpu_decompress_core (synchronous, copies included; bytes counted by the library)",
-                   max_abs_err=float(np.max(np.abs(hout.array - hx.array))))
-        for h in (hx, hout, hb, hdc, hac):
-            h.free()
+            def step(self):
+                t0 = time.perf_counter()
+                g = self.ctx.compress_core(self.hx.array, EB, qt=qt, out=self.pre)
+                t1 = time.perf_counter()
+                self.st_c = self.ctx.last_call_stats()
+                self.ctx.decompress_core(g["bin_index"], g["dc"], g["ac"], ne, np_dt, EB, g["sf"], qt=qt, qtable=g.get("qtable"), out=self.hout.array)
+                t2 = time.perf_counter()
+                self.st_d = self.ctx.last_call_stats()
+                self.trace.append((t0, t1, t2, self.st_c, self.st_d))
+
+            def run(self, k):
+                try:
+                    for _ in range(k):
+                        self.step()
+                except Exception as e:  # noqa: BLE001
+                    self.err = e
+
+            def free(self):
+                for h in (self.hx, self.hout, self.hb, self.hdc, self.hac):
+                    h.free()
+
+        lane_list = [Lane(ctx)] + [Lane(dctz_b200.Context(local)) for _ in range(lanes - 1)]
+        src = x[:ne].cpu().numpy()
+        for ln in lane_list:
+            ln.hx.array[:] = src
+            ln.step()  # warm-up: buffers grown, kernels loaded
+        del src
+
+        def timed(active):
+            barrier()
+            t0 = time.perf_counter()
+            if len(active) == 1:
+                active[0].run(ksteps)
+            else:
+                th = [threading.Thread(target=ln.run, args=(ksteps,)) for ln in active]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+            torch.cuda.synchronize()
+            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            for ln in active:
+                if ln.err is not None:
+                    raise ln.err
+            return world * len(active) * ne * es * ksteps / 1e9 / float(te.item())
+
+        v_serial = timed(lane_list[:1])
+        for ln in lane_list:
+            ln.trace = []
+        v_lanes = timed(lane_list) if lanes > 1 else v_serial
+        if os.environ.get("DCTZ_BENCH_TRACE"):
+            tb = min(t[0] for ln in lane_list for t in ln.trace)
+            for i, ln in enumerate(lane_list):
+                print(f"e2e lane {i}: " + " | ".join(
+                    f"C {1e3 * (a - tb):.1f} (gate +{sc['gate_taken_ms']:.1f}, kernels done +{sc['wall_to_kernels_ms']:.1f}) -{1e3 * (b - tb):.1f} "
+                    f"D (gate +{sd['gate_taken_ms']:.1f}, first piece +{sd['first_dominant_piece_ms']:.1f}) -{1e3 * (c - tb):.1f}"
+                    for a, b, c, sc, sd in ln.trace), file=sys.stderr)
+        l0 = lane_list[0]
+        e2e = dict(value=v_lanes, unit=UNIT, serial_value=v_serial, fields_in_flight=lanes,
+                   h2d_bytes_per_step=l0.st_c["h2d_bytes"] + l0.st_d["h2d_bytes"], d2h_bytes_per_step=l0.st_c["d2h_bytes"] + l0.st_d["d2h_bytes"],
+                   steps=ksteps * lanes,
+                   sample=f"a step = the first {ne} elements of the rank's slab through dctz_gpu_compress_core + dctz_gpu_decompress_core (synchronous "
+                          f"calls on pinned host buffers, copies included; bytes per step counted by the library); {lanes} host thread(s) with a context "
+                          f"each keep {lanes} independent field(s) in flight so that one field's upload overlaps the other's download on the full-duplex "
+                          f"link (serial_value: one field at a time); wall clock over {ksteps} step(s) per thread",
+                   max_abs_err=float(max(np.max(np.abs(ln.hout.array - ln.hx.array)) for ln in lane_list)))
+        for ln in lane_list:
+            ln.free()
+        for ln in lane_list[1:]:
+            ln.ctx.close()
 
     # (every rank takes part: barrier + max over ranks -- hence before the other ranks leave)
     # Reported beside the headline, never as it: compress with KNOWN statistics (those of the previous step, as a

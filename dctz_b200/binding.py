@@ -196,6 +196,7 @@ class Context:
         h, d = C.c_uint64(0), C.c_uint64(0)
         self._check(self._lib.dctz_gpu_last_call_stats(self._h, t, C.byref(h), C.byref(d)))
         return dict(upload_ms=t[0], stats_ms=t[1], transform_ms=t[2], wall_to_kernels_ms=t[3], wall_downloads_ms=t[4],
+                    gate_taken_ms=t[5], first_dominant_piece_ms=t[6],
                     h2d_bytes=int(h.value), d2h_bytes=int(d.value))
 
     def sf_from_max(self, max_abs, dtype):

@@ -132,6 +132,28 @@ class HostPool {
 constexpr size_t STAGE_BYTES = (size_t)16 << 20;  // one slot of the pinned staging ring
 constexpr int NSTAGE = 3;
 constexpr size_t PINNED_CHUNK = (size_t)64 << 20;  // copy granularity when the caller's memory is already page-locked
+constexpr size_t GATE_BYTES = (size_t)64 << 20;    // transfers of at least this size take their direction's link gate
+
+// One PCIe link per device, full duplex.  A compress call is upload-heavy, a decompress call download-heavy; two host
+// threads with a context each that would run in phase (both uploading, then both downloading) use one direction at a
+// time.  The direction-dominant transfer of a call therefore holds its direction's gate: concurrent callers fall into
+// step with one uploading while the other downloads.  The other call's SHORT transfer in the gated direction must not
+// queue behind the long one: a copy engine stays with a stream for as long as that stream has another copy queued
+// (tools/probes/link_interleave.cu: 128 MiB submitted beside a 1 GiB transfer kept 2-3 pieces deep completes after
+// 17 ms, beside one kept ONE piece deep after 2.5 ms), so while a second host-buffer call is active on the device a
+// dominant transfer submits its next piece only when the previous one has landed.  DCTZ_LINK_GATES=0: gates off.
+struct LinkGate { std::mutex up, down; std::atomic<int> busy{0}; };
+static LinkGate g_gate[64];
+struct BusyMark {  // a host-buffer call in progress on the device
+  explicit BusyMark(int dev) : g(dev >= 0 && dev < 64 ? &g_gate[dev] : nullptr) { if (g) g->busy.fetch_add(1); }
+  ~BusyMark() { if (g) g->busy.fetch_sub(1); }
+  LinkGate *g;
+};
+static bool link_contended(int dev) { return dev >= 0 && dev < 64 && g_gate[dev].busy.load(std::memory_order_relaxed) > 1; }
+static bool link_gates_enabled() {
+  static const bool on = [] { const char *e = getenv("DCTZ_LINK_GATES"); return !(e && atoi(e) == 0); }();
+  return on;
+}
 
 struct dctz_gpu_ctx {
   int device = 0;
@@ -145,6 +167,7 @@ struct dctz_gpu_ctx {
   DevBuf chunk_stats;  // {max,min,sum} per chunk of a pipelined upload
   int timing = 0;      // stage timers requested (dctz_gpu_set_timing): the stages then run one after the other
   double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::chrono::steady_clock::time_point t_call;  // start of the current host-buffer call (times[5..7] count from here)
   uint64_t h2d_bytes = 0, d2h_bytes = 0;  // PCIe traffic of the last host-buffer call
   char err[512] = "";
   uint64_t launches = 0;
@@ -1131,12 +1154,17 @@ static int ensure_pool(dctz_gpu_ctx *ctx) {
   return DCTZ_GPU_OK;
 }
 
+static int ensure_stage_events(dctz_gpu_ctx *ctx) {
+  for (int i = 0; i < NSTAGE; i++)
+    if (!ctx->stage_ev[i]) CU(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+  return DCTZ_GPU_OK;
+}
+
 static int ensure_stage(dctz_gpu_ctx *ctx) {
   TRY(ensure_pool(ctx));
-  for (int i = 0; i < NSTAGE; i++) {
+  TRY(ensure_stage_events(ctx));
+  for (int i = 0; i < NSTAGE; i++)
     if (!ctx->stage[i]) CU(cudaMallocHost(&ctx->stage[i], STAGE_BYTES));
-    if (!ctx->stage_ev[i]) CU(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
-  }
   return DCTZ_GPU_OK;
 }
 
@@ -1150,27 +1178,33 @@ static void pool_memcpy(HostPool *pool, void *dst, const void *src, size_t bytes
   });
 }
 
-// Host -> device, chunked on the copy stream.  after_chunk(index, byte offset, bytes) is called once the chunk's copy
-// has been enqueued and the compute stream has been told to wait for it.
+// Host -> device on the copy stream.  after_chunk(index, byte offset, bytes) is called once a chunk's copy has been
+// enqueued and the compute stream has been told to wait for it.  `dominant` marks the direction-dominant transfer of a
+// call (it holds the link gate, see LinkGate); the other transfers from page-locked memory are submitted whole.
 static int upload(dctz_gpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, size_t chunk_align,
-                  const std::function<int(size_t, size_t, size_t)> &after_chunk) {
+                  const std::function<int(size_t, size_t, size_t)> &after_chunk, bool dominant = false) {
   if (bytes == 0) return DCTZ_GPU_OK;
   const bool pinned = host_is_pinned(h_src);
-  if (!pinned) TRY(ensure_stage(ctx));
+  if (pinned) TRY(ensure_stage_events(ctx));
+  else TRY(ensure_stage(ctx));
   size_t chunk = pinned ? PINNED_CHUNK : STAGE_BYTES;
+  if (pinned && !after_chunk && !dominant) chunk = bytes + chunk_align;  // submitted whole
   chunk -= chunk % chunk_align;
   size_t c = 0;
   for (size_t off = 0; off < bytes; off += chunk, c++) {
     const size_t len = bytes - off < chunk ? bytes - off : chunk;
     const void *src = (const char *)h_src + off;
     const int s = (int)(c % NSTAGE);
+    // staged: the slot's previous content (this upload's or an earlier one's) is on the device; page-locked: at most
+    // NSTAGE chunks in flight -- one while another call wants the link
+    CU(cudaEventSynchronize(ctx->stage_ev[s]));
+    if (pinned && dominant && c > 0 && link_contended(ctx->device)) CU(cudaEventSynchronize(ctx->stage_ev[(c - 1) % NSTAGE]));
     if (!pinned) {
-      CU(cudaEventSynchronize(ctx->stage_ev[s]));  // the slot's previous content (this upload's or an earlier one's) is on the device
       pool_memcpy(ctx->pool, ctx->stage[s], src, len);
       src = ctx->stage[s];
     }
     CU(cudaMemcpyAsync((char *)d_dst + off, src, len, cudaMemcpyHostToDevice, ctx->copy_stream));
-    if (!pinned) CU(cudaEventRecord(ctx->stage_ev[s], ctx->copy_stream));
+    CU(cudaEventRecord(ctx->stage_ev[s], ctx->copy_stream));
     CU(cudaEventRecord(ctx->ev_chain, ctx->copy_stream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_chain, 0));
     if (after_chunk) TRY(after_chunk(c, off, len));
@@ -1181,23 +1215,27 @@ static int upload(dctz_gpu_ctx *ctx, void *d_dst, const void *h_src, size_t byte
 
 // Device -> host of data produced on the compute stream; synchronous.  on_ready(byte offset, bytes) reports every
 // piece as soon as it is valid in the caller's buffer (the host library starts deflating it while the rest is still
-// on its way).
-static int download(dctz_gpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, const std::function<void(size_t, size_t)> &on_ready) {
+// on its way).  `dominant`: as for upload().
+static int download(dctz_gpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, const std::function<void(size_t, size_t)> &on_ready,
+                    bool dominant = false) {
   if (bytes == 0) return DCTZ_GPU_OK;
   CU(cudaEventRecord(ctx->ev_chain, ctx->stream));
   CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chain, 0));
   const bool pinned = host_is_pinned(h_dst);
   ctx->d2h_bytes += bytes;
-  if (pinned && !on_ready) {
+  if (pinned && !on_ready && !dominant) {  // submitted whole
     CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
     CU(cudaStreamSynchronize(ctx->copy_stream));
     return DCTZ_GPU_OK;
   }
-  TRY(ensure_stage(ctx));  // (the events are used in both modes)
-  const size_t chunk = STAGE_BYTES;
+  if (pinned) TRY(ensure_stage_events(ctx));  // (the events are used in both modes)
+  else TRY(ensure_stage(ctx));
+  const size_t chunk = pinned ? PINNED_CHUNK : STAGE_BYTES;
   const size_t nchunks = (bytes + chunk - 1) / chunk;
+  // chunks on the wire beside the one being handed over (none while another call wants the link, see LinkGate)
+  const size_t depth = !pinned ? 1 : dominant && link_contended(ctx->device) ? 0 : NSTAGE - 1;
   auto span = [&](size_t c, size_t *off, size_t *len) { *off = c * chunk; *len = bytes - *off < chunk ? bytes - *off : chunk; };
-  for (size_t c = 0; c <= nchunks; c++) {  // chunk c goes on the wire, chunk c-1 is handed over
+  for (size_t c = 0; c < nchunks + depth; c++) {  // chunk c goes on the wire, chunk c-depth is handed over
     if (c < nchunks) {
       size_t off, len;
       span(c, &off, &len);
@@ -1206,11 +1244,12 @@ static int download(dctz_gpu_ctx *ctx, void *h_dst, const void *d_src, size_t by
       CU(cudaMemcpyAsync(dst, (const char *)d_src + off, len, cudaMemcpyDeviceToHost, ctx->copy_stream));
       CU(cudaEventRecord(ctx->stage_ev[s], ctx->copy_stream));
     }
-    if (c > 0) {
+    if (c >= depth) {
       size_t off, len;
-      span(c - 1, &off, &len);
-      const int s = (int)((c - 1) % NSTAGE);
+      span(c - depth, &off, &len);
+      const int s = (int)((c - depth) % NSTAGE);
       CU(cudaEventSynchronize(ctx->stage_ev[s]));
+      if (dominant && c == depth) ctx->times[6] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ctx->t_call).count();
       if (!pinned) pool_memcpy(ctx->pool, (char *)h_dst + off, ctx->stage[s], len);
       if (on_ready) on_ready(off, len);
     }
@@ -1258,17 +1297,23 @@ static int compress_core_impl(dctz_gpu_ctx *ctx, const void *in, size_t N, size_
   const size_t up_chunk = pinned_in ? PINNED_CHUNK : STAGE_BYTES;
   const size_t nchunks = (N * es + up_chunk - 1) / up_chunk;
   const auto t_begin = std::chrono::steady_clock::now();
+  ctx->t_call = t_begin;
+  BusyMark busy(ctx->device);
   if (ctx->timing) CU(cudaEventRecord(ctx->ev_time[0], st));
+  // compress is the upload-heavy call: it holds the device's upload gate until its kernels have run (see LinkGate)
+  std::unique_lock<std::mutex> up_gate;
+  if (link_gates_enabled() && N * es >= GATE_BYTES && ctx->device < 64) up_gate = std::unique_lock<std::mutex>(g_gate[ctx->device].up);
+  ctx->times[5] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();  // gate taken
 
   if (stats3) {  // the caller's global statistics decide the scaling factor
     CU(cudaMemcpyAsync(ctx->d_stats_host3, stats3, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr));
+    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr, up_gate.owns_lock()));
     if (ctx->timing) { CU(cudaStreamSynchronize(st)); CU(cudaEventRecord(ctx->ev_time[1], st)); CU(cudaEventRecord(ctx->ev_time[2], st)); }
     TRY(dctz_gpu_compress_dev(ctx, ctx->in.p, N, N_total, datatype, eb, mode_qt, ctx->d_stats_host3, 1, first_piece, (uint8_t *)ctx->bins.p,
                               (float *)ctx->dc.p, (float *)ctx->ac.p, ctx->qtraw.p, d_info, st));
     if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, ctx->qtraw.p, ctx->qt.p, (float *)ctx->ac.p, d_info, st));
   } else if (ctx->timing) {  // stage timers wanted (the reference's -DTIME_DEBUG lines): upload, statistics, transform one after the other
-    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr));
+    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr, up_gate.owns_lock()));
     CU(cudaStreamSynchronize(st));
     CU(cudaEventRecord(ctx->ev_time[1], st));
     TRY(dctz_gpu_stats_dev(ctx, ctx->in.p, N, datatype, ctx->d_stats3, st));
@@ -1277,7 +1322,7 @@ static int compress_core_impl(dctz_gpu_ctx *ctx, const void *in, size_t N, size_
                               (float *)ctx->ac.p, ctx->qtraw.p, d_info, st));
     if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, ctx->qtraw.p, ctx->qt.p, (float *)ctx->ac.p, d_info, st));
   } else if (nchunks == 1 || fused_grid(ctx, 0, N, es, mode_qt)) {  // one upload, then the single-field path (small fields: ONE launch)
-    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr));
+    TRY(upload(ctx, ctx->in.p, in, N * es, 1024, nullptr, up_gate.owns_lock()));
     TRY(dctz_gpu_compress_field_dev(ctx, ctx->in.p, N, datatype, eb, mode_qt, (uint8_t *)ctx->bins.p, (float *)ctx->dc.p,
                                     (float *)ctx->ac.p, ctx->qt.p, ctx->qtraw.p, d_info, st));
   } else {  // statistics of chunk k while chunk k+1 is on the wire; the chunks are merged like ranks
@@ -1285,7 +1330,7 @@ static int compress_core_impl(dctz_gpu_ctx *ctx, const void *in, size_t N, size_
     double *d_cs = (double *)ctx->chunk_stats.p;
     TRY(upload(ctx, ctx->in.p, in, N * es, 1024, [&](size_t c, size_t off, size_t len) -> int {
       return dctz_gpu_stats_dev(ctx, (const char *)ctx->in.p + off, len / es, datatype, d_cs + 3 * c, st);
-    }));
+    }, up_gate.owns_lock()));
     TRY(dctz_gpu_compress_dev(ctx, ctx->in.p, N, N, datatype, eb, mode_qt, d_cs, (int)nchunks, 1, (uint8_t *)ctx->bins.p,
                               (float *)ctx->dc.p, (float *)ctx->ac.p, ctx->qtraw.p, d_info, st));
     if (mode_qt) TRY(dctz_gpu_qt_finish_dev(ctx, datatype, eb, ctx->qtraw.p, ctx->qt.p, (float *)ctx->ac.p, d_info, st));
@@ -1293,6 +1338,7 @@ static int compress_core_impl(dctz_gpu_ctx *ctx, const void *in, size_t N, size_
   if (ctx->timing) CU(cudaEventRecord(ctx->ev_time[3], st));
   CU(cudaMemcpyAsync(info, ctx->d_info, sizeof(Info), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (up_gate.owns_lock()) up_gate.unlock();
   ctx->d2h_bytes += sizeof(Info);
   if (info->status != 0)
     return fail(ctx, info->status, "compress_core: max|x| = %g gives no usable scaling factor (util.c:28 would yield 0/inf/NaN)", info->max_abs);
@@ -1477,6 +1523,8 @@ extern "C" int dctz_gpu_decompress_core(dctz_gpu_ctx *ctx, const uint8_t *bin_in
   ctx->h2d_bytes = ctx->d2h_bytes = 0;
   for (double &t : ctx->times) t = 0.0;
   const auto t_begin = std::chrono::steady_clock::now();
+  ctx->t_call = t_begin;
+  BusyMark busy(ctx->device);
   if (ctx->timing) CU(cudaEventRecord(ctx->ev_time[0], st));
   TRY(upload(ctx, ctx->bins.p, bin_index, N, 1024, nullptr));
   TRY(upload(ctx, ctx->dc.p, DC, nblk * 4, 4, nullptr));
@@ -1492,7 +1540,12 @@ extern "C" int dctz_gpu_decompress_core(dctz_gpu_ctx *ctx, const uint8_t *bin_in
   unsigned corrupt = 0;
   CU(cudaMemcpyAsync(&corrupt, &ctx->d_ctl[1].corrupt, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   const auto t_gpu = std::chrono::steady_clock::now();
-  TRY(download(ctx, out, ctx->out.p, N * es, nullptr));
+  {  // decompress is the download-heavy call: it holds the device's download gate while the reconstruction travels
+    std::unique_lock<std::mutex> down_gate;
+    if (link_gates_enabled() && N * es >= GATE_BYTES && ctx->device < 64) down_gate = std::unique_lock<std::mutex>(g_gate[ctx->device].down);
+    ctx->times[5] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ctx->t_call).count();  // gate taken
+    TRY(download(ctx, out, ctx->out.p, N * es, nullptr, down_gate.owns_lock()));
+  }
   CU(cudaStreamSynchronize(st));
   if (ctx->timing) {
     ctx->times[0] = elapsed_ms(ctx->ev_time[0], ctx->ev_time[1]);  // upload
