@@ -201,6 +201,10 @@ struct dctz_gpu_ctx {
   DevBuf in, bins, dc, ac, qt, qtraw, out;
   double *d_dfrag[2] = {nullptr, nullptr};  // DMMA A-fragments of the DCT matrix (forward, inverse)
   int occ[2][2][2] = {};  // resident CTAs/SM per [kernel][datatype][qt]
+  int occ_ahead[2][2] = {};  // ... of the count-ahead decompress kernel [datatype][qt]
+  int decomp_ahead = 0;      // DCTZ_DECOMP_AHEAD=1: streaming decompress without the pre-pass (measured: the second read of the bin ids disappears, the kernel gets slower by as much -- DESIGN.md)
+  int l2_hints = -1;         // DCTZ_L2_HINTS: bit 0 stores evict_first, bit 1 bin-id copies evict_first; -1 = 3 for the count-ahead path, 0 otherwise
+  DevBuf ahead_buf;          // count-ahead decompress: agg[u] | S[u/64] | T[u/2048], zeroed before every launch
   // single-launch kernels for small fields (fused.cuh)
   int occ_fused[2][2][2] = {};
   size_t fused_max_bytes = (size_t)256 << 20;  // fields up to this size take the single-launch path (DCTZ_FUSED_MAX_MB, 0 = never)
@@ -338,6 +342,7 @@ extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
   for (double *p : ctx->d_dfrag) if (p) cudaFree(p);
   if (ctx->chunk_stats.p) cudaFree(ctx->chunk_stats.p);
+  if (ctx->ahead_buf.p) cudaFree(ctx->ahead_buf.p);
   delete ctx->pool;
   for (int i = 0; i < NSTAGE; i++) {
     if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
@@ -367,6 +372,11 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   if (device < 0 || device >= ndev) return fail(ctx, DCTZ_GPU_EINVAL, "device %d out of range [0,%d)", device, ndev);
   ctx->device = device;
   CU(cudaSetDevice(device));
+  {
+    const char *e = getenv("DCTZ_L2_HINTS");
+    const int v = e ? (atoi(e) > 0) : 0;  // (the pre-pass reads the bin ids with evict_last)
+    CU(cudaMemcpyToSymbol(c_l2_hints, &v, sizeof(int)));
+  }
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
@@ -419,10 +429,20 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
       kernel_occupancy(k_compress<float, false, true>, CompressCfg<float, false>::THREADS, CompressCfg<float, false>::SMEM) < 1 ||
       kernel_occupancy(k_compress<float, true, true>, CompressCfg<float, true>::THREADS, CompressCfg<float, true>::SMEM) < 1)
     return fail(ctx, DCTZ_GPU_ECUDA, "k_compress<VERIFY> cannot be made resident");
-  ctx->occ[1][1][0] = kernel_occupancy(k_decompress<double, false>, DecompressCfg<double, false>::THREADS, DecompressCfg<double, false>::SMEM);
-  ctx->occ[1][1][1] = kernel_occupancy(k_decompress<double, true>, DecompressCfg<double, true>::THREADS, DecompressCfg<double, true>::SMEM);
-  ctx->occ[1][0][0] = kernel_occupancy(k_decompress<float, false>, DecompressCfg<float, false>::THREADS, DecompressCfg<float, false>::SMEM);
-  ctx->occ[1][0][1] = kernel_occupancy(k_decompress<float, true>, DecompressCfg<float, true>::THREADS, DecompressCfg<float, true>::SMEM);
+  ctx->occ[1][1][0] = kernel_occupancy(k_decompress<double, false, false>, DecompressCfg<double, false>::THREADS, DecompressCfg<double, false>::SMEM);
+  ctx->occ[1][1][1] = kernel_occupancy(k_decompress<double, true, false>, DecompressCfg<double, true>::THREADS, DecompressCfg<double, true>::SMEM);
+  ctx->occ[1][0][0] = kernel_occupancy(k_decompress<float, false, false>, DecompressCfg<float, false>::THREADS, DecompressCfg<float, false>::SMEM);
+  ctx->occ[1][0][1] = kernel_occupancy(k_decompress<float, true, false>, DecompressCfg<float, true>::THREADS, DecompressCfg<float, true>::SMEM);
+  ctx->occ_ahead[1][0] = kernel_occupancy(k_decompress<double, false, true>, DecompressCfg<double, false>::THREADS, DecompressCfg<double, false>::SMEM);
+  ctx->occ_ahead[1][1] = kernel_occupancy(k_decompress<double, true, true>, DecompressCfg<double, true>::THREADS, DecompressCfg<double, true>::SMEM);
+  ctx->occ_ahead[0][0] = kernel_occupancy(k_decompress<float, false, true>, DecompressCfg<float, false>::THREADS, DecompressCfg<float, false>::SMEM);
+  ctx->occ_ahead[0][1] = kernel_occupancy(k_decompress<float, true, true>, DecompressCfg<float, true>::THREADS, DecompressCfg<float, true>::SMEM);
+  {
+    const char *e = getenv("DCTZ_DECOMP_AHEAD");
+    ctx->decomp_ahead = e ? atoi(e) : 0;
+    e = getenv("DCTZ_L2_HINTS");
+    ctx->l2_hints = e ? atoi(e) : -1;  // -1: the path's own default
+  }
   ctx->occ_fused[0][1][0] = kernel_occupancy(k_compress_fused<double, false>, CompressCfg<double, false>::THREADS, CompressCfg<double, false>::SMEM);
   ctx->occ_fused[0][1][1] = kernel_occupancy(k_compress_fused<double, true>, CompressCfg<double, true>::THREADS, CompressCfg<double, true>::SMEM);
   ctx->occ_fused[0][0][0] = kernel_occupancy(k_compress_fused<float, false>, CompressCfg<float, false>::THREADS, CompressCfg<float, false>::SMEM);
@@ -1049,6 +1069,25 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
   if (nblk_full) {
     const size_t ntiles = (nblk_full + WTILE - 1) / WTILE;
     if (ntiles > 0xFFFFF000ull) return fail(ctx, DCTZ_GPU_EINVAL, "slab too large: %zu tiles", ntiles);
+    if (ctx->decomp_ahead) {  // no pre-pass: the warps count ahead and look their offsets up (AheadExtents)
+      const size_t resident = (size_t)ctx->sm_count * ctx->occ_ahead[sizeof(T) == 8][QT];
+      const size_t ctas = (ntiles + Cfg::WARPS - 1) / Cfg::WARPS;
+      const int grid = (int)(ctas < resident ? ctas : resident);
+      const unsigned batch = tile_batch(ntiles, (size_t)grid * Cfg::WARPS);
+      const size_t nunits = (ntiles + batch - 1) / batch, ngroups = (nunits + 63) / 64, nsuper = (nunits + 2047) / 2048;
+      const size_t off_s = up128(nunits * sizeof(unsigned)), off_t = off_s + up128(ngroups * 8), total = off_t + up128(nsuper * 8);
+      TRY(grow(ctx, ctx->ahead_buf, total));
+      CU(cudaMemsetAsync(ctx->ahead_buf.p, 0, total, st));
+      unsigned *agg = (unsigned *)ctx->ahead_buf.p;
+      unsigned long long *S = (unsigned long long *)((char *)ctx->ahead_buf.p + off_s), *Tt = (unsigned long long *)((char *)ctx->ahead_buf.p + off_t);
+      CUtensorMap tmap;
+      TRY(make_tile_map(ctx, &tmap, d_out, BLK * sizeof(T), nblk_full));
+      k_decompress<T, QT, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, tmap, agg, S, Tt,
+                                                                       ctx->d_nconsumed, ac_limit, &ctx->d_ctl[1], d_corrupt, aligned16(d_dc) ? 1 : 0,
+                                                                       batch, ctx->l2_hints < 0 ? 3 : ctx->l2_hints);
+      ctx->launches++;
+      CU(cudaGetLastError());
+    } else {
     ScanBufs sb;
     TRY(scan_bufs(ctx, ntiles, &sb));
     {
@@ -1070,11 +1109,13 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
     const int grid = (int)(ctas < resident ? ctas : resident);
     CUtensorMap tmap;
     TRY(make_tile_map(ctx, &tmap, d_out, BLK * sizeof(T), nblk_full));
-    k_decompress<T, QT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, tmap, sb.counts,
-                                                               sb.out.group_prefix, sb.out.chunk_prefix, ctx->d_nconsumed, ac_limit, &ctx->d_ctl[1],
-                                                               d_corrupt, aligned16(d_dc) ? 1 : 0, tile_batch(ntiles, (size_t)grid * Cfg::WARPS));
+    k_decompress<T, QT, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(d_bins, d_dc, d_ac, d_qtable, nblk_full, bw, sfT, qk, tmap, sb.counts,
+                                                                      sb.out.group_prefix, sb.out.chunk_prefix, ctx->d_nconsumed, ac_limit,
+                                                                      &ctx->d_ctl[1], d_corrupt, aligned16(d_dc) ? 1 : 0,
+                                                                      tile_batch(ntiles, (size_t)grid * Cfg::WARPS), ctx->l2_hints > 0 ? ctx->l2_hints : 0);
     ctx->launches++;
     CU(cudaGetLastError());
+    }
   }
   if (rem) {
     k_tail_decompress<T, QT><<<1, 32, 0, st>>>(d_bins, d_dc, d_ac, d_qtable, rem, nblk_full, bw, sfT, qk, d_out,
@@ -1373,9 +1414,10 @@ static int compress_core_impl(dctz_gpu_ctx *ctx, const void *in, size_t N, size_
     if (!cb) return nullptr;
     return [=](size_t off, size_t len) { cb(cb_user, id, off, len); };
   };
-  TRY(download(ctx, bin_index, ctx->bins.p, N, section(0)));
+  // the float sections first: they are small on the wire and slow to deflate, so the host library's workers start on them
   TRY(download(ctx, DC, ctx->dc.p, nblk * 4, section(1)));
   TRY(download(ctx, AC_exact, ctx->ac.p, (size_t)info->n_outliers * 4, section(2)));
+  TRY(download(ctx, bin_index, ctx->bins.p, N, section(0)));
   if (cb && info->n_outliers == 0) cb(cb_user, 2, 0, 0);  // every section is reported at least once
   if (mode_qt) {
     CU(cudaMemcpyAsync(qtable, ctx->qt.p, BLK * es, cudaMemcpyDeviceToHost, st));

@@ -373,6 +373,8 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
 // Extents of the single-launch decompress kernel: the tile's count and its offset inside the CTA's range (both written
 // by this CTA before the barrier: plain, L2-coherent loads) + the CTA's base.
 struct LocalExtents {
+  typedef ExtentRaw Raw;
+  static __device__ __forceinline__ Raw none() { Raw r; r.gp = 0; r.cp = 0; r.c = 0; r.k = 0; return r; }
   const unsigned *counts, *tile_off;
   unsigned long long base, n_limit;
   unsigned *corrupt_flag;
@@ -384,8 +386,10 @@ struct LocalExtents {
     r.k = 0u;
     return r;
   }
-  __device__ __forceinline__ Extent finish(const ExtentRaw &r, int) const {
+  __device__ __forceinline__ Extent finish(ExtentRaw &r, int) const {
     Extent e;
+    r.c = pin_here(r.c);
+    r.gp = pin_here(r.gp);
     e.total = r.c;
     e.base = base + r.gp;
     e.bad = e.base + e.total > n_limit;

@@ -14,6 +14,7 @@
  * Build with -DUSE_QTABLE for the "qt" flavour, exactly like the reference's Makefile:12-17.
  * Error convention of the reference: message on stderr, exit(1).  No CPU fallback exists.
  */
+#include <fcntl.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdint.h>
@@ -103,7 +104,12 @@ static void dump(const char *name, const void *p, size_t bytes) {
  * DCTZ_ZLIB_THREADS=<n> overrides the worker count; 1 reproduces the reference byte for byte.
  */
 #define DCTZ_Z_CHUNK ((size_t)1 << 20)
+#define DCTZ_Z_CHUNK_FLOAT ((size_t)1 << 17)
 #define DCTZ_Z_SERIAL ((size_t)1 << 21)
+/* Section 0 (bin_index: long runs, deflates at several hundred MB/s per core) is cut into 1 MiB chunks; sections 1 and 2
+ * (DC, AC_exact: float data, ~30 MB/s per core at the default level) into 128 KiB chunks, or the eight 1 MiB chunks of an
+ * 8 MiB DC section would each keep one core busy for 40 ms while the others idle.  A chunk costs ~100 bytes of stream. */
+static size_t zchunk_size(int section) { return section == 0 ? DCTZ_Z_CHUNK : DCTZ_Z_CHUNK_FLOAT; }
 
 typedef struct {
   const void *src;
@@ -219,7 +225,7 @@ static void deflate_sections(zjob *jobs, int nsec) {
   for (i = 0; i < nsec; i++) {
     parallel[i] = nthreads > 1 && jobs[i].n_src > DCTZ_Z_SERIAL;
     c0[i] = nchunks;
-    if (parallel[i]) nchunks += (jobs[i].n_src + DCTZ_Z_CHUNK - 1) / DCTZ_Z_CHUNK;
+    if (parallel[i]) nchunks += (jobs[i].n_src + zchunk_size(i) - 1) / zchunk_size(i);
   }
   if (nchunks == 0) { /* small sections: the reference's own three single-stream calls */
     for (i = 0; i < nsec; i++) {
@@ -236,11 +242,11 @@ static void deflate_sections(zjob *jobs, int nsec) {
   for (i = 0; i < nsec; i++) {
     size_t off;
     if (!parallel[i]) continue;
-    for (off = 0; off < jobs[i].n_src; off += DCTZ_Z_CHUNK, k++) {
+    for (off = 0; off < jobs[i].n_src; off += zchunk_size(i), k++) {
       zchunk *c = &q.chunks[k];
       c->src = (const unsigned char *)jobs[i].src;
       c->begin = off;
-      c->len = jobs[i].n_src - off < DCTZ_Z_CHUNK ? jobs[i].n_src - off : DCTZ_Z_CHUNK;
+      c->len = jobs[i].n_src - off < zchunk_size(i) ? jobs[i].n_src - off : zchunk_size(i);
       c->last = (off + c->len == jobs[i].n_src);
       c->cap = compressBound((uLong)c->len) + 16;
       c->dst = (unsigned char *)xmalloc(c->cap, "zlib chunk");
@@ -262,7 +268,7 @@ static void deflate_sections(zjob *jobs, int nsec) {
   pthread_mutex_destroy(&q.mu);
   /* stitch: zlib header | raw blocks ... | Adler-32 (big endian) */
   for (i = 0; i < nsec; i++) {
-    size_t n = (jobs[i].n_src + DCTZ_Z_CHUNK - 1) / DCTZ_Z_CHUNK, total = 2 + 4, j;
+    size_t n = (jobs[i].n_src + zchunk_size(i) - 1) / zchunk_size(i), total = 2 + 4, j;
     uLong ad = adler32(0L, Z_NULL, 0);
     unsigned char *o;
     if (!parallel[i]) continue;
@@ -339,7 +345,7 @@ static void zpipe_feed(zpipe *z, int sec, const void *base, size_t total, size_t
     z->total[sec] = total;
     z->parallel[sec] = z->nthreads > 1 && total > DCTZ_Z_SERIAL;
     if (z->parallel[sec]) {
-      z->nchunks[sec] = (total + DCTZ_Z_CHUNK - 1) / DCTZ_Z_CHUNK;
+      z->nchunks[sec] = (total + zchunk_size(sec) - 1) / zchunk_size(sec);
       z->chunks[sec] = (zchunk *)xmalloc(z->nchunks[sec] * sizeof(zchunk), "zlib chunks");
       z->fifo = (size_t *)realloc(z->fifo, (z->cap + z->nchunks[sec]) * sizeof(size_t));
       if (!z->fifo) die("Out of memory", "zlib queue");
@@ -349,7 +355,7 @@ static void zpipe_feed(zpipe *z, int sec, const void *base, size_t total, size_t
   if (off + len > z->ready[sec]) z->ready[sec] = off + len;
   if (z->parallel[sec]) {
     for (k = z->queued[sec]; k < z->nchunks[sec]; k++) { /* every chunk whose bytes are all there */
-      const size_t begin = k * DCTZ_Z_CHUNK, end = begin + DCTZ_Z_CHUNK < z->total[sec] ? begin + DCTZ_Z_CHUNK : z->total[sec];
+      const size_t cs = zchunk_size(sec), begin = k * cs, end = begin + cs < z->total[sec] ? begin + cs : z->total[sec];
       zchunk *c = &z->chunks[sec][k];
       if (end > z->ready[sec]) break;
       c->src = z->src[sec];
@@ -423,6 +429,31 @@ size_t dctz_host_deflate(const void *src, size_t n, void *dst, size_t cap) {
   out = j.n_dst <= cap ? j.n_dst : 0;
   if (out) memcpy(dst, j.dst, out);
   free(j.dst);
+  return out;
+}
+
+/* extension, used by the CPU tests: section number `section` (0 bin_index, 1 DC, 2 AC_exact: they differ in chunk size)
+ * deflated from the complete array (piece == 0) or while it arrives in pieces of `piece` bytes. */
+size_t dctz_host_deflate_section(const void *src, size_t n, void *dst, size_t cap, int section, size_t piece) {
+  zjob j[3];
+  size_t out;
+  if (section < 0 || section > 2) return 0;
+  memset(j, 0, sizeof j);
+  j[section].src = src;
+  j[section].n_src = n;
+  if (piece == 0) {
+    deflate_sections(j, section + 1);
+  } else {
+    zpipe z;
+    size_t off;
+    zpipe_init(&z);
+    for (off = 0; off < n; off += piece) zpipe_feed(&z, section, src, n, off, n - off < piece ? n - off : piece);
+    if (n == 0) zpipe_feed(&z, section, src, 0, 0, 0);
+    zpipe_finish(&z, j, section + 1);
+  }
+  out = j[section].n_dst <= cap ? j[section].n_dst : 0;
+  if (out) memcpy(dst, j[section].dst, out);
+  for (int i = 0; i <= section; i++) free(j[i].dst);
   return out;
 }
 
@@ -528,9 +559,99 @@ static size_t assemble_stream(t_datatype dt, size_t n, double error_bound, const
   return total;
 }
 
+/* ---- side files written while the sections arrive -----------------------------------------------------------------
+ * bin_index.bin / AC_exact.bin (dctz-comp-lib.c:583-595) are as large as the sections themselves; one thread writing them
+ * after the GPU call was the longest stage of dctz_compress.  dpipe writes every piece of a section to its place in the
+ * file (pwrite) as soon as it has landed, on a few threads of its own. */
+#define DPIPE_THREADS 4
+#define DPIPE_PIECE ((size_t)4 << 20)
+typedef struct { int fd; const unsigned char *p; size_t off, len; } ditem;
+typedef struct {
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  ditem *items;
+  size_t head, tail, cap;
+  int closing, started, opened, fd[3];
+  pthread_t th[DPIPE_THREADS];
+} dpipe;
+
+static void dpipe_open(dpipe *d) { /* (truncating last call's files costs milliseconds: done by a worker, not by the caller) */
+  const int f0 = open("bin_index.bin", O_WRONLY | O_CREAT | O_TRUNC, 0666);
+  const int f2 = open("AC_exact.bin", O_WRONLY | O_CREAT | O_TRUNC, 0666);
+  pthread_mutex_lock(&d->mu);
+  d->fd[0] = f0; d->fd[1] = -1; d->fd[2] = f2; /* DC has no side file */
+  d->opened = 1;
+  pthread_cond_broadcast(&d->cv);
+  pthread_mutex_unlock(&d->mu);
+}
+
+static void *dpipe_worker(void *arg) {
+  dpipe *d = (dpipe *)arg;
+  int first;
+  pthread_mutex_lock(&d->mu);
+  first = (d->opened == 0);
+  if (first) d->opened = -1; /* being opened */
+  pthread_mutex_unlock(&d->mu);
+  if (first) dpipe_open(d);
+  for (;;) {
+    ditem it;
+    pthread_mutex_lock(&d->mu);
+    while ((d->opened != 1 || d->head == d->tail) && !(d->closing && d->opened == 1 && d->head == d->tail)) pthread_cond_wait(&d->cv, &d->mu);
+    if (d->head == d->tail) { pthread_mutex_unlock(&d->mu); return NULL; }
+    it = d->items[d->head++];
+    it.fd = d->fd[it.fd]; /* the item carries the section number */
+    pthread_mutex_unlock(&d->mu);
+    while (it.fd >= 0 && it.len) { /* (errors are ignored like the reference's unchecked fwrite) */
+      const ssize_t w = pwrite(it.fd, it.p, it.len, (off_t)it.off);
+      if (w <= 0) break;
+      it.p += w; it.off += (size_t)w; it.len -= (size_t)w;
+    }
+  }
+}
+
+static void dpipe_init(dpipe *d, size_t total_bytes) {
+  int t;
+  memset(d, 0, sizeof *d);
+  d->fd[0] = d->fd[1] = d->fd[2] = -1;
+  pthread_mutex_init(&d->mu, NULL);
+  pthread_cond_init(&d->cv, NULL);
+  d->cap = total_bytes / DPIPE_PIECE + 4096;
+  d->items = (ditem *)xmalloc(d->cap * sizeof(ditem), "side-file queue");
+  for (t = 0; t < DPIPE_THREADS; t++, d->started++)
+    if (pthread_create(&d->th[t], NULL, dpipe_worker, d)) break;
+}
+
+static void dpipe_feed(dpipe *d, int sec, const void *base, size_t off, size_t len) {
+  if (sec == 1 || len == 0) return;
+  pthread_mutex_lock(&d->mu);
+  while (len && d->tail < d->cap) { /* (the queue holds every piece of both files: see dpipe_init) */
+    const size_t l = len < DPIPE_PIECE ? len : DPIPE_PIECE;
+    ditem *it = &d->items[d->tail++];
+    it->fd = sec; it->p = (const unsigned char *)base + off; it->off = off; it->len = l;
+    off += l; len -= l;
+  }
+  pthread_cond_broadcast(&d->cv);
+  pthread_mutex_unlock(&d->mu);
+}
+
+static void dpipe_finish(dpipe *d) {
+  int t;
+  pthread_mutex_lock(&d->mu);
+  d->closing = 1;
+  pthread_cond_broadcast(&d->cv);
+  pthread_mutex_unlock(&d->mu);
+  if (d->started == 0) dpipe_worker(d); /* no thread could be created: open, drain the queue and return here */
+  for (t = 0; t < d->started; t++) pthread_join(d->th[t], NULL);
+  for (t = 0; t < 3; t++) if (d->fd[t] >= 0) close(d->fd[t]);
+  free(d->items);
+  pthread_mutex_destroy(&d->mu);
+  pthread_cond_destroy(&d->cv);
+}
+
 /* ---- dctz_compress (dctz.h:126) ------------------------------------------------------------------ */
 typedef struct {
   zpipe *zp;
+  dpipe *dp; /* NULL: no side files */
   const void *base[3];
   size_t n, nblk;
   const dctz_gpu_info *info;
@@ -540,6 +661,7 @@ static void on_section(void *user, int section, size_t off, size_t bytes) {
   feed_ctx *f = (feed_ctx *)user;
   const size_t total = section == 0 ? f->n : section == 1 ? f->nblk * sizeof(float) : (size_t)f->info->n_outliers * sizeof(float);
   zpipe_feed(f->zp, section, f->base[section], total, off, bytes);
+  if (f->dp) dpipe_feed(f->dp, section, f->base[section], off, bytes);
 }
 
 /* -DDCT_FILE_DEBUG of the reference (dctz-comp-lib.c:422-433): the coefficients of the scaled data and the DC array.
@@ -568,6 +690,8 @@ int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error
   unsigned char qtable[DCTZ_BLK_SZ * sizeof(double)], qtable_raw[DCTZ_BLK_SZ * sizeof(double)];
   dctz_gpu_info info;
   zpipe zp;
+  dpipe dp;
+  int piped_dumps = 0;
   feed_ctx fc;
   double t0 = wall(), t1, t2;
   void *data = is_double ? (void *)var->buf.d : (void *)var->buf.f;
@@ -589,6 +713,9 @@ int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error
   dctz_gpu_set_timing(gpu(), timing);
   if (!timing) {
     zpipe_init(&zp);
+    piped_dumps = dumps_enabled();
+    if (piped_dumps) dpipe_init(&dp, n * (1 + sizeof(float)));
+    fc.dp = piped_dumps ? &dp : NULL;
     fc.zp = &zp; fc.base[0] = bin_index; fc.base[1] = DC; fc.base[2] = AC_exact; fc.n = n; fc.nblk = nblk; fc.info = &info;
     rc = dctz_gpu_compress_core_cb(g_ctx, data, n, is_double ? DCTZ_GPU_DOUBLE : DCTZ_GPU_FLOAT, error_bound, MODE_QT, data, bin_index, DC,
                                    AC_exact, MODE_QT ? qtable : NULL, MODE_QT ? qtable_raw : NULL, &info, on_section, &fc);
@@ -605,7 +732,13 @@ int dctz_compress(t_var *var, int N, size_t *outSize, t_var *var_z, double error
   }
   if (env_on("DCTZ_DCT_FILE_DEBUG") && dumps_enabled()) dump_coefficients(var, n, DC, nblk);
   *outSize = assemble_stream(var->datatype, n, error_bound, &info, bin_index, DC, AC_exact, qtable, qtable_raw,
-                             is_double ? (unsigned char *)var_z->buf.d : (unsigned char *)var_z->buf.f, 1, timing ? NULL : &zp);
+                             is_double ? (unsigned char *)var_z->buf.d : (unsigned char *)var_z->buf.f, !piped_dumps, timing ? NULL : &zp);
+  if (piped_dumps) {
+    const double t_d = wall();
+    if (MODE_QT) dump("qtable.bin", qtable_raw, DCTZ_BLK_SZ * (is_double ? sizeof(double) : sizeof(float))); /* dctz-comp-lib.c:443-448 */
+    dpipe_finish(&dp);
+    if (env_on("DCTZ_PROFILE")) fprintf(stderr, "dctz profile: waiting for the side files %.1f ms\n", 1e3 * (wall() - t_d));
+  }
   t2 = wall();
   free(bin_index);
   free(DC);

@@ -923,11 +923,25 @@ __global__ void __launch_bounds__(256) k_resolve_extremes(const double *__restri
       const unsigned long long first = (unsigned long long)t * (WTILE * BLK);
       unsigned long long last = first + WTILE * BLK;
       if (last > nblk_full * BLK) last = nblk_full * BLK;
-      for (unsigned long long i = first + lane; i < last; i += 32) {
-        const unsigned long long a = (unsigned long long)__double_as_longlong(__ldg(in + i)) & 0x7FFFFFFFFFFFFFFFull;
-        const unsigned h = (unsigned)(a >> 32);
-        if (h == hx) bmax = a > bmax ? a : bmax;
-        if (h == hn) bmin = a < bmin ? a : bmin;
+      // 16-byte vectors, eight loads in flight per lane (a lone warp walking a tile element by element took 36 us: the
+      // whole launch waited for it); slabs start 16-byte aligned and tiles are 16 KB, so the vectors are aligned
+      const uint4 *pv = reinterpret_cast<const uint4 *>(in + first);
+      const unsigned nvec = (unsigned)((last - first) >> 1);
+      for (unsigned i0 = 0; i0 < nvec; i0 += 256) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const unsigned i = i0 + 32 * u + lane; v[u] = i < nvec ? __ldg(pv + i) : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (i0 + 32 * u + lane >= nvec) continue;
+          const unsigned long long a0 = (((unsigned long long)v[u].y << 32) | v[u].x) & 0x7FFFFFFFFFFFFFFFull;
+          const unsigned long long a1 = (((unsigned long long)v[u].w << 32) | v[u].z) & 0x7FFFFFFFFFFFFFFFull;
+          const unsigned h0 = (unsigned)(a0 >> 32), h1 = (unsigned)(a1 >> 32);
+          if (h0 == hx) bmax = a0 > bmax ? a0 : bmax;
+          if (h0 == hn) bmin = a0 < bmin ? a0 : bmin;
+          if (h1 == hx) bmax = a1 > bmax ? a1 : bmax;
+          if (h1 == hn) bmin = a1 < bmin ? a1 : bmin;
+        }
       }
     }
   }
@@ -1347,12 +1361,16 @@ __global__ void __launch_bounds__(256) k_qt_gather(const unsigned *__restrict__ 
   if (dropped) atomicAdd(&info->n_qt_dropped, (unsigned long long)dropped);
 }
 
+__constant__ int c_l2_hints;  // DCTZ_L2_HINTS: 1 = bin ids read with evict_last by the pre-pass, reconstruction stored with evict_first
+
 // Decompress pre-pass: number of 255 markers at positions j >= 1 per warp tile (32 blocks = 2 KB of bin ids).
 __global__ void __launch_bounds__(256) k_count_bins(const uint8_t *__restrict__ bins, unsigned long long nblk_full,
                                                     unsigned *__restrict__ counts, unsigned *done_counter, FusedScan fused) {
   const int lane = threadIdx.x & 31;
   const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
   const unsigned wpg = (gridDim.x * blockDim.x) >> 5;
+  const int hints = c_l2_hints;
+  const unsigned long long pol_last = policy_evict_last();
   // two tiles per warp and trip: eight independent 16-byte loads in flight per lane
   for (unsigned t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < ntiles; t += 2 * wpg) {
     uint4 v[2][4];
@@ -1368,7 +1386,7 @@ __global__ void __launch_bounds__(256) k_count_bins(const uint8_t *__restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const unsigned chunk = i * 32 + lane;  // 16-byte chunk of the tile; 4 chunks per block
-          v[h][i] = (chunk < rows[h] * 4u) ? __ldg(p + chunk) : make_uint4(0u, 0u, 0u, 0u);
+          v[h][i] = (chunk < rows[h] * 4u) ? (hints ? ldg_hint(p + chunk, pol_last) : __ldg(p + chunk)) : make_uint4(0u, 0u, 0u, 0u);
         }
       }
     }
@@ -1486,6 +1504,8 @@ struct ExtentRaw { unsigned long long gp, cp; unsigned c; unsigned k; };  // loa
 // Extents from the scan of the pre-pass (k_count_bins + k_scan_groups): offset of the first outlier = scanned group prefix
 // + the counts of the earlier tiles of its group; the size is the tile's count.
 struct ScannedExtents {
+  typedef ExtentRaw Raw;
+  static __device__ __forceinline__ Raw none() { Raw r; r.gp = 0; r.cp = 0; r.c = 0; r.k = 0; return r; }
   const unsigned *__restrict__ counts;
   const unsigned long long *__restrict__ group_prefix, *__restrict__ chunk_prefix;
   unsigned long long n_limit;
@@ -1498,8 +1518,11 @@ struct ScannedExtents {
     r.cp = __ldg(chunk_prefix + (t >> 15));  // prefix_of_group(), its addition left to finish()
     return r;
   }
-  __device__ __forceinline__ Extent finish(const ExtentRaw &r, int lane) const {
+  __device__ __forceinline__ Extent finish(ExtentRaw &r, int lane) const {
     Extent e;
+    r.c = pin_here(r.c);  // first use of the loaded values: here, at the end of the iteration
+    r.gp = pin_here(r.gp);
+    r.cp = pin_here(r.cp);
     e.total = __shfl_sync(0xFFFFFFFFu, r.c, (int)r.k);
     unsigned before = ((unsigned)lane < r.k) ? r.c : 0u;
 #pragma unroll
@@ -1513,13 +1536,207 @@ struct ScannedExtents {
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// Decompress WITHOUT the pre-pass (k_count_bins + k_scan_groups): every warp counts the markers of the tiles it is going to
+// process AHEAD tiles before it processes them -- 64 bytes of bin ids per lane, loaded at the top of an iteration and
+// counted at its end, with the evict_last hint so that the lines are still in L2 when the tile's bulk copy asks for them --
+// and PUBLISHES the count of every finished unit (a ticket's batch of tiles) in three levels:
+//     agg[u]      the unit's outliers                                   (flag bit 31 | count)
+//     S[u / 64]   sum over the group of 64 units, by atomic addition    (contributions << 48 | sum)
+//     T[u / 2048] sum over the super-group of 32 groups, likewise       (contributions << 48 | sum)
+// The offset of a unit's first outlier is then a pure READ: complete super-groups below it + complete groups of its
+// super-group below it + the units of its group below it -- five coalesced loads, no chain of waiting warps: nobody
+// waits for a prefix, only (and by then never in practice: the counts were published AHEAD tiles ago) for counts, and
+// counting never waits for anything.  Units are handed out in increasing order, so every unit below a ticketed one has an
+// owner that is resident and publishes it before it waits for anything itself: no deadlock.
+// The object is both the tile sequence (advance) and the extent source (load / finish) of decompress_tiles.
+// ------------------------------------------------------------------------------------------
+struct AheadBufs { unsigned *agg; unsigned long long *S, *T; };
+struct AheadRaw { uint4 v[4]; unsigned a0, a1; unsigned long long s, t; unsigned flags; };  // flags: 1 = tile to count, 2 = extent wanted
+__device__ __forceinline__ unsigned ld_volatile(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+struct AheadExtents {
+  typedef AheadRaw Raw;
+  static constexpr unsigned AHEAD = 10;  // tiles between the count cursor and the extent cursor (>= batch + 3)
+  static constexpr unsigned long long LOW48 = 0xFFFFFFFFFFFFull;
+  static __device__ __forceinline__ Raw none() {
+    Raw r;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.v[i] = make_uint4(0u, 0u, 0u, 0u);
+    r.a0 = r.a1 = 0x80000000u; r.s = r.t = 0ull; r.flags = 0u;
+    return r;
+  }
+  const uint8_t *bins;
+  unsigned long long nblk_full, n_limit, pol;
+  unsigned ntiles, batch, nunits, base;
+  AheadBufs b;
+  unsigned *corrupt_flag, *counter;
+  unsigned pend;                                       // lane 0: the ticket requested for the unit after the one being counted
+  unsigned c_start, c_off, c_sum, c_pos, c_units;      // count cursor: unit start, tile in unit, outliers so far, tiles / units so far
+  bool c_done;
+  unsigned ring_cnt, ring_start;                       // lane p & 31: outliers of the warp's p-th tile; lane k & 31: first tile of its k-th unit
+  unsigned p_unit, p_off;                              // process cursor (advance)
+  unsigned e_unit, e_off, e_pos, e_within;             // extent cursor (finish)
+  unsigned long long e_base;
+  unsigned t_upto;                                     // super-groups [0, t_upto) are complete and summed in t_sum
+  unsigned long long t_sum;
+
+  __device__ __forceinline__ void open_unit(unsigned start, int lane) {
+    c_start = start; c_off = 0; c_sum = 0;
+    if ((unsigned)lane == (c_units & 31u)) ring_start = start;
+    c_units++;
+    c_done = start >= ntiles;
+  }
+  __device__ __forceinline__ void load_count(Raw &r, int lane) const {
+    const unsigned t = c_start + c_off;
+    if (c_done || t >= ntiles) return;
+    r.flags |= 1u;
+    const unsigned long long first = (unsigned long long)t * WTILE;
+    const unsigned rows = (nblk_full - first < (unsigned long long)WTILE) ? (unsigned)(nblk_full - first) : (unsigned)WTILE;
+    const uint4 *p = reinterpret_cast<const uint4 *>(bins + first * BLK);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const unsigned chunk = i * 32 + lane;  // 16-byte chunk of the tile; 4 chunks per block
+      r.v[i] = (chunk < rows * 4u) ? ldg_hint(p + chunk, pol) : make_uint4(0u, 0u, 0u, 0u);  // (zero words hold no marker)
+    }
+  }
+  __device__ __forceinline__ void finish_count(const Raw &r, int lane) {
+    if (!(r.flags & 1u)) return;
+    unsigned cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const unsigned chunk = i * 32 + lane;
+      const unsigned x0 = (chunk & 3u) ? r.v[i].x : (r.v[i].x & 0xFFFFFF00u);  // byte 0 of a block is the DC marker
+      cnt += __popc(ff_bytes(x0)) + __popc(ff_bytes(r.v[i].y)) + __popc(ff_bytes(r.v[i].z)) + __popc(ff_bytes(r.v[i].w));
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if ((unsigned)lane == (c_pos & 31u)) ring_cnt = cnt;
+    c_sum += cnt; c_pos++; c_off++;
+    if (c_off == batch || c_start + c_off >= ntiles) {  // the unit is counted: publish it, open the next one
+      const unsigned u = c_start / batch;
+      if (lane == 0) {
+        asm volatile("st.volatile.global.u32 [%0], %1;\n" ::"l"(b.agg + u), "r"(0x80000000u | c_sum) : "memory");
+        const unsigned long long contrib = (1ull << 48) | (unsigned long long)c_sum;
+        atomicAdd(b.S + (u >> 6), contrib);
+        atomicAdd(b.T + (u >> 11), contrib);
+      }
+      const unsigned start = (base + __shfl_sync(0xFFFFFFFFu, pin_here(pend), 0)) * batch;
+      if (lane == 0) pend = ticket_next(counter);
+      open_unit(start, lane);
+    }
+  }
+  __device__ __forceinline__ void init(const uint8_t *bins_, unsigned long long nblk_full_, unsigned ntiles_, unsigned batch_, AheadBufs bufs,
+                                       unsigned long long n_limit_, unsigned *corrupt_flag_, unsigned *ticket_counter, unsigned warp_global,
+                                       unsigned nwarps_grid, int lane) {
+    bins = bins_; nblk_full = nblk_full_; ntiles = ntiles_; batch = batch_; nunits = (ntiles_ + batch_ - 1) / batch_; b = bufs;
+    n_limit = n_limit_; corrupt_flag = corrupt_flag_; counter = ticket_counter; base = 0u;
+    (void)warp_global; (void)nwarps_grid;
+    pol = policy_evict_last();
+    pend = 0; c_pos = 0; c_units = 0; ring_cnt = 0; ring_start = 0xFFFFFFFFu;
+    p_unit = 0; p_off = 0; e_unit = 0; e_off = 0; e_pos = 0; e_within = 0; e_base = 0ull; t_upto = 0; t_sum = 0ull;
+    // EVERY unit comes from the ticket counter, the first one too: a unit below a ticketed one then belongs to a warp that
+    // is running (a statically assigned first unit could belong to a CTA that is not resident yet -- two such kernels of two
+    // contexts sharing the device would wait for each other's missing CTAs for ever)
+    if (lane == 0) pend = ticket_next(counter);
+    {
+      const unsigned start = __shfl_sync(0xFFFFFFFFu, pin_here(pend), 0) * batch;
+      if (lane == 0) pend = ticket_next(counter);
+      open_unit(start, lane);
+    }
+    for (unsigned i = 0; i < AHEAD; i++) {  // (latency exposed AHEAD times, once per warp and launch)
+      Raw r = none();
+      load_count(r, lane);
+      finish_count(r, lane);
+    }
+  }
+  __device__ __forceinline__ unsigned advance(int) {  // warp-uniform: the next tile to process
+    const unsigned st = __shfl_sync(0xFFFFFFFFu, ring_start, (int)(p_unit & 31u));
+    if (st >= ntiles) return 0xFFFFFFFFu;
+    const unsigned t = st + p_off;
+    if (t >= ntiles) return 0xFFFFFFFFu;
+    if (++p_off == batch) { p_off = 0; p_unit++; }
+    return t;
+  }
+  // what unit u's offset needs: lanes hold the units of its group below it, the groups of its super-group below its
+  // group, and a window of the not yet summed super-groups below its super-group
+  __device__ __forceinline__ void load_lookback(Raw &r, unsigned u, unsigned w0, int lane) const {
+    const unsigned g = u >> 6, h = u >> 11;
+    const unsigned i0 = (g << 6) + (unsigned)lane, i1 = i0 + 32u, gi = (h << 5) + (unsigned)lane, wi = w0 + (unsigned)lane;
+    r.a0 = (i0 < u) ? ld_volatile(b.agg + i0) : 0x80000000u;
+    r.a1 = (i1 < u) ? ld_volatile(b.agg + i1) : 0x80000000u;
+    r.s = (gi < g) ? ld_volatile(b.S + gi) : 0ull;
+    r.t = (wi < h) ? ld_volatile(b.T + wi) : 0ull;
+  }
+  __device__ __forceinline__ bool lookback_complete(const Raw &r, unsigned u, unsigned w0, int lane) const {
+    const unsigned g = u >> 6, h = u >> 11;
+    const unsigned gi = (h << 5) + (unsigned)lane, wi = w0 + (unsigned)lane;
+    bool ok = (r.a0 >> 31) && (r.a1 >> 31);
+    if (gi < g) { const unsigned want = nunits - (gi << 6) < 64u ? nunits - (gi << 6) : 64u; ok = ok && (unsigned)(r.s >> 48) == want; }
+    if (wi < h) { const unsigned want = nunits - (wi << 11) < 2048u ? nunits - (wi << 11) : 2048u; ok = ok && (unsigned)(r.t >> 48) == want; }
+    return __all_sync(0xFFFFFFFFu, ok);
+  }
+  __device__ __forceinline__ Raw load(unsigned /*nn: the tile whose extent the matching finish() returns*/, int lane) const {
+    Raw r = none();
+    r.flags = 2u;
+    load_count(r, lane);
+    if (e_off == 0) {  // its extent starts a unit: the unit's offset is looked up
+      const unsigned u = __shfl_sync(0xFFFFFFFFu, ring_start, (int)(e_unit & 31u)) / batch;
+      load_lookback(r, u, t_upto, lane);
+    }
+    return r;
+  }
+  __device__ __forceinline__ Extent finish(Raw &r, int lane) {
+    finish_count(r, lane);
+    Extent e;
+    e.base = 0; e.total = 0; e.bad = false;
+    if (!(r.flags & 2u)) return e;
+    if (e_off == 0) {
+      const unsigned u = __shfl_sync(0xFFFFFFFFu, ring_start, (int)(e_unit & 31u)) / batch;
+      const unsigned h = u >> 11;
+      for (;;) {  // (complete at the first look unless a warp has fallen AHEAD tiles behind the others)
+        while (!lookback_complete(r, u, t_upto, lane)) load_lookback(r, u, t_upto, lane);
+        if (t_upto + 32u >= h) break;
+        t_sum += warp_sum_u64(r.t & LOW48);  // more than 32 new super-groups (a very large slab's first look): next window
+        t_upto += 32u;
+        load_lookback(r, u, t_upto, lane);
+      }
+      t_sum += warp_sum_u64(r.t & LOW48);
+      t_upto = h;
+      const unsigned within = __reduce_add_sync(0xFFFFFFFFu, (r.a0 & 0x7FFFFFFFu) + (r.a1 & 0x7FFFFFFFu));
+      e_base = t_sum + warp_sum_u64(r.s & LOW48) + within;
+      e_within = 0;
+    }
+    e.total = __shfl_sync(0xFFFFFFFFu, ring_cnt, (int)(e_pos & 31u));
+    e.base = e_base + e_within;
+    e_within += e.total;
+    e_pos++;
+    if (++e_off == batch) { e_off = 0; e_unit++; }
+    e.bad = e.base + e.total > n_limit;
+    if (e.bad) { e.total = 0u; *corrupt_flag = 1u; }
+    return e;
+  }
+};
+
 // The tile loop of the decompress kernels: one warp, tiles handed out by `seq`, outlier extents by `ext`.
 template <typename T, bool QT, class Seq, class Ext>
 __device__ __forceinline__ void decompress_tiles(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, const float *__restrict__ ac_in,
                                                  unsigned long long nblk_full, T sf, const QtConsts<T> &qk, const CUtensorMap *tmap_out,
                                                  unsigned long long n_ac /* end of the readable part of AC_exact */, int dc_aligned16,
-                                                 unsigned char *wsm, unsigned mb, const T *center, const T *s_qt, Seq &seq, const Ext &ext,
-                                                 int lane, unsigned &phase) {
+                                                 unsigned char *wsm, unsigned mb, const T *center, const T *s_qt, Seq &seq, Ext &ext,
+                                                 int lane, unsigned &phase, int l2_hints = 0) {
   typedef typename ArithOf<T>::type A;
   typedef DecompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
@@ -1529,6 +1746,9 @@ __device__ __forceinline__ void decompress_tiles(const uint8_t *__restrict__ bin
   unsigned char *binbuf = wsm + Cfg::OFF_BINS;
   float *dcbuf = reinterpret_cast<float *>(wsm + Cfg::OFF_DC);
   const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
+  // l2_hints: bit 0 = the reconstruction is stored with evict_first, bit 1 = the bin ids are fetched with evict_first (both
+  // so that lines somebody still needs -- the bin ids the count-ahead path has touched -- outlive the streaming traffic)
+  const unsigned long long pol_first = policy_evict_first();
   auto rows_of = [&](unsigned t) -> unsigned {
     const unsigned long long left = nblk_full - (unsigned long long)t * WTILE;
     return left < (unsigned long long)WTILE ? (unsigned)left : (unsigned)WTILE;
@@ -1567,7 +1787,8 @@ __device__ __forceinline__ void decompress_tiles(const uint8_t *__restrict__ bin
     }
     if (lane == 0) {
       mbar_expect_tx(mb, rows * BLK + (dc_bulk ? WTILE * 4 : 0) + (k1 - k0) * 4u);
-      bulk_g2s(smem_u32(binbuf), bins + (unsigned long long)t * WTILE * BLK, rows * BLK, mb);
+      if (l2_hints & 2) bulk_g2s_hint(smem_u32(binbuf), bins + (unsigned long long)t * WTILE * BLK, rows * BLK, mb, pol_first);
+      else bulk_g2s(smem_u32(binbuf), bins + (unsigned long long)t * WTILE * BLK, rows * BLK, mb);
       if (dc_bulk) bulk_g2s(smem_u32(dcbuf), dc_in + (unsigned long long)t * WTILE, WTILE * 4, mb);
       if (k1 > k0) bulk_g2s(smem_u32(stage) + (pl.fofs + k0) * 4u, ac_in + e.base + k0 - pl.lead, (k1 - k0) * 4u, mb);
     }
@@ -1591,12 +1812,11 @@ __device__ __forceinline__ void decompress_tiles(const uint8_t *__restrict__ bin
   Extent ext_cur, ext_nxt;
   ext_cur.base = 0; ext_cur.total = 0; ext_cur.bad = false;
   ext_nxt = ext_cur;
-  if (cur < ntiles) { ext_cur = ext.finish(ext.load(cur, lane), lane); park_ragged(issue_tile(cur, ext_cur)); }
-  if (nxt < ntiles) ext_nxt = ext.finish(ext.load(nxt, lane), lane);
+  if (cur < ntiles) { typename Ext::Raw r0 = ext.load(cur, lane); ext_cur = ext.finish(r0, lane); park_ragged(issue_tile(cur, ext_cur)); }
+  if (nxt < ntiles) { typename Ext::Raw r1 = ext.load(nxt, lane); ext_nxt = ext.finish(r1, lane); }
 
   while (cur < ntiles) {
-    ExtentRaw raw_nn;
-    raw_nn.gp = 0; raw_nn.cp = 0; raw_nn.c = 0; raw_nn.k = 0;
+    typename Ext::Raw raw_nn = Ext::none();
     if (nn < ntiles) raw_nn = ext.load(nn, lane);  // loads in flight for the whole iteration
     const unsigned rows = rows_of(cur);
     const unsigned long long blk = (unsigned long long)cur * WTILE + lane;
@@ -1771,30 +1991,36 @@ __device__ __forceinline__ void decompress_tiles(const uint8_t *__restrict__ bin
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
+      if (l2_hints & 1) {
 #pragma unroll
-      for (int q = 0; q < L::SLABS; q++) tma_store_2d(tmap_out, q * 128, (int)(cur * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES);
+        for (int q = 0; q < L::SLABS; q++) tma_store_2d_hint(tmap_out, q * 128, (int)(cur * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES, pol_first);
+      } else {
+#pragma unroll
+        for (int q = 0; q < L::SLABS; q++) tma_store_2d(tmap_out, q * 128, (int)(cur * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES);
+      }
       bulk_commit();
     }
     park_ragged(rag);
     cur = nxt;
     ext_cur = ext_nxt;
     nxt = nn;
-    raw_nn.c = pin_here(raw_nn.c);
-    raw_nn.gp = pin_here(raw_nn.gp);
-    raw_nn.cp = pin_here(raw_nn.cp);
     ext_nxt = ext.finish(raw_nn, lane);
     nn = seq.advance(lane);
   }
 }
 
-template <typename T, bool QT>
+// AHEAD = false: extents from the pre-pass (k_count_bins + k_scan_groups).  AHEAD = true: no pre-pass, the warps count
+// ahead and look the offsets up (AheadExtents); `counts` / `group_prefix` / `chunk_prefix` then carry AheadBufs' agg / S / T
+// (zeroed by the host before the launch) and the last CTA writes the number of outliers the full blocks hold to
+// `n_outliers_total` (the tail block's offset).
+template <typename T, bool QT, bool AHEAD>
 __global__ void __launch_bounds__(DecompressCfg<T, QT>::THREADS, DecompressCfg<T, QT>::CTAS_PER_SM)
 k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, const float *__restrict__ ac_in,
              const T *__restrict__ qtable, unsigned long long nblk_full, T bin_width, T sf, QtConsts<T> qk,
-             const __grid_constant__ CUtensorMap tmap_out, const unsigned *__restrict__ counts,
-             const unsigned long long *__restrict__ group_prefix, const unsigned long long *__restrict__ chunk_prefix,
-             const unsigned long long *__restrict__ n_outliers_total, unsigned long long n_limit, TileControl *ctl,
-             unsigned *corrupt_flag, int dc_aligned16, unsigned batch) {
+             const __grid_constant__ CUtensorMap tmap_out, unsigned *counts,
+             unsigned long long *group_prefix, unsigned long long *chunk_prefix,
+             unsigned long long *n_outliers_total, unsigned long long n_limit, TileControl *ctl,
+             unsigned *corrupt_flag, int dc_aligned16, unsigned batch, int l2_hints) {
   typedef DecompressCfg<T, QT> Cfg;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
@@ -1820,23 +2046,49 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
   if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
   __syncthreads();  // the only CTA-wide barrier before the epilogue
 
-  const unsigned long long n_scan = __ldg(n_outliers_total);
-  ScannedExtents ext;
-  ext.counts = counts; ext.group_prefix = group_prefix; ext.chunk_prefix = chunk_prefix; ext.n_limit = n_limit; ext.corrupt_flag = corrupt_flag;
-  TileSeq seq;
-  seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
   unsigned phase = 0;
-  decompress_tiles<T, QT>(bins, dc_in, ac_in, nblk_full, sf, qk, &tmap_out, n_scan < n_limit ? n_scan : n_limit, dc_aligned16, wsm, mb, center, s_qt,
-                          seq, ext, lane, phase);
-  bulk_wait_all();
-  // every warp still has one look-ahead ticket request outstanding (TileSeq::advance): its result is consumed here, so
-  // the increment has been performed before this thread's fence and therefore before the last CTA resets the counter
-  if (lane == 0) (void)pin_here(seq.pend);
+  if constexpr (AHEAD) {
+    AheadExtents ah;
+    AheadBufs ab;
+    ab.agg = counts; ab.S = group_prefix; ab.T = chunk_prefix;
+    const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
+    ah.init(bins, nblk_full, ntiles, batch, ab, n_limit, corrupt_flag, &ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, lane);
+    decompress_tiles<T, QT>(bins, dc_in, ac_in, nblk_full, sf, qk, &tmap_out, n_limit, dc_aligned16, wsm, mb, center, s_qt, ah, ah, lane, phase,
+                            l2_hints);
+    bulk_wait_all();
+    if (lane == 0) (void)pin_here(ah.pend);  // (as below)
+  } else {
+    const unsigned long long n_scan = __ldg(n_outliers_total);
+    ScannedExtents ext;
+    ext.counts = counts; ext.group_prefix = group_prefix; ext.chunk_prefix = chunk_prefix; ext.n_limit = n_limit; ext.corrupt_flag = corrupt_flag;
+    TileSeq seq;
+    seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
+    decompress_tiles<T, QT>(bins, dc_in, ac_in, nblk_full, sf, qk, &tmap_out, n_scan < n_limit ? n_scan : n_limit, dc_aligned16, wsm, mb, center,
+                            s_qt, seq, ext, lane, phase, l2_hints);
+    bulk_wait_all();
+    // every warp still has one look-ahead ticket request outstanding (TileSeq::advance): its result is consumed here, so
+    // the increment has been performed before this thread's fence and therefore before the last CTA resets the counter
+    if (lane == 0) (void)pin_here(seq.pend);
+  }
   __threadfence();
   __syncthreads();
+  __shared__ bool s_last;
   if (threadIdx.x == 0) {
     const unsigned prev = atomicAdd(&ctl->done, 1u);
-    if (prev == gridDim.x - 1) { ctl->ticket = 0u; ctl->done = 0u; }
+    s_last = (prev == gridDim.x - 1);
+    if (s_last) { ctl->ticket = 0u; ctl->done = 0u; }
+  }
+  if constexpr (AHEAD) {
+    __syncthreads();
+    if (s_last && warp == 0) {  // every unit has been published: the full blocks' outliers = the sum over the super-groups
+      __threadfence();
+      const unsigned ntiles = (unsigned)((nblk_full + WTILE - 1) / WTILE);
+      const unsigned nunits = (ntiles + batch - 1) / batch, nsuper = (nunits + 2047u) >> 11;
+      unsigned long long tot = 0ull;
+      for (unsigned w = lane; w < nsuper; w += 32) tot += ld_volatile(chunk_prefix + w) & AheadExtents::LOW48;
+      tot = warp_sum_u64(tot);
+      if (lane == 0) *n_outliers_total = tot;
+    }
   }
 }
 

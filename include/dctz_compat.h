@@ -87,6 +87,8 @@ void dctz_large_set_piece(size_t elements);
 size_t dctz_host_deflate(const void *src, size_t n, void *dst, size_t cap);
 /* the same while the section arrives in pieces (what dctz_compress does with the GPU's downloads); byte-identical */
 size_t dctz_host_deflate_streamed(const void *src, size_t n, void *dst, size_t cap, size_t piece);
+/* the same for stream section `section` (0 bin_index, 1 DC, 2 AC_exact; the float sections are cut into smaller chunks) */
+size_t dctz_host_deflate_section(const void *src, size_t n, void *dst, size_t cap, int section, size_t piece);
 
 #ifdef __cplusplus
 }

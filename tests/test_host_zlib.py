@@ -77,3 +77,28 @@ def test_streamed_deflate_is_byte_identical(n, piece):
     m = lib.dctz_host_deflate_streamed(src, n, out, cap, piece)
     assert m > 0 and out.raw[:m] == _deflate(data)
     assert zlib.decompress(out.raw[:m]) == data
+
+
+@pytest.mark.parametrize("section", [1, 2])
+@pytest.mark.parametrize("n,piece", [(0, 0), (300000, 0), ((1 << 21) + 4, 0), (9 << 20, 0), (9 << 20, 1 << 20), ((8 << 20) + 12, 700000)])
+def test_float_sections_use_small_chunks_and_stay_one_stream(section, n, piece):
+    """DC / AC_exact (float data, slow to deflate) are cut into 128 KiB chunks: still ONE valid zlib stream, the same bytes
+    whether the section is deflated whole or while it arrives, and close to the serial size."""
+    lib = _lib()
+    lib.dctz_host_deflate_section.restype = C.c_size_t
+    lib.dctz_host_deflate_section.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t]
+    rng = np.random.default_rng(17)
+    data = (np.cumsum(rng.standard_normal(n // 4)) * 0.01).astype(np.float32).tobytes()
+    n = len(data)
+    cap = n + n // 8 + 4096
+    src = C.create_string_buffer(data, n) if n else C.create_string_buffer(1)
+    out = C.create_string_buffer(cap)
+    m = lib.dctz_host_deflate_section(src, n, out, cap, section, piece)
+    assert m > 0
+    z = out.raw[:m]
+    d = zlib.decompressobj()
+    assert d.decompress(z) == data and d.eof and d.unused_data == b""
+    whole = C.create_string_buffer(cap)
+    mw = lib.dctz_host_deflate_section(src, n, whole, cap, section, 0)
+    assert whole.raw[:mw] == z
+    assert m <= len(zlib.compress(data, -1)) * 1.01 + 64
