@@ -384,6 +384,9 @@ template <> struct Quantizer<double> {
   // outliers are stored as float (USE_TRUNCATE): c_u * RN(1/sf) differs from c_u / sf by at most one double ulp,
   // i.e. the float it rounds to differs with probability ~2^-29 -- one multiply instead of the division sequence
   __device__ __forceinline__ float outlier(double c_u) const { return (float)__dmul_rn(c_u, sfdiv.y); }
+  // candidate parking of the sparse emission path: what goes into the float-sized candidate array, and what comes out
+  __device__ __forceinline__ float park(double c_u) const { return outlier(c_u); }
+  __device__ __forceinline__ float unpark(float v) const { return v; }
   __device__ __forceinline__ unsigned quantize(double c_u) const {
     const double v = __fma_rn(c_u, kq, 127.5);
     const double z = __dadd_rd(v, 6442450944.0 /* 1.5 * 2^32 */);  // ROUND DOWN: the 2^-20 grid must not round v up past an integer
@@ -402,6 +405,10 @@ template <> struct Quantizer<float> {
   }
   __device__ __forceinline__ float scaled(float c_u) const { return div_exact(c_u, sfdiv); }
   __device__ __forceinline__ float outlier(float c_u) const { return div_exact(c_u, sfdiv); }
+  // float: the RAW coefficient is parked (no arithmetic for the 60 coefficients that are no outliers); the exact division
+  // is done for the few that are picked up
+  __device__ __forceinline__ float park(float c_u) const { return c_u; }
+  __device__ __forceinline__ float unpark(float v) const { return div_exact(v, sfdiv); }
   __device__ __forceinline__ unsigned quantize(float c_u) const {
     const int t = __float2int_rd(__fmaf_rn(c_u, kq, 127.5f));
     const int b = (int)(2u * min((unsigned)t, 255u)) - 255;  // negative t wraps to a huge unsigned -> 255
@@ -701,8 +708,20 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
         // by hand -- the compiler turns the plain `if` into 63 divergent branches.
         T *praw = raw_slots + (unsigned long long)cur * TILE_SLOT + my_off;
         uint8_t *pj = j_slots + (unsigned long long)cur * TILE_SLOT + my_off;
+        // (coefficient positions in groups of eight: a group in which no block of the tile has an outlier -- the high
+        // frequencies of a smooth field -- is skipped by a warp-uniform branch)
 #pragma unroll
-        for (int j = 1; j < BLK; j++) park_if(praw, pj, x[j], (unsigned)j, (j < 32 ? mlo >> j : mhi >> (j - 32)) & 1u);
+        for (int g = 0; g < 8; g++) {
+          const unsigned mg = ((g < 4) ? (mlo >> (8 * g)) : (mhi >> (8 * (g - 4)))) & 0xFFu;
+          if (__any_sync(FULL, mg != 0u)) {
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+              const int j = 8 * g + b;
+              if (j == 0) continue;
+              park_if(praw, pj, x[j], (unsigned)j, (mg >> b) & 1u);
+            }
+          }
+        }
       } else {
         // Uniform, branch-free part: every lane parks all 63 scaled AC coefficients as float (:537, USE_TRUNCATE) in
         // its own column of the candidate array (conflict-free; register indices stay compile-time).  Then a short
@@ -715,8 +734,16 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
           float *tile_run = ac_slots + (unsigned long long)cur * TILE_SLOT;  // warp-uniform base, 32-bit lane offsets
           unsigned off = my_off;
 #pragma unroll
-          for (int j = 1; j < BLK; j++) {
-            if ((j < 32 ? mlo >> j : mhi >> (j - 32)) & 1u) tile_run[off++] = qz.outlier(x[j]);
+          for (int g = 0; g < 8; g++) {  // (groups of eight positions; an empty group is skipped warp-uniformly, see the QT branch)
+            const unsigned mg = ((g < 4) ? (mlo >> (8 * g)) : (mhi >> (8 * (g - 4)))) & 0xFFu;
+            if (__any_sync(FULL, mg != 0u)) {
+#pragma unroll
+              for (int b = 0; b < 8; b++) {
+                const int j = 8 * g + b;
+                if (j == 0) continue;
+                if ((mg >> b) & 1u) tile_run[off++] = qz.outlier(x[j]);
+              }
+            }
           }
           cur = nxt;
           nxt = seq.advance(lane);
@@ -724,7 +751,7 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
         }
         float *cand = reinterpret_cast<float *>(wsm + Cfg::OFF_CAND) + lane;
 #pragma unroll
-        for (int j = 1; j < BLK; j++) cand[(j - 1) * WTILE] = qz.outlier(x[j]);
+        for (int j = 1; j < BLK; j++) cand[(j - 1) * WTILE] = qz.park(x[j]);
         // two independent chains per trip: the lowest remaining position goes to the front of the run, the highest
         // to its back
         const unsigned trips = (maxcnt + 1u) >> 1;
@@ -732,12 +759,12 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
         for (unsigned it = 0; it < trips; it++) {
           if (mlo | mhi) {
             const int j = mlo ? (__ffs(mlo) - 1) : (31 + __ffs(mhi));
-            *lo++ = cand[(j - 1) * WTILE];
+            *lo++ = qz.unpark(cand[(j - 1) * WTILE]);
             if (mlo) mlo &= mlo - 1u; else mhi &= mhi - 1u;
           }
           if (mlo | mhi) {
             const int j = mhi ? (63 - __clz(mhi)) : (31 - __clz(mlo));
-            *--hi = cand[(j - 1) * WTILE];
+            *--hi = qz.unpark(cand[(j - 1) * WTILE]);
             if (mhi) mhi &= ~(1u << (j - 32)); else mlo &= ~(1u << j);
           }
         }
