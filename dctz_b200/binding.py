@@ -20,7 +20,7 @@ EXPORTS = [
     "dctz_gpu_host_alloc", "dctz_gpu_host_free", "dctz_gpu_compress_core", "dctz_gpu_decompress_core", "dctz_gpu_stats",
     "dctz_gpu_compress_core_with_stats", "dctz_gpu_quality", "dctz_gpu_quality_dev",
     "dctz_gpu_stats_dev", "dctz_gpu_compress_dev", "dctz_gpu_compress_known_stats_dev", "dctz_gpu_qt_finish_dev", "dctz_gpu_compress_field_dev",
-    "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_dct64_dev", "dctz_gpu_fill_hash_field",
+    "dctz_gpu_decompress_dev", "dctz_gpu_scale_dev", "dctz_gpu_dct_blocks", "dctz_gpu_dct64_dev", "dctz_gpu_fp64_rate", "dctz_gpu_fill_hash_field",
     "dctz_gpu_sf_from_max", "dctz_gpu_selftest_division", "dctz_gpu_launch_count", "dctz_gpu_compress_core_cb",
     "dctz_gpu_set_timing", "dctz_gpu_last_call_stats", "dctz_gpu_fused_phase_times", "dctz_gpu_compress_slab_comm",
     "dctz_gpu_sample_dev", "dctz_gpu_compress_spec_dev", "dctz_gpu_compress_spec_finish_dev",
@@ -81,6 +81,7 @@ def load_library():
         "dctz_gpu_scale_dev": (i32, [vp, vp, sz, i32, dbl, i32, vp]),
         "dctz_gpu_dct_blocks": (i32, [vp, vp, vp, sz, i32, i32, i32]),
         "dctz_gpu_dct64_dev": (i32, [vp, vp, vp, sz, i32, i32, i32, vp]),
+        "dctz_gpu_fp64_rate": (i32, [vp, i32, vp]),
         "dctz_gpu_fill_hash_field": (i32, [vp, vp, u64, u64, C.c_uint32, C.c_uint32, vp]),
         "dctz_gpu_sf_from_max": (dbl, [vp, dbl, i32]),
         "dctz_gpu_selftest_division": (i32, [vp, i32, dbl, u64, C.c_uint32, C.POINTER(u64)]),
@@ -334,6 +335,12 @@ class Context:
 
     def scale_dev(self, d_x, n, code, sf, multiply, stream=0):
         self._check(self._lib.dctz_gpu_scale_dev(self._h, d_x, n, code, float(sf), int(bool(multiply)), stream or None))
+
+    def fp64_rate(self, kind):
+        """measured FP64 rate in TFLOP/s: kind 0 = DFMA on the vector pipe, 1 = DMMA m8n8k4 on the tensor pipe"""
+        v = C.c_double(0.0)
+        self._check(self._lib.dctz_gpu_fp64_rate(self._h, int(kind), C.byref(v)))
+        return v.value
 
     def dct64_dev(self, d_in, d_out, nblocks, code, inverse=False, variant=0, stream=0):
         self._check(self._lib.dctz_gpu_dct64_dev(self._h, d_in, d_out, int(nblocks), code, int(bool(inverse)), int(variant), stream or None))

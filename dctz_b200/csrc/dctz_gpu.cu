@@ -200,6 +200,7 @@ struct dctz_gpu_ctx {
   // buffers of the host-buffer API
   DevBuf in, bins, dc, ac, qt, qtraw, out;
   double *d_dfrag[2] = {nullptr, nullptr};  // DMMA A-fragments of the DCT matrix (forward, inverse)
+  double *d_dfrag2[2] = {nullptr, nullptr}; // ... of its even / odd halves (k_dct64_dmma_split)
   int occ[2][2][2] = {};  // resident CTAs/SM per [kernel][datatype][qt]
   int occ_ahead[2][2] = {};  // ... of the count-ahead decompress kernel [datatype][qt]
   int decomp_ahead = 0;      // DCTZ_DECOMP_AHEAD=1: streaming decompress without the pre-pass (measured: the second read of the bin ids disappears, the kernel gets slower by as much -- DESIGN.md)
@@ -341,6 +342,7 @@ extern "C" void dctz_gpu_destroy(dctz_gpu_ctx *ctx) {
                     &ctx->qt, &ctx->qtraw, &ctx->out};
   for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
   for (double *p : ctx->d_dfrag) if (p) cudaFree(p);
+  for (double *p : ctx->d_dfrag2) if (p) cudaFree(p);
   if (ctx->chunk_stats.p) cudaFree(ctx->chunk_stats.p);
   if (ctx->ahead_buf.p) cudaFree(ctx->ahead_buf.p);
   delete ctx->pool;
@@ -1652,11 +1654,53 @@ static int ensure_dfrag(dctz_gpu_ctx *ctx, int inverse) {
   return DCTZ_GPU_OK;
 }
 
+static int ensure_dfrag_split(dctz_gpu_ctx *ctx, int inverse) {
+  if (ctx->d_dfrag2[inverse]) return DCTZ_GPU_OK;
+  std::vector<double> f(2 * 32 * 32);
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int m = 0; m < 2; m++)
+    for (int i = 0; i < 4; i++)
+      for (int s = 0; s < 8; s++)
+        for (int lane = 0; lane < 32; lane++) {
+          const int row = 8 * i + lane / 4, col = 4 * s + lane % 4;
+          const int kh = inverse ? col : row, n = inverse ? row : col;  // forward: M_m[kh][n] = C[2 kh + m][n]; inverse: transposed
+          const int k = 2 * kh + m;
+          long double v = sqrtl(2.0L / BLK) * cosl(pi * (long double)(((2 * n + 1) * k) % (4 * BLK)) / (2.0L * BLK));
+          if (k == 0) v /= sqrtl(2.0L);
+          f[(size_t)m * 1024 + (i * 8 + s) * 32 + lane] = (double)v;
+        }
+  CU(cudaMalloc(&ctx->d_dfrag2[inverse], f.size() * sizeof(double)));
+  CU(cudaMemcpy(ctx->d_dfrag2[inverse], f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return DCTZ_GPU_OK;
+}
+
+// FP64 rate probes: kind 0 = DFMA (vector pipe), 1 = DMMA m8n8k4 (tensor pipe); *tflops = the measured rate.
+extern "C" int dctz_gpu_fp64_rate(dctz_gpu_ctx *ctx, int kind, double *tflops) {
+  if (!ctx || !tflops || kind < 0 || kind > 1) return fail(ctx, DCTZ_GPU_EINVAL, "fp64_rate: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const int iters = 4096, grid = ctx->sm_count * 8;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  k_fp64_rate<<<grid, 256, 0, ctx->stream>>>(kind, 64, 1.0, ctx->d_stats3);  // warm-up
+  CU(cudaEventRecord(e0, ctx->stream));
+  k_fp64_rate<<<grid, 256, 0, ctx->stream>>>(kind, iters, 1.0, ctx->d_stats3);
+  CU(cudaEventRecord(e1, ctx->stream));
+  CU(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  ctx->launches += 2;
+  // kind 0: 32 DFMA per thread and iteration = 64 flop; kind 1: 32 DMMA per WARP and iteration, 8*8*4*2 = 512 flop each
+  const double flop = kind == 0 ? (double)grid * 256 * iters * 64.0 : (double)grid * 8 * iters * 32.0 * 512.0;
+  *tflops = flop / (ms * 1e-3) / 1e12;
+  return DCTZ_GPU_OK;
+}
+
 extern "C" int dctz_gpu_dct64_dev(dctz_gpu_ctx *ctx, const void *d_in, void *d_out, size_t nblocks, int datatype, int inverse, int variant,
                                   void *stream) {
   TRY(check_common(ctx, datatype, 1.0));
   if (!d_in || !d_out || nblocks == 0 || !aligned16(d_in) || !aligned16(d_out)) return fail(ctx, DCTZ_GPU_EINVAL, "dct64_dev: bad pointers");
-  if (variant != 0 && !(variant == 1 && datatype == DCTZ_GPU_DOUBLE)) return fail(ctx, DCTZ_GPU_EINVAL, "dct64_dev: variant %d not available for this type", variant);
+  if (variant != 0 && !((variant == 1 || variant == 2) && datatype == DCTZ_GPU_DOUBLE)) return fail(ctx, DCTZ_GPU_EINVAL, "dct64_dev: variant %d not available for this type", variant);
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t es = datatype == DCTZ_GPU_DOUBLE ? 8 : 4;
@@ -1666,7 +1710,12 @@ extern "C" int dctz_gpu_dct64_dev(dctz_gpu_ctx *ctx, const void *d_in, void *d_o
   const size_t ntiles = (nblocks + WTILE - 1) / WTILE, ctas = (ntiles + 3) / 4;
   const size_t resident = (size_t)ctx->sm_count * (datatype == DCTZ_GPU_DOUBLE ? 2 : 3);
   const int grid = (int)(ctas < resident ? ctas : resident);
-  if (variant == 1) {
+  if (variant == 2) {
+    TRY(ensure_dfrag_split(ctx, inverse ? 1 : 0));
+    auto k = inverse ? k_dct64_dmma_split<true> : k_dct64_dmma_split<false>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DctOnlyCfg<double>::SMEM));
+    k<<<grid, DctOnlyCfg<double>::THREADS, DctOnlyCfg<double>::SMEM, st>>>(tin, tout, nblocks, ctx->d_dfrag2[inverse ? 1 : 0]);
+  } else if (variant == 1) {
     TRY(ensure_dfrag(ctx, inverse ? 1 : 0));
     CU(cudaFuncSetAttribute(k_dct64_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, DctOnlyCfg<double>::SMEM));
     k_dct64_dmma<<<grid, DctOnlyCfg<double>::THREADS, DctOnlyCfg<double>::SMEM, st>>>(tin, tout, nblocks, ctx->d_dfrag[inverse ? 1 : 0]);

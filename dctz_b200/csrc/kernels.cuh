@@ -2343,6 +2343,126 @@ k_dct64_dmma(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
   bulk_wait_all();
 }
 
+// The matrix form with the even/odd split: x -> (s, d) = (x[i] + x[63-i], x[i] - x[63-i]), i < 32; the even coefficients are
+// a 32x32 matrix times s, the odd ones a 32x32 matrix times d (the rows of the DCT-II matrix are symmetric / antisymmetric
+// about the middle): 64 instead of 128 flop per element, 256 instead of 512 DMMA per tile.  Inverse: u = E^T X_even,
+// v = O^T X_odd, x[i] = u[i] + v[i], x[63-i] = u[i] - v[i].
+// dfrag2[m][(i*8 + s)*32 + lane] = M_m[8i + lane/4][4s + lane%4]; forward: M_0[k][i] = C[2k][i], M_1[k][i] = C[2k+1][i]
+// (C = orthonormal DCT-II matrix); inverse: their transposes.
+template <bool INVERSE>
+__global__ void __launch_bounds__(DctOnlyCfg<double>::THREADS, 2)
+k_dct64_dmma_split(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out, unsigned long long nblk,
+                   const double *__restrict__ dfrag2) {
+  typedef WarpTile<double> L;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_mbar[DctOnlyCfg<double>::WARPS];
+  __shared__ __align__(16) double s_d[2 * 32 * 32];  // 16 KB, fragment order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wsm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) + warp * L::BYTES;
+  const unsigned mb = smem_u32(&s_mbar[warp]);
+  const unsigned ntiles = (unsigned)((nblk + WTILE - 1) / WTILE);
+  for (int i = threadIdx.x; i < 2 * 32 * 32; i += blockDim.x) s_d[i] = dfrag2[i];
+  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
+  __syncthreads();
+  unsigned phase = 0;
+  const int brow = lane >> 2, kk = lane & 3;
+  auto elem = [&](int r, int n) -> double * {  // element n of block row r of the swizzled tile
+    const int c = n >> 1;
+    return reinterpret_cast<double *>(wsm + L::chunk_offset(c >> 3, r, c & 7) + (n & 1) * 8);
+  };
+  for (unsigned t = blockIdx.x * DctOnlyCfg<double>::WARPS + warp; t < ntiles; t += gridDim.x * DctOnlyCfg<double>::WARPS) {
+    if (lane == 0) {
+      bulk_wait_read();
+      mbar_expect_tx(mb, L::BYTES);
+#pragma unroll
+      for (int q = 0; q < L::SLABS; q++) tma_load_2d(smem_u32(wsm) + q * L::SLAB_BYTES, &tmap_in, q * 128, (int)(t * WTILE), mb);
+    }
+    mbar_wait(mb, phase);
+    phase ^= 1u;
+    double a0[4][4][2], a1[4][4][2];  // [block group g][row group i][C fragment element]: matrix 0 / matrix 1
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) a0[g][i][0] = a0[g][i][1] = a1[g][i][0] = a1[g][i][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      double b0[4], b1[4];
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        const int n = 4 * s + kk, r = 8 * g + brow;
+        if (INVERSE) {  // X[2n], X[2n+1]: one 16-byte chunk
+          const double2 v = *reinterpret_cast<const double2 *>(elem(r, 2 * n));
+          b0[g] = v.x; b1[g] = v.y;
+        } else {
+          const double p = *elem(r, n), q = *elem(r, BLK - 1 - n);
+          b0[g] = __dadd_rn(p, q); b1[g] = __dsub_rn(p, q);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const double f0 = s_d[(i * 8 + s) * 32 + lane], f1 = s_d[1024 + (i * 8 + s) * 32 + lane];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          dmma_m8n8k4(a0[g][i][0], a0[g][i][1], f0, b0[g]);
+          dmma_m8n8k4(a1[g][i][0], a1[g][i][1], f1, b1[g]);
+        }
+      }
+    }
+    __syncwarp();  // every lane has consumed the input tile
+#pragma unroll
+    for (int g = 0; g < 4; g++)
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {  // C fragment: row m = 8i + lane/4, column (block) 2*(lane%4) + e
+          const int m = 8 * i + brow, r = 8 * g + 2 * kk + e;
+          if (INVERSE) {
+            *elem(r, m) = __dadd_rn(a0[g][i][e], a1[g][i][e]);
+            *elem(r, BLK - 1 - m) = __dsub_rn(a0[g][i][e], a1[g][i][e]);
+          } else {
+            *reinterpret_cast<double2 *>(elem(r, 2 * m)) = make_double2(a0[g][i][e], a1[g][i][e]);
+          }
+        }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < L::SLABS; q++) tma_store_2d(&tmap_out, q * 128, (int)(t * WTILE), smem_u32(wsm) + q * L::SLAB_BYTES);
+      bulk_commit();
+    }
+  }
+  bulk_wait_all();
+}
+
+// FP64 issue-rate probes (the denominators of the butterfly / DMMA comparison): kind 0 = independent DFMA chains on the vector
+// pipe, kind 1 = mma.sync.m8n8k4.f64 on the tensor pipe.  `iters` x 32 operations per thread; the result keeps the
+// compiler honest.
+__global__ void __launch_bounds__(256) k_fp64_rate(int kind, int iters, double seed, double *sink) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = seed + (double)(threadIdx.x + i);
+  const double m = 1.0000001, c = 1e-9;
+  if (kind == 0) {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int i = 0; i < 16; i++) a[i] = __fma_rn(a[i], m, c);
+    }
+  } else {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) dmma_m8n8k4(a[2 * i], a[2 * i + 1], m, c);
+    }
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) t += a[i];
+  if (t == 123.456) sink[0] = t;
+}
+
 // DCT-only kernels behind dctz_gpu_dct_blocks (dct.h:17-27 equivalents)
 constexpr int DCT_ONLY_THREADS = 128;
 template <typename T, bool INVERSE>

@@ -240,9 +240,13 @@ int dctz_gpu_dct_blocks(dctz_gpu_ctx *ctx, const void *in, void *out, size_t nbl
 
 /* Transform only, device buffers: nblocks blocks of 64 elements, d_in -> d_out (may be the same buffer).
  * variant 0 = register-resident butterfly (the kernel the codec uses), 1 = matrix form on the FP64 tensor
- * pipe (mma.sync m8n8k4, double only) -- the comparison BASELINE config[3] asks for.                  */
+ * pipe (mma.sync m8n8k4, double only), 2 = the matrix form with the even/odd split (two 32x32 products, half
+ * the flops; double only) -- the comparison BASELINE config[3] asks for.                                */
 int dctz_gpu_dct64_dev(dctz_gpu_ctx *ctx, const void *d_in, void *d_out, size_t nblocks, int datatype, int inverse,
                        int variant, void *stream);
+/* Measured FP64 issue rate of the device in TFLOP/s: kind 0 = fused multiply-adds on the vector pipe,
+ * 1 = mma.sync.m8n8k4.f64 on the tensor pipe (the denominators of that comparison).  Synchronous.        */
+int dctz_gpu_fp64_rate(dctz_gpu_ctx *ctx, int kind, double *tflops);
 
 /* ---- utilities ----------------------------------------------------------------------------- */
 /* Elements [start, start+count) of the exactly reproducible synthetic 3-D field of SURVEY.md §8d

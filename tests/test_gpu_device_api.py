@@ -216,11 +216,11 @@ def test_full_size_properties_nyx_like(ctx):
         d0[w0 // 64:(w0 + (1 << 20)) // 64].cpu().numpy(), o["dc"], rtol=2e-7)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_transform_only_kernels_butterfly_and_dmma(ctx, variant, inverse):
-    """dctz_gpu_dct64_dev: the register butterfly (variant 0) and the FP64-DMMA matrix form (variant 1) compute the
-    same orthonormal DCT-II / DCT-III as the oracle (dct.c:55-103 / 115-205) to 1e-12."""
+    """dctz_gpu_dct64_dev: the register butterfly (variant 0), the FP64-DMMA matrix form (variant 1) and the matrix form with the
+    even/odd split (variant 2) compute the same orthonormal DCT-II / DCT-III as the oracle (dct.c:55-103 / 115-205) to 1e-12."""
     rng = np.random.default_rng(4)
     nblk = 32 * 50 + 7  # a partial last tile
     x = rng.standard_normal(nblk * 64) * rng.choice([1e-3, 1.0, 30.0], nblk * 64)

@@ -32,7 +32,8 @@ def main():
         pass
     res = {}
     ref = None
-    for name, variant in (("butterfly", 0), ("dmma", 1)):
+    flop = {0: 9.25, 1: 128.0, 2: 64.0}  # FP64 operations per element: generated butterfly / full matrix / even-odd split
+    for name, variant in (("butterfly", 0), ("dmma", 1), ("dmma_even_odd_split", 2)):
         for _ in range(3):
             ctx.dct64_dev(x.data_ptr(), out.data_ptr(), n // 64, DOUBLE, False, variant, st.cuda_stream)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,12 +46,14 @@ def main():
         ms = e0.elapsed_time(e1) / steps
         gbs = 16.0 * n / ms / 1e6
         res[name] = dict(ms=ms, hbm_gbs=gbs, frac_of_measured_peak=gbs / peak, gelem_s=n / ms / 1e6,
-                         fp64_flop_per_element=(2 * 64 if variant else 9.25), tflops=(2 * 64 if variant else 9.25) * n / ms / 1e9)
+                         fp64_flop_per_element=flop[variant], tflops=flop[variant] * n / ms / 1e9)
         if ref is None:
             ref = out.clone()
         else:
-            res["max_abs_diff_between_variants"] = float((out - ref).abs().max().item())
+            res[name]["max_abs_diff_vs_butterfly"] = float((out - ref).abs().max().item())
             res["max_abs_coefficient"] = float(ref.abs().max().item())
+    res["fp64_rate_tflops"] = dict(vector_dfma=ctx.fp64_rate(0), tensor_dmma_m8n8k4=ctx.fp64_rate(1),
+                                   note="measured issue-rate probes (dctz_gpu_fp64_rate): independent DFMA chains / back-to-back mma.sync.m8n8k4.f64")
     print(json.dumps(dict(workload="config[3]: 512^3 double (NYX-like), forward 64-point DCT only, 16 B/element", peak_gbs=peak, **res)))
 
 
