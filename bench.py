@@ -686,7 +686,14 @@ def main_ours(args):
                 for h in (self.hx, self.hout, self.hb, self.hdc, self.hac):
                     h.free()
 
-        lane_list = [Lane(ctx)] + [Lane(dctz_b200.Context(local)) for _ in range(lanes - 1)]
+        lane_list = [Lane(ctx)]
+        for _ in range(lanes - 1):  # (page-locked memory is a limited resource: run with the lanes that could be set up)
+            try:
+                lane_list.append(Lane(dctz_b200.Context(local)))
+            except Exception as e:  # noqa: BLE001
+                print(f"bench.py: e2e lane {len(lane_list)} could not be set up ({e}); continuing with {len(lane_list)}", file=sys.stderr)
+                break
+        lanes = len(lane_list)
         src = x[:ne].cpu().numpy()
         for ln in lane_list:
             ln.hx.array[:] = src
