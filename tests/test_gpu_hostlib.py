@@ -227,3 +227,58 @@ def test_quality_metrics_on_the_gpu(ctx, dtype):
     psnr = lib.calc_psnr(C.byref(va), C.byref(vb), C.c_int(a.size), C.c_double(1e-3))
     want = 20 * np.log10((float(a.max()) - float(a.min())) / np.sqrt(float(np.sum(e * e)) / a.size))
     assert abs(psnr - want) < 1e-9 * abs(want)
+
+
+def test_concurrent_contexts_through_the_host_buffer_calls():
+    """Three host threads with a context each push independent fields through dctz_gpu_compress_core / decompress_core on
+    page-locked buffers at the same time (the per-device link gates put them in step; a dominant transfer keeps one piece
+    queued while another call is active): every field must come out exactly as it does alone."""
+    import threading
+
+    from dctz_b200 import binding
+
+    n = 64 * 32 * 9000 + 64 * 3  # 147 MB of doubles: above the gates' threshold, streaming path
+    rng = np.random.default_rng(21)
+    t = np.arange(n, dtype=np.float64)
+    fields_ = [3.0 + 2.0 * np.sin(t / (50.0 + 13 * k)) + 0.03 * rng.standard_normal(n) for k in range(3)]
+    with dctz_b200.Context(0) as c0:
+        alone = []
+        for x in fields_:
+            g = c0.compress_core(x, 1e-3)
+            r = c0.decompress_core(g["bin_index"], g["dc"], g["ac"], n, np.float64, 1e-3, g["sf"])
+            alone.append((g["bin_index"].copy(), g["dc"].copy(), g["ac"].copy(), r.copy()))
+    ctxs = [dctz_b200.Context(0) for _ in fields_]
+    pins = []
+    for x in fields_:
+        hx, hout = binding.PinnedArray((n,), np.float64), binding.PinnedArray((n,), np.float64)
+        hb, hdc, hac = binding.PinnedArray((n,), np.uint8), binding.PinnedArray((n // 64,), np.float32), binding.PinnedArray((n,), np.float32)
+        hx.array[:] = x
+        pins.append((hx, hout, hb, hdc, hac))
+    errs = []
+
+    def work(k):
+        try:
+            hx, hout, hb, hdc, hac = pins[k]
+            for _ in range(3):
+                g = ctxs[k].compress_core(hx.array, 1e-3, out=dict(bin_index=hb.array, dc=hdc.array, ac_full=hac.array))
+                ctxs[k].decompress_core(g["bin_index"], g["dc"], g["ac"], n, np.float64, 1e-3, g["sf"], out=hout.array)
+                b, d, a, r = alone[k]
+                assert np.array_equal(g["bin_index"], b) and np.array_equal(g["dc"], d) and np.array_equal(g["ac"], a)
+                assert np.array_equal(hout.array, r)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(3)]
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join(timeout=180)
+    alive = any(t_.is_alive() for t_ in th)
+    for c in ctxs:
+        if not alive:
+            c.close()
+    for p in pins:
+        for h in p:
+            h.free()
+    assert not alive, "concurrent host-buffer calls are stuck"
+    assert not errs, errs
