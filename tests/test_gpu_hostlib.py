@@ -235,6 +235,7 @@ def test_concurrent_contexts_through_the_host_buffer_calls():
     queued while another call is active): every field must come out exactly as it does alone."""
     import threading
 
+    import dctz_b200
     from dctz_b200 import binding
 
     n = 64 * 32 * 9000 + 64 * 3  # 147 MB of doubles: above the gates' threshold, streaming path
