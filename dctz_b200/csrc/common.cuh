@@ -292,22 +292,28 @@ __device__ __forceinline__ unsigned ticket_next(unsigned *counter) {
 struct TileSeq {
   unsigned next, end, pend, base, batch;
   unsigned *counter;
-  __device__ __forceinline__ void init(unsigned *ticket_counter, unsigned warp_global, unsigned nwarps_grid, unsigned batch_, int lane) {
+  unsigned flip;  // 0: tiles in ascending order; ntiles - 1: the sequence runs from the LAST tile down (advance returns flip - index)
+  __device__ __forceinline__ void init(unsigned *ticket_counter, unsigned warp_global, unsigned nwarps_grid, unsigned batch_, int lane,
+                                       unsigned flip_ = 0u) {
     counter = ticket_counter;
     batch = batch_;
     base = nwarps_grid;
     next = warp_global * batch;
     end = next + batch;
     pend = 0;
+    flip = flip_;
     if (lane == 0) pend = ticket_next(counter);
   }
+  __device__ __forceinline__ unsigned map(unsigned idx) const {  // an index past the end stays past the end
+    return (flip == 0u) ? idx : (idx <= flip ? flip - idx : 0xFFFFFFFFu);
+  }
   __device__ __forceinline__ unsigned advance(int lane) {  // warp-uniform
-    if (next < end) return next++;
+    if (next < end) return map(next++);
     const unsigned start = (base + __shfl_sync(0xFFFFFFFFu, pin_here(pend), 0)) * batch;
     if (lane == 0) pend = ticket_next(counter);
     next = start + 1u;
     end = start + batch;
-    return start;
+    return map(start);
   }
 };
 

@@ -204,7 +204,7 @@ struct dctz_gpu_ctx {
   int occ[2][2][2] = {};  // resident CTAs/SM per [kernel][datatype][qt]
   int occ_ahead[2][2] = {};  // ... of the count-ahead decompress kernel [datatype][qt]
   int decomp_ahead = 0;      // DCTZ_DECOMP_AHEAD=1: streaming decompress without the pre-pass (measured: the second read of the bin ids disappears, the kernel gets slower by as much -- DESIGN.md)
-  int l2_hints = -1;         // DCTZ_L2_HINTS: bit 0 stores evict_first, bit 1 bin-id copies evict_first; -1 = 3 for the count-ahead path, 0 otherwise
+  int l2_hints = -1;         // DCTZ_L2_HINTS: bit 0 stores evict_first, bit 1 bin-id copies evict_first, bit 2 pre-pass path: tiles from the last one down; -1 = 3 for the count-ahead path, 0 otherwise
   DevBuf ahead_buf;          // count-ahead decompress: agg[u] | S[u/64] | T[u/2048], zeroed before every launch
   // single-launch kernels for small fields (fused.cuh)
   int occ_fused[2][2][2] = {};

@@ -2089,7 +2089,9 @@ k_decompress(const uint8_t *__restrict__ bins, const float *__restrict__ dc_in, 
     ScannedExtents ext;
     ext.counts = counts; ext.group_prefix = group_prefix; ext.chunk_prefix = chunk_prefix; ext.n_limit = n_limit; ext.corrupt_flag = corrupt_flag;
     TileSeq seq;
-    seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane);
+    // l2_hints bit 2: from the last tile down -- what the pre-pass read last (with evict_last) is what L2 still holds
+    const unsigned ntiles_ = (unsigned)((nblk_full + WTILE - 1) / WTILE);
+    seq.init(&ctl->ticket, blockIdx.x * Cfg::WARPS + warp, gridDim.x * Cfg::WARPS, batch, lane, (l2_hints & 4) ? ntiles_ - 1u : 0u);
     decompress_tiles<T, QT>(bins, dc_in, ac_in, nblk_full, sf, qk, &tmap_out, n_scan < n_limit ? n_scan : n_limit, dc_aligned16, wsm, mb, center,
                             s_qt, seq, ext, lane, phase, l2_hints);
     bulk_wait_all();

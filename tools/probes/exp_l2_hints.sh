@@ -1,7 +1,7 @@
-B="python bench.py --slab-log2 26 --steps 20 --warmup 3 --no-cpu --no-e2e --no-outlier-leg --no-configs"
-for h in 0 1 0 1; do DCTZ_L2_HINTS=$h $B 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('hints $h: ms_decompress', d['ms_decompress'], 'ms_compress', d['ms_compress'])"; done
-for h in 0 1; do DCTZ_L2_HINTS=$h ncu --cache-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"k_decompress|k_count_bins" -s 8 -c 2 --csv python bench.py --slab-log2 26 --steps 2 --warmup 3 --no-cpu --no-e2e --no-outlier-leg --no-configs 2>/dev/null | grep -v "^==" | python -c "
-import csv,sys
-for r in csv.reader(sys.stdin):
-    if len(r)>5 and r[0]!='ID' and 'k_' in r[4]: print('hints $h', r[4][:30], r[-3], r[-2], r[-1])"; done
+for h in 0 7 5 0 7; do
+DCTZ_L2_HINTS=$h timeout -s KILL 300 python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e --no-configs 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); o=d['outlier_leg']; print('hints $h: 2^30 dec', round(d['ms_decompress'],4), 'comp', round(d['ms_compress'],4), '| 2^28 5% dec ec/qt/f32/f32qt', round(o['ms_decompress'],4), round(o['qt_mode']['ms_decompress'],4), round(o['f32']['ms_decompress'],4), round(o['f32_qt']['ms_decompress'],4))"
+DCTZ_L2_HINTS=$h timeout -s KILL 300 python bench.py --workload c4 --steps 20 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('hints $h: c4 dec', round(d['ms_decompress'],4))"
+done
+DCTZ_L2_HINTS=7 timeout -s KILL 600 python -m pytest tests/test_gpu_device_api.py tests/test_gpu_parity.py -x -q 2>&1 | tail -2
