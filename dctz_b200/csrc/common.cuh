@@ -223,6 +223,14 @@ __device__ __forceinline__ void bulk_g2s_hint(unsigned dst, const void *src, uns
                "r"(bytes), "r"(mb), "l"(pol)
                : "memory");
 }
+// 128-bit shared-memory load the compiler may not narrow: asked for a uint4 of which only two words are used it emits two
+// 32-bit LDS, and a 32-bit access by the 32 lanes of a warp to "own row, swizzled chunk" addresses is a 4-way bank conflict
+// (rows r, r+8, r+16, r+24 share their banks), where the 128-bit form -- served per quarter-warp -- has none.
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }

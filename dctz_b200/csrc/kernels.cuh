@@ -589,6 +589,7 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
   while (cur < ntiles) {
     mbar_wait(mb, phase);
     phase ^= 1u;
+    unsigned keep = 0u;  // VERIFY: the low words of the pre-pass, fed into the probe below so that its loads stay 128 bits wide (lds128)
     if constexpr (VERIFY) {
       // The statistics pass folded into this one (util.c:12-44).  max|x| / min|x| are taken on the HIGH WORD of the bit
       // pattern (one integer max and min per element; for float that is the value, for double k_resolve_extremes settles
@@ -602,11 +603,12 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
         for (int q = 0; q < L::SLABS; q++) {
 #pragma unroll
           for (int c = 0; c < 8; c++) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(wsm + L::chunk_offset(q, lane, c));
+            const uint4 v = lds128(tile_s + L::chunk_offset(q, lane, c));  // (see lds128: two narrowed loads cost four times the wavefronts)
             if constexpr (sizeof(T) == 8) {
               const unsigned h0 = v.y & 0x7FFFFFFFu, h1 = v.w & 0x7FFFFFFFu;
               hx2[c & 1] = max(hx2[c & 1], max(h0, h1));
               hn2[c & 1] = min(hn2[c & 1], min(h0, h1));
+              keep |= v.x | v.z;
             } else {
               const unsigned h0 = v.x & 0x7FFFFFFFu, h1 = v.y & 0x7FFFFFFFu, h2 = v.z & 0x7FFFFFFFu, h3 = v.w & 0x7FFFFFFFu;
               hx2[c & 1] = max(hx2[c & 1], max(max(h0, h1), max(h2, h3)));
@@ -619,7 +621,7 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
       if (lane == 0) vstat.tile_ext[cur] = make_uint2(hmax, hmin);
     }
     T x[BLK];
-    unsigned probe = 0;
+    unsigned probe = keep;
 #pragma unroll
     for (int q = 0; q < L::SLABS; q++) {
 #pragma unroll
