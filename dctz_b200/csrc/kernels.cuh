@@ -389,10 +389,16 @@ template <> struct Quantizer<double> {
   __device__ __forceinline__ float unpark(float v) const { return v; }
   __device__ __forceinline__ unsigned quantize(double c_u) const {
     const double v = __fma_rn(c_u, kq, 127.5);
+#ifdef DCTZ_QUANT_MAGIC_ADD
     const double z = __dadd_rd(v, 6442450944.0 /* 1.5 * 2^32 */);  // ROUND DOWN: the 2^-20 grid must not round v up past an integer
     const unsigned lo = (unsigned)__double2loint(z), hi = (unsigned)__double2hiint(z);
     const unsigned u = (hi == 0x41F80000u) ? lo : 0xFFFFFFFFu;  // v outside [0, 4096) saturates
     const int b = (int)(2u * min(u >> 20, 255u)) - 255;
+#else
+    // floor(v) by the conversion instruction (F2I.F64.FLOOR saturates; a negative result wraps to a huge unsigned): three
+    // instructions fewer per coefficient than the magic add, the same integer for every finite v
+    const int b = (int)(2u * min((unsigned)__double2int_rd(v), 255u)) - 255;
+#endif
     return (unsigned)max(b, ~b);
   }
 };
