@@ -346,6 +346,9 @@ __device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, int lane) {
   return v;
 }
 
+// per 32-bit word of four bin ids: 0x80 in every byte that equals 0xFF (the outlier marker) -- three instructions: the low
+// seven bits + 1 carry into bit 7 exactly when they are all ones (never beyond it), and bit 7 itself must be set
+__device__ __forceinline__ unsigned ff_flags(unsigned w) { return ((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u; }
 // per 32-bit word of four bin ids: 0x01 in every byte that equals 0xFF (the outlier marker)
 __device__ __forceinline__ unsigned ff_bytes(unsigned w) {
   unsigned y = w & (w >> 4);

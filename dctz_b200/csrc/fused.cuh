@@ -456,7 +456,7 @@ k_decompress_fused(const uint8_t *__restrict__ bins, const float *__restrict__ d
         const unsigned chunk = k * 32 + lane;
         if (chunk < rows[h] * 4u) {
           const unsigned x0 = (chunk & 3u) ? v[h][k].x : (v[h][k].x & 0xFFFFFF00u);  // byte 0 of a block is the DC marker
-          cnt += __popc(ff_bytes(x0)) + __popc(ff_bytes(v[h][k].y)) + __popc(ff_bytes(v[h][k].z)) + __popc(ff_bytes(v[h][k].w));
+          cnt += __popc(ff_flags(x0)) + __popc(ff_flags(v[h][k].y)) + __popc(ff_flags(v[h][k].z)) + __popc(ff_flags(v[h][k].w));
         }
       }
 #pragma unroll

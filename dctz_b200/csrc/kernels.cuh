@@ -675,7 +675,7 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
           if (j == 0) continue;
           word |= qz.quantize(x[j]) << (8 * b);
         }
-        const unsigned nib = (ff_bytes(word) * 0x01020408u) >> 24;  // flag of byte b -> bit b
+        const unsigned nib = (ff_flags(word) * 0x00204081u) >> 28;  // flag (bit 7) of byte b -> bit b: 16 partial products, all at different positions
         if (q4 < 2) mlo |= nib << (16 * q4 + 4 * k); else mhi |= nib << (16 * (q4 - 2) + 4 * k);
         wq[k] = word;
       }
@@ -1435,7 +1435,7 @@ __global__ void __launch_bounds__(256) k_count_bins(const uint8_t *__restrict__ 
         const unsigned chunk = i * 32 + lane;
         if (chunk < rows[h] * 4u) {
           const unsigned x0 = (chunk & 3u) ? v[h][i].x : (v[h][i].x & 0xFFFFFF00u);  // byte 0 of a block is the DC marker
-          cnt += __popc(ff_bytes(x0)) + __popc(ff_bytes(v[h][i].y)) + __popc(ff_bytes(v[h][i].z)) + __popc(ff_bytes(v[h][i].w));
+          cnt += __popc(ff_flags(x0)) + __popc(ff_flags(v[h][i].y)) + __popc(ff_flags(v[h][i].z)) + __popc(ff_flags(v[h][i].w));
         }
       }
 #pragma unroll
@@ -1655,7 +1655,7 @@ struct AheadExtents {
     for (int i = 0; i < 4; i++) {
       const unsigned chunk = i * 32 + lane;
       const unsigned x0 = (chunk & 3u) ? r.v[i].x : (r.v[i].x & 0xFFFFFF00u);  // byte 0 of a block is the DC marker
-      cnt += __popc(ff_bytes(x0)) + __popc(ff_bytes(r.v[i].y)) + __popc(ff_bytes(r.v[i].z)) + __popc(ff_bytes(r.v[i].w));
+      cnt += __popc(ff_flags(x0)) + __popc(ff_flags(r.v[i].y)) + __popc(ff_flags(r.v[i].z)) + __popc(ff_flags(r.v[i].w));
     }
     cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
     if ((unsigned)lane == (c_pos & 31u)) ring_cnt = cnt;
@@ -1875,7 +1875,7 @@ __device__ __forceinline__ void decompress_tiles(const uint8_t *__restrict__ bin
     }
     unsigned cnt = 0;
 #pragma unroll
-    for (int q = 0; q < 16; q++) cnt += __popc(ff_bytes(q == 0 ? (w[0] & 0xFFFFFF00u) : w[q]));  // position 0 is the DC marker
+    for (int q = 0; q < 16; q++) cnt += __popc(ff_flags(q == 0 ? (w[0] & 0xFFFFFF00u) : w[q]));  // position 0 is the DC marker
     const unsigned my_off = warp_inclusive_scan(cnt, lane) - cnt;
     const Plan pl = plan_of(ext_cur);
 
