@@ -203,7 +203,7 @@ struct dctz_gpu_ctx {
   double *d_dfrag2[2] = {nullptr, nullptr}; // ... of its even / odd halves (k_dct64_dmma_split)
   int occ[2][2][2] = {};  // resident CTAs/SM per [kernel][datatype][qt]
   int occ_ahead[2][2] = {};  // ... of the count-ahead decompress kernel [datatype][qt]
-  int decomp_ahead = 0;      // DCTZ_DECOMP_AHEAD=1: streaming decompress without the pre-pass (measured: the second read of the bin ids disappears, the kernel gets slower by as much -- DESIGN.md)
+  int decomp_ahead = -1;     // DCTZ_DECOMP_AHEAD: 1 = streaming decompress always without the pre-pass, 0 = never, unset = where the stated outlier density is below 1/128
   int l2_hints = -1;         // DCTZ_L2_HINTS: bit 0 stores evict_first, bit 1 bin-id copies evict_first, bit 2 pre-pass path: tiles from the last one down; -1 = 3 for the count-ahead path, 0 otherwise
   DevBuf ahead_buf;          // count-ahead decompress: agg[u] | S[u/64] | T[u/2048], zeroed before every launch
   // single-launch kernels for small fields (fused.cuh)
@@ -441,7 +441,7 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   ctx->occ_ahead[0][1] = kernel_occupancy(k_decompress<float, true, true>, DecompressCfg<float, true>::THREADS, DecompressCfg<float, true>::SMEM);
   {
     const char *e = getenv("DCTZ_DECOMP_AHEAD");
-    ctx->decomp_ahead = e ? atoi(e) : 0;
+    ctx->decomp_ahead = e ? atoi(e) : -1;  // -1: by the outlier density of the call
     e = getenv("DCTZ_L2_HINTS");
     ctx->l2_hints = e ? atoi(e) : -1;  // -1: the path's own default
   }
@@ -1071,7 +1071,12 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
   if (nblk_full) {
     const size_t ntiles = (nblk_full + WTILE - 1) / WTILE;
     if (ntiles > 0xFFFFF000ull) return fail(ctx, DCTZ_GPU_EINVAL, "slab too large: %zu tiles", ntiles);
-    if (ctx->decomp_ahead) {  // no pre-pass: the warps count ahead and look their offsets up (AheadExtents)
+    // No pre-pass (the warps count ahead and look their offsets up, AheadExtents) where it pays: the count-ahead kernel saves
+    // the second read of the bin ids and costs ~15 % more instructions -- measured 1.68 against 1.71 ms on the outlier-free 8 GiB
+    // slab, 0.53 against 0.51 ms with 5 % outliers, whose tile loop has no issue slots to spare.  The caller states the
+    // number of outliers, so the choice is made per call: below one outlier per 128 elements.
+    const bool ahead = ctx->decomp_ahead > 0 || (ctx->decomp_ahead < 0 && ac_limit <= (unsigned long long)(N >> 7));
+    if (ahead) {
       const size_t resident = (size_t)ctx->sm_count * ctx->occ_ahead[sizeof(T) == 8][QT];
       const size_t ctas = (ntiles + Cfg::WARPS - 1) / Cfg::WARPS;
       const int grid = (int)(ctas < resident ? ctas : resident);
