@@ -222,6 +222,7 @@ struct dctz_gpu_ctx {
   DevBuf tile_sums;                            // per-tile sums + per-4096-tile partials (MODE_BELIEF)
   unsigned long long *d_dbg = nullptr;         // phase timestamps of the last single-launch kernels: [2][sm_count * 4][8]
   int dbg_grid[2] = {0, 0};
+  int fused_stamps = 0;                        // DCTZ_FUSED_STAMPS=1: the single-launch kernels record their phase boundaries (dctz_gpu_fused_phase_times)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -442,6 +443,8 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   {
     const char *e = getenv("DCTZ_DECOMP_AHEAD");
     ctx->decomp_ahead = e ? atoi(e) : -1;  // -1: by the outlier density of the call
+    e = getenv("DCTZ_FUSED_STAMPS");
+    ctx->fused_stamps = e ? atoi(e) : 0;
     e = getenv("DCTZ_L2_HINTS");
     ctx->l2_hints = e ? atoi(e) : -1;  // -1: the path's own default
   }
@@ -923,8 +926,8 @@ static int launch_compress_fused(dctz_gpu_ctx *ctx, int grid, const T *d_in, siz
   unsigned long long base = ctx->barrier_base[0];
   DevParams *params = ctx->d_params;
   unsigned *counts = sb.counts;
-  unsigned long long *dbg = ctx->d_dbg;
-  ctx->dbg_grid[0] = grid;
+  unsigned long long *dbg = ctx->fused_stamps ? ctx->d_dbg : nullptr;  // (six %globaltimer reads per CTA: diagnostics only)
+  ctx->dbg_grid[0] = ctx->fused_stamps ? grid : 0;
   void *args[] = {&tmap, &d_in, &nblk_full, &qc, &qk, &d_bins, &d_dc, &counts, &ac_slots, &raw, &jpos, &d_ac, &q_out, &q_raw, &qmax,
                   &partials, &totals, &tb, &params, &d_info, &bar, &base, &dbg};
   CU(cudaLaunchCooperativeKernel((const void *)k_compress_fused<T, QT>, dim3(grid), dim3(Cfg::THREADS), args, Cfg::SMEM, st));
@@ -1060,8 +1063,8 @@ static int launch_decompress(dctz_gpu_ctx *ctx, const uint8_t *d_bins, const flo
     unsigned long long *totals = ctx->d_cta_totals + (size_t)ctx->sm_count * 4, *bar = ctx->d_barrier + 1;
     unsigned long long base = ctx->barrier_base[1], lim = ac_limit;
     int dca = aligned16(d_dc) ? 1 : 0;
-    unsigned long long *dbg = ctx->d_dbg + (size_t)ctx->sm_count * 4 * 8;
-    ctx->dbg_grid[1] = fgrid;
+    unsigned long long *dbg = ctx->fused_stamps ? ctx->d_dbg + (size_t)ctx->sm_count * 4 * 8 : nullptr;
+    ctx->dbg_grid[1] = ctx->fused_stamps ? fgrid : 0;
     void *args[] = {&d_bins, &d_dc, &d_ac, &d_qtable, &nb, &bw_, &sf_, &qk_, &tmap, &counts, &toff, &totals, &lim, &d_corrupt, &dca, &bar, &base, &dbg};
     CU(cudaLaunchCooperativeKernel((const void *)k_decompress_fused<T, QT>, dim3(fgrid), dim3(Cfg::THREADS), args, Cfg::SMEM, st));
     ctx->barrier_base[1] += (unsigned long long)fgrid;
@@ -1472,7 +1475,7 @@ extern "C" int dctz_gpu_compress_core_with_stats(dctz_gpu_ctx *ctx, const void *
 extern "C" int dctz_gpu_fused_phase_times(dctz_gpu_ctx *ctx, int kernel, double out_us[16]) {
   if (!ctx || kernel < 0 || kernel > 1 || !out_us) return fail(ctx, DCTZ_GPU_EINVAL, "fused_phase_times: bad arguments");
   const int grid = ctx->dbg_grid[kernel];
-  if (grid <= 0) return fail(ctx, DCTZ_GPU_EINVAL, "fused_phase_times: no single-launch kernel has run");
+  if (grid <= 0) return fail(ctx, DCTZ_GPU_EINVAL, "fused_phase_times: no single-launch kernel has run with DCTZ_FUSED_STAMPS=1");
   CU(cudaSetDevice(ctx->device));
   CU(cudaDeviceSynchronize());
   std::vector<unsigned long long> h((size_t)grid * 8);

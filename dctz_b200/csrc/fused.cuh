@@ -122,6 +122,7 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
   constexpr unsigned FULL = 0xFFFFFFFFu;
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long s_mbar[Cfg::WARPS];
+  __shared__ __align__(8) unsigned long long s_mbar2[Cfg::WARPS];  // statistics phase: the second half-buffer's barrier
   __shared__ DevParams s_params;
   __shared__ Info s_info;
   __shared__ StatPartial s_sp[Cfg::WARPS];
@@ -136,18 +137,20 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
   unsigned t0, t1;
   cta_tile_range(ntiles, &t0, &t1);
   const unsigned nt = t1 - t0;
-  if (lane == 0) { mbar_init(mb, 1); fence_mbar_init(); }
+  const unsigned mb2 = smem_u32(&s_mbar2[warp]);
+  if (lane == 0) { mbar_init(mb, 1); mbar_init(mb2, 1); fence_mbar_init(); }
   if (QT && blockIdx.x == 0 && threadIdx.x < BLK) qmax_scratch[threadIdx.x] = 0;  // ordered before every use by the first barrier
 
   stamp(dbg, 0);
-  // ---- phase 1: statistics of the CTA's own range (util.c:12-44).  Every warp streams chunks of one tile buffer's size
-  //      through its own buffer with TMA bulk copies (one instruction per 16 / 8 KB instead of a thousand LDG.128; 8-12
-  //      warps per SM keep > 100 KB in flight), the next chunk requested as soon as the current one is in registers ----
+  // ---- phase 1: statistics of the CTA's own range (util.c:12-44).  Every warp streams chunks of HALF a tile buffer through
+  //      the two halves of its own buffer with TMA bulk copies (one instruction per 8 / 4 KB instead of hundreds of LDG.128):
+  //      while one half is looked at the other is on its way (one whole-buffer chunk at a time left the warp with nothing in
+  //      flight while it computed: 2.7 round trips per warp set the phase's length) ----
   unsigned phase = 0;  // parity of the warp's mbarrier, carried on into the compress loop
   __syncthreads();     // (the mbarriers are initialised)
   {
     typedef WarpTile<T> L;
-    constexpr unsigned CH = (unsigned)L::BYTES;
+    constexpr unsigned CH = (unsigned)L::BYTES / 2;
     constexpr int NV = (int)(CH / 16 / 32);  // 128-bit vectors per lane and chunk
     const unsigned long long e0 = (unsigned long long)t0 * (WTILE * BLK);
     unsigned long long e1 = (unsigned long long)t1 * (WTILE * BLK);
@@ -156,43 +159,47 @@ k_compress_fused(const __grid_constant__ CUtensorMap tmap_in, const T *__restric
     const unsigned long long bytes = (e1 - e0) * sizeof(T);  // a multiple of 64 elements: of 16 bytes
     const unsigned nchunks = (unsigned)((bytes + CH - 1) / CH);
     auto len_of = [&](unsigned c) -> unsigned { const unsigned long long left = bytes - (unsigned long long)c * CH; return left < CH ? (unsigned)left : CH; };
-    auto issue = [&](unsigned c) {
-      if (lane == 0) { mbar_expect_tx(mb, len_of(c)); bulk_g2s(smem_u32(wsm), src + (unsigned long long)c * CH, len_of(c), mb); }
+    auto issue = [&](unsigned c, unsigned half) {
+      if (lane == 0) {
+        const unsigned bar = half ? mb2 : mb;
+        mbar_expect_tx(bar, len_of(c));
+        bulk_g2s(smem_u32(wsm) + half * CH, src + (unsigned long long)c * CH, len_of(c), bar);
+      }
     };
     unsigned long long umax = 0ull, umin = ~0ull;
     double s0 = 0.0, s1 = 0.0;
-    unsigned c = (unsigned)warp;
-    if (c < nchunks) issue(c);
+    unsigned c = (unsigned)warp, half = 0, phase2 = 0;
+    if (c < nchunks) issue(c, 0);
+    if (c + Cfg::WARPS < nchunks) issue(c + Cfg::WARPS, 1);
     while (c < nchunks) {
-      mbar_wait(mb, phase);
-      phase ^= 1u;
+      if (half) { mbar_wait(mb2, phase2); phase2 ^= 1u; } else { mbar_wait(mb, phase); phase ^= 1u; }
       const unsigned nv = len_of(c) / 16;
-      const uint4 *buf = reinterpret_cast<const uint4 *>(wsm);
+      const uint4 *buf = reinterpret_cast<const uint4 *>(wsm + half * CH);
       unsigned probe = 0;
+      uint4 v[NV];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {  // two batches bound the registers
-        uint4 v[NV / 2];
+      for (int u = 0; u < NV; u++) { const unsigned i = (unsigned)u * 32u + lane; v[u] = i < nv ? buf[i] : make_uint4(0u, 0u, 0u, 0u); }
 #pragma unroll
-        for (int u = 0; u < NV / 2; u++) { const unsigned i = (unsigned)(h * (NV / 2) + u) * 32u + lane; v[u] = i < nv ? buf[i] : make_uint4(0u, 0u, 0u, 0u); }
+      for (int u = 0; u < NV; u++) probe |= v[u].x ^ v[u].w;
+      // the half is in registers (completed, not just issued): the chunk after the next one may overwrite it
+      const unsigned cn = c + 2u * Cfg::WARPS;
+      __syncwarp();
+      if (reads_have_landed(probe) && cn < nchunks) issue(cn, half);
 #pragma unroll
-        for (int u = 0; u < NV / 2; u++) {
-          probe |= v[u].x ^ v[u].w;
-          if ((unsigned)(h * (NV / 2) + u) * 32u + lane < nv) {
-            const T *e = reinterpret_cast<const T *>(&v[u]);
+      for (int u = 0; u < NV; u++) {
+        if ((unsigned)u * 32u + lane < nv) {
+          const T *e = reinterpret_cast<const T *>(&v[u]);
 #pragma unroll
-            for (int q = 0; q < VEC; q++) {
-              const unsigned long long a = AbsBits<T>::get(e[q]);
-              umax = a > umax ? a : umax;
-              umin = a < umin ? a : umin;
-              if (q & 1) s1 += (double)e[q]; else s0 += (double)e[q];
-            }
+          for (int q = 0; q < VEC; q++) {
+            const unsigned long long a = AbsBits<T>::get(e[q]);
+            umax = a > umax ? a : umax;
+            umin = a < umin ? a : umin;
+            if (q & 1) s1 += (double)e[q]; else s0 += (double)e[q];
           }
         }
       }
-      const unsigned cn = c + Cfg::WARPS;
-      __syncwarp();
-      if (reads_have_landed(probe) && cn < nchunks) issue(cn);
-      c = cn;
+      c += Cfg::WARPS;
+      half ^= 1u;
     }
     double sum = s0 + s1;
 #pragma unroll

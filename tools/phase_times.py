@@ -1,5 +1,6 @@
 """where the microseconds of the small BASELINE configs go: phase stamps of the single-launch kernels"""
 import os, sys, json
+os.environ.setdefault("DCTZ_FUSED_STAMPS", "1")  # the stamps are off unless asked for
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import dctz_b200
