@@ -1220,12 +1220,29 @@ __global__ void __launch_bounds__(256) k_gather_ec(const unsigned *__restrict__ 
     if (__shfl_sync(0xFFFFFFFFu, incl, 31) == 0u) continue;
     float *gdst = ac_out + prefix_of_group(group_prefix, chunk_prefix, g);
     const float *gsrc = ac_slots + (unsigned long long)g * 32u * TILE_SLOT;
-    for (int s = warp; s < 32; s += 8) {
-      const unsigned n = __shfl_sync(0xFFFFFFFFu, c, s);
-      const unsigned off = __shfl_sync(0xFFFFFFFFu, incl - c, s);
-      const float *src = gsrc + (unsigned)s * TILE_SLOT;
-      float *dst = gdst + off;
-      for (unsigned i0 = 0; i0 < n; i0 += 256u) {
+    // the warp's four runs (tiles warp, warp + 8, ...): the first 128 outliers of ALL of them are requested before any is stored
+    // (one run at a time, the warp sat out the load latency four times per group); longer runs finish in the loop below
+    unsigned n4[4], off4[4];
+    float v4[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      n4[q] = __shfl_sync(0xFFFFFFFFu, c, warp + 8 * q);
+      off4[q] = __shfl_sync(0xFFFFFFFFu, incl - c, warp + 8 * q);
+      const float *src = gsrc + (unsigned)(warp + 8 * q) * TILE_SLOT;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const unsigned i = 32u * k + lane; v4[q][k] = (i < n4[q]) ? __ldg(src + i) : 0.f; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      float *dst = gdst + off4[q];
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const unsigned i = 32u * k + lane; if (i < n4[q]) dst[i] = v4[q][k]; }
+    }
+    for (int q = 0; q < 4; q++) {
+      const unsigned n = n4[q];
+      const float *src = gsrc + (unsigned)(warp + 8 * q) * TILE_SLOT;
+      float *dst = gdst + off4[q];
+      for (unsigned i0 = 128u; i0 < n; i0 += 256u) {
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) { const unsigned i = i0 + 32u * k + lane; v[k] = (i < n) ? __ldg(src + i) : 0.f; }
