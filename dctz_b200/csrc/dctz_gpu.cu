@@ -552,7 +552,15 @@ static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 // Tiles per ticket (TileSeq, common.cuh): 4 once every warp has many batches to go through, 1 for small fields, where
 // whole batches would leave part of the grid without work.
-static unsigned tile_batch(size_t ntiles, size_t nwarps) { return ntiles >= 16 * nwarps ? 4u : 1u; }
+#ifndef DCTZ_TILE_BATCH_C
+#define DCTZ_TILE_BATCH_C 2u  // (measured on one box against 4 and 1: the same on the 8 GiB slab, 1-2 % faster with outliers and on c4)
+#endif
+#ifndef DCTZ_TILE_BATCH_D
+#define DCTZ_TILE_BATCH_D 4u
+#endif
+static unsigned tile_batch(size_t ntiles, size_t nwarps, bool compress = false) {
+  return ntiles >= 16 * nwarps ? (compress ? DCTZ_TILE_BATCH_C : DCTZ_TILE_BATCH_D) : 1u;
+}
 
 struct ScanBufs { unsigned *counts; ScanOut out; unsigned nchunks; };
 static size_t up128(size_t v) { return (v + 127) / 128 * 128; }
@@ -695,7 +703,7 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
     fused.total = &d_info->n_outliers;
     // small field, true statistics: the last CTA scans (one launch less); the single-read modes scan after the REDO launch
     fused.n_entries = (sa.mode == MODE_STATS && rem == 0 && (n_entries + 31) / 32 <= 1024) ? (unsigned)n_entries : 0u;
-    const unsigned batch = tile_batch(ntiles, (size_t)grid * Cfg::WARPS);
+    const unsigned batch = tile_batch(ntiles, (size_t)grid * Cfg::WARPS, true);
     if (sa.mode == MODE_BELIEF)
       k_compress<T, QT, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tmap, nblk_full, src, qc, d_bins, d_dc, sb.counts, ac_slots, raw, jpos,
                                                                      (T *)d_qtable_raw, &ctx->d_ctl[0], d_info, fused, batch);

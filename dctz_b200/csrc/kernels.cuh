@@ -529,7 +529,13 @@ template <typename T, bool QT> struct CompressCfg {
   // convert + store per coefficient), sparser tiles the parked-candidates loop.  Measured on B200 (2^28-element slab
   // + white noise, 5% outliers): double 0.848 / 0.832 / 0.815 of roofline at thresholds 3 / 6 / 16, float 0.57 at 6,
   // 0.66 at 16 (its exact-division outliers make the dense form expensive); at 20-40% outliers all thresholds agree.
-  static constexpr unsigned DENSE_MIN = (sizeof(T) == 8) ? 3u : 16u;
+#ifndef DCTZ_DENSE_MIN_D
+#define DCTZ_DENSE_MIN_D 3u
+#endif
+#ifndef DCTZ_DENSE_MIN_F
+#define DCTZ_DENSE_MIN_F 16u
+#endif
+  static constexpr unsigned DENSE_MIN = (sizeof(T) == 8) ? DCTZ_DENSE_MIN_D : DCTZ_DENSE_MIN_F;
   static constexpr int WARPS = 4;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int CTAS_PER_SM = (sizeof(T) == 8) ? 2 : 3;
@@ -1622,7 +1628,10 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 }
 struct AheadExtents {
   typedef AheadRaw Raw;
-  static constexpr unsigned AHEAD = 10;  // tiles between the count cursor and the extent cursor (>= batch + 3)
+#ifndef DCTZ_AHEAD_DIST
+#define DCTZ_AHEAD_DIST 10
+#endif
+  static constexpr unsigned AHEAD = DCTZ_AHEAD_DIST;  // tiles between the count cursor and the extent cursor (>= batch + 3)
   static constexpr unsigned long long LOW48 = 0xFFFFFFFFFFFFull;
   static __device__ __forceinline__ Raw none() {
     Raw r;
