@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dct64_gen.cuh"  // (global scope) the generated transform and its constant table ::dct64_kd
+
 namespace dctz {
 
 constexpr int BLK = 64;            // BLK_SZ, dctz.h:28
@@ -14,7 +16,9 @@ constexpr int BLK = 64;            // BLK_SZ, dctz.h:28
 // ------------------------------------------------------------------------------------------
 struct ArithD {
   typedef double V;
-  static __device__ __forceinline__ constexpr double cst(double k) { return k; }
+  // entry i of the constant table: ptxas then feeds the DMUL / DFMA a constant-bank operand; a double LITERAL costs two UMOVs
+  // (its two 32-bit halves into a uniform register pair) per use, ~250 instructions of the 592-operation transform
+  static __device__ __forceinline__ double cst(int i, double) { return ::dct64_kd[i]; }
   static __device__ __forceinline__ V add(V a, V b) { return __dadd_rn(a, b); }
   static __device__ __forceinline__ V sub(V a, V b) { return __dsub_rn(a, b); }
   static __device__ __forceinline__ V mul(V a, double k) { return __dmul_rn(a, k); }
@@ -23,9 +27,16 @@ struct ArithD {
   static __device__ __forceinline__ V neg(V a) { return -a; }
 };
 
+// The same with the constants as literals: what the EC decompress kernels use.  Same-box A/B on B200 (tools/probes/ab.sh): with the
+// table the compress kernels gain 1-2 % (5 % outlier slab, c4), QT compress 4 % and QT decompress 5 %; the count-ahead EC
+// decompress of the 8 GiB slab LOSES 7 % (1.70 -> 1.82 ms) and the pre-pass EC decompress 1 %, so those keep the literals.
+struct ArithDLit : ArithD {
+  static __device__ __forceinline__ constexpr double cst(int, double k) { return k; }
+};
+
 struct ArithF {
   typedef float V;
-  static __device__ __forceinline__ constexpr float cst(double k) { return (float)k; }
+  static __device__ __forceinline__ constexpr float cst(int, double k) { return (float)k; }  // an immediate of the FMUL / FFMA
   static __device__ __forceinline__ V add(V a, V b) { return __fadd_rn(a, b); }
   static __device__ __forceinline__ V sub(V a, V b) { return __fsub_rn(a, b); }
   static __device__ __forceinline__ V mul(V a, float k) { return __fmul_rn(a, k); }
@@ -34,9 +45,10 @@ struct ArithF {
   static __device__ __forceinline__ V neg(V a) { return -a; }
 };
 
-template <typename T> struct ArithOf;
-template <> struct ArithOf<double> { typedef ArithD type; };
-template <> struct ArithOf<float> { typedef ArithF type; };
+template <typename T, bool TABLE = true> struct ArithOf;
+template <> struct ArithOf<double, true> { typedef ArithD type; };
+template <> struct ArithOf<double, false> { typedef ArithDLit type; };
+template <bool TABLE> struct ArithOf<float, TABLE> { typedef ArithF type; };
 
 // ------------------------------------------------------------------------------------------
 // Exact division by a loop-invariant divisor b with y = RN(1/b) precomputed.

@@ -375,6 +375,7 @@ static int ctx_init(dctz_gpu_ctx *ctx, int device) {
   if (device < 0 || device >= ndev) return fail(ctx, DCTZ_GPU_EINVAL, "device %d out of range [0,%d)", device, ndev);
   ctx->device = device;
   CU(cudaSetDevice(device));
+  CU(cudaMemcpyToSymbol(dct64_kd, dct64_kd_host, sizeof(dct64_kd_host)));  // the double transform's constants (dct64_gen.cuh)
   {
     const char *e = getenv("DCTZ_L2_HINTS");
     const int v = e ? (atoi(e) > 0) : 0;  // (the pre-pass reads the bin ids with evict_last)

@@ -1798,7 +1798,7 @@ __device__ __forceinline__ void decompress_tiles(const uint8_t *__restrict__ bin
                                                  unsigned long long n_ac /* end of the readable part of AC_exact */, int dc_aligned16,
                                                  unsigned char *wsm, unsigned mb, const T *center, const T *s_qt, Seq &seq, Ext &ext,
                                                  int lane, unsigned &phase, int l2_hints = 0) {
-  typedef typename ArithOf<T>::type A;
+  typedef typename ArithOf<T, QT>::type A;  // double: constants from the table in QT mode, literals in EC mode (same-box A/B, common.cuh)
   typedef DecompressCfg<T, QT> Cfg;
   typedef WarpTile<T> L;
   constexpr bool WIDE = (sizeof(T) == 8);

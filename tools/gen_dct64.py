@@ -273,11 +273,18 @@ def _lit(k):
         return repr(float(k))
 
 
-def emit_function(p: Prog, name: str) -> str:
-    """In-place transform of `V (&x)[N]`.  A is the arithmetic policy (see dct64_arith.cuh):
+def emit_function(p: Prog, name: str, table: dict) -> str:
+    """In-place transform of `V (&x)[N]`.  A is the arithmetic policy (common.cuh):
     A::add(a,b) A::sub(a,b) A::mul(a,k) A::fma(a,k,b)=a*k+b A::fms(a,k,b)=a*k-b A::neg(a),
-    with k a compile-time double literal converted by A::cst()."""
+    with k = A::cst(i, literal): entry i of the constant table dct64_kd (the double policy: a constant-bank operand of the
+    DMUL / DFMA instead of two UMOVs per use) or the literal itself (the float policy: an immediate)."""
     n = p.n_in
+
+    def cst(k):
+        lit = _lit(k)
+        idx = table.setdefault(lit, len(table))
+        return f"A::cst({idx}, {lit})"
+
     lines = []
     lines.append(f"template <typename A>\n__device__ __forceinline__ void {name}(typename A::V (&x)[{n}]) {{")
     lines.append("  typedef typename A::V V;")
@@ -291,11 +298,11 @@ def emit_function(p: Prog, name: str) -> str:
         elif kind == "sub":
             e = f"A::sub({ref(a)}, {ref(b)})"
         elif kind == "mul":
-            e = f"A::mul({ref(a)}, A::cst({_lit(k)}))"
+            e = f"A::mul({ref(a)}, {cst(k)})"
         elif kind == "fma":
-            e = f"A::fma({ref(a)}, A::cst({_lit(k)}), {ref(b)})"
+            e = f"A::fma({ref(a)}, {cst(k)}, {ref(b)})"
         elif kind == "fms":
-            e = f"A::fms({ref(a)}, A::cst({_lit(k)}), {ref(b)})"
+            e = f"A::fms({ref(a)}, {cst(k)}, {ref(b)})"
         lines.append(f"  const V t{dst} = {e};")
     for i, (vid, s) in enumerate(p.outputs):
         lines.append(f"  x[{i}] = {ref(vid) if s > 0 else 'A::neg(' + ref(vid) + ')'};")
@@ -319,7 +326,15 @@ def main():
     f = build_forward(64)
     i = build_inverse(64)
     txt = HEADER % {"fwd": op_counts(f), "inv": op_counts(i)}
-    txt += "\n" + emit_function(f, "dct64_forward") + "\n\n" + emit_function(i, "dct64_inverse") + "\n"
+    table = {}
+    body = emit_function(f, "dct64_forward", table) + "\n\n" + emit_function(i, "dct64_inverse", table) + "\n"
+    lits = sorted(table, key=table.get)
+    txt += f"\n// the distinct constants of both flow graphs ({len(lits)}); see A::cst\n"
+    txt += ("// (left uninitialised on the device and uploaded by the host once per context: with an initialiser in sight the compiler\n"
+            "// folds dct64_kd[i] back into the literal)\n")
+    txt += f"constexpr int DCT64_NK = {len(lits)};\n__constant__ double dct64_kd[DCT64_NK];\n"
+    txt += "static const double dct64_kd_host[DCT64_NK] = {\n" + "".join(f"    {v},\n" for v in lits) + "};\n"
+    txt += "\n" + body
     os.makedirs(os.path.dirname(out), exist_ok=True)
     with open(out, "w") as fh:
         fh.write(txt)
