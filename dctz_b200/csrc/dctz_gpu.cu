@@ -251,6 +251,10 @@ static int fail(dctz_gpu_ctx *ctx, int code, const char *fmt, ...) {
     if (r_ != DCTZ_GPU_OK) return r_; \
   } while (0)
 
+// The QT outlier slots start at the first address of their allocation that is a multiple of a slot's size (park_if, kernels.cuh)
+static void *qt_raw_slots(const dctz_gpu_ctx *ctx) { return (void *)(((uintptr_t)ctx->qt_raw.p + QT_RAW_ALIGN - 1) / QT_RAW_ALIGN * QT_RAW_ALIGN); }
+static uint8_t *qt_j_slots(const dctz_gpu_ctx *ctx) { return (uint8_t *)(((uintptr_t)ctx->qt_j.p + QT_J_ALIGN - 1) / QT_J_ALIGN * QT_J_ALIGN); }
+
 static int grow(dctz_gpu_ctx *ctx, DevBuf &b, size_t bytes, bool zero = false) {
   if (bytes <= b.cap) return DCTZ_GPU_OK;
   if (b.p) { CU(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
@@ -671,10 +675,10 @@ static int launch_compress(dctz_gpu_ctx *ctx, const T *d_in, size_t N, double eb
   FusedScan fused;
   fused.n_entries = 0;
   if (QT) {
-    TRY(grow(ctx, ctx->qt_raw, n_entries * TILE_SLOT * sizeof(T)));
-    TRY(grow(ctx, ctx->qt_j, n_entries * TILE_SLOT));
-    raw = (T *)ctx->qt_raw.p;
-    jpos = (uint8_t *)ctx->qt_j.p;
+    TRY(grow(ctx, ctx->qt_raw, n_entries * TILE_SLOT * sizeof(T) + QT_RAW_ALIGN));
+    TRY(grow(ctx, ctx->qt_j, n_entries * TILE_SLOT + QT_J_ALIGN));
+    raw = (T *)qt_raw_slots(ctx);
+    jpos = qt_j_slots(ctx);
     ctx->qt_entries = (unsigned)n_entries;
     ctx->qt_tail_tile = rem ? (unsigned)ntiles : 0xFFFFFFFFu;
   } else {
@@ -866,7 +870,7 @@ static int launch_qt_finish(dctz_gpu_ctx *ctx, double eb, const T *d_qraw, T *d_
   TRY(scan_bufs(ctx, n_entries, &sb));  // same layout as in the compress call: nothing is reallocated
   const size_t want = ((size_t)n_entries + 31) / 32;  // one CTA per group of 32 tiles
   const int grid = (int)(want < (size_t)ctx->sm_count * 8 ? (want ? want : 1) : (size_t)ctx->sm_count * 8);
-  k_qt_gather<T><<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, n_entries, (const T *)ctx->qt_raw.p, (const uint8_t *)ctx->qt_j.p,
+  k_qt_gather<T><<<grid, 256, 0, st>>>(sb.counts, sb.out.group_prefix, sb.out.chunk_prefix, n_entries, (const T *)qt_raw_slots(ctx), (const uint8_t *)qt_j_slots(ctx),
                                        d_qraw, d_qtable, k, d_ac, d_info, ctx->d_params, ctx->qt_tail_tile);
   ctx->launches++;
   CU(cudaGetLastError());
@@ -915,10 +919,10 @@ static int launch_compress_fused(dctz_gpu_ctx *ctx, int grid, const T *d_in, siz
   T *raw = nullptr;
   uint8_t *jpos = nullptr;
   if (QT) {
-    TRY(grow(ctx, ctx->qt_raw, ntiles * TILE_SLOT * sizeof(T)));
-    TRY(grow(ctx, ctx->qt_j, ntiles * TILE_SLOT));
-    raw = (T *)ctx->qt_raw.p;
-    jpos = (uint8_t *)ctx->qt_j.p;
+    TRY(grow(ctx, ctx->qt_raw, ntiles * TILE_SLOT * sizeof(T) + QT_RAW_ALIGN));
+    TRY(grow(ctx, ctx->qt_j, ntiles * TILE_SLOT + QT_J_ALIGN));
+    raw = (T *)qt_raw_slots(ctx);
+    jpos = qt_j_slots(ctx);
     ctx->qt_entries = 0;  // nothing is left for dctz_gpu_qt_finish_dev: the kernel rescales itself
   } else {
     TRY(grow(ctx, ctx->slots, ntiles * TILE_SLOT * sizeof(float)));

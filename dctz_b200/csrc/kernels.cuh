@@ -504,23 +504,34 @@ __device__ __forceinline__ void cta_scan_small(const unsigned *counts, const Fus
 // K2: fused scale + DCT-II + quantise + ordered outlier compaction.
 // Shared memory per warp: [ tile: 4 (2) swizzled slabs ][ EC: outlier candidates 63 x 32 floats ][ bin ids 2 KB ]
 // ------------------------------------------------------------------------------------------
-// QT outlier emission: store value and position and advance both cursors, all under one predicate.
-__device__ __forceinline__ void park_if(double *&praw, uint8_t *&pj, double v, unsigned j, unsigned hit) {
+// QT outlier emission: store value and position and advance both cursors, all under one predicate taken straight from a
+// bit of the group mask.  Only the LOW words of the two cursors move: a tile's slots (TILE_SLOT values, TILE_SLOT position
+// bytes) are aligned to their own size (QT_RAW_ALIGN / QT_J_ALIGN on the arrays' bases, dctz_gpu.cu), so a cursor inside
+// a slot never carries into the high word.  (With two 64-bit cursors and the hit flag taken as a value SASS showed 12.5
+// instructions per coefficient position -- 29 % of the instructions of k_compress<double,QT> at 5 % outliers; a 32-bit
+// offset from a 64-bit base is no better, ptxas spells the wide multiply-add as four instructions.)
+constexpr size_t QT_RAW_ALIGN = (size_t)2048 * 8;  // = TILE_SLOT * sizeof(double) (static_assert below)
+constexpr size_t QT_J_ALIGN = 2048;                // = TILE_SLOT
+__device__ __forceinline__ void park_if(unsigned &plo, unsigned phi, unsigned &qlo, unsigned qhi, double v, unsigned j, unsigned mg, unsigned bit) {
   asm volatile(
-      "{\n.reg .pred q;\nsetp.ne.u32 q, %4, 0;\n"
-      "@q st.global.f64 [%0], %2;\n@q st.global.u8 [%1], %3;\n"
-      "@q add.u64 %0, %0, 8;\n@q add.u64 %1, %1, 1;\n}\n"
-      : "+l"(praw), "+l"(pj)
-      : "d"(v), "r"(j), "r"(hit)
+      "{\n.reg .pred q;\n.reg .b32 t;\n.reg .u64 a, b;\n"
+      "and.b32 t, %6, %7;\nsetp.ne.u32 q, t, 0;\n"
+      "mov.b64 a, {%0, %2};\nmov.b64 b, {%1, %3};\n"
+      "@q st.global.f64 [a], %4;\n@q st.global.u8 [b], %5;\n"
+      "@q add.u32 %0, %0, 8;\n@q add.u32 %1, %1, 1;\n}\n"
+      : "+r"(plo), "+r"(qlo)
+      : "r"(phi), "r"(qhi), "d"(v), "r"(j), "r"(mg), "r"(bit)
       : "memory");
 }
-__device__ __forceinline__ void park_if(float *&praw, uint8_t *&pj, float v, unsigned j, unsigned hit) {
+__device__ __forceinline__ void park_if(unsigned &plo, unsigned phi, unsigned &qlo, unsigned qhi, float v, unsigned j, unsigned mg, unsigned bit) {
   asm volatile(
-      "{\n.reg .pred q;\nsetp.ne.u32 q, %4, 0;\n"
-      "@q st.global.f32 [%0], %2;\n@q st.global.u8 [%1], %3;\n"
-      "@q add.u64 %0, %0, 4;\n@q add.u64 %1, %1, 1;\n}\n"
-      : "+l"(praw), "+l"(pj)
-      : "f"(v), "r"(j), "r"(hit)
+      "{\n.reg .pred q;\n.reg .b32 t;\n.reg .u64 a, b;\n"
+      "and.b32 t, %6, %7;\nsetp.ne.u32 q, t, 0;\n"
+      "mov.b64 a, {%0, %2};\nmov.b64 b, {%1, %3};\n"
+      "@q st.global.f32 [a], %4;\n@q st.global.u8 [b], %5;\n"
+      "@q add.u32 %0, %0, 4;\n@q add.u32 %1, %1, 1;\n}\n"
+      : "+r"(plo), "+r"(qlo)
+      : "r"(phi), "r"(qhi), "f"(v), "r"(j), "r"(mg), "r"(bit)
       : "memory");
 }
 
@@ -720,8 +731,11 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
         // values: here they would cost a look-up and a branch per coefficient POSITION (measured: the branches,
         // not the arithmetic, held this kernel at half its EC speed).  For the same reason the stores are predicated
         // by hand -- the compiler turns the plain `if` into 63 divergent branches.
-        T *praw = raw_slots + (unsigned long long)cur * TILE_SLOT + my_off;
-        uint8_t *pj = j_slots + (unsigned long long)cur * TILE_SLOT + my_off;
+        static_assert(QT_RAW_ALIGN == (size_t)TILE_SLOT * 8 && QT_J_ALIGN == (size_t)TILE_SLOT, "slot alignment");
+        const unsigned long long praw = (unsigned long long)(raw_slots + (unsigned long long)cur * TILE_SLOT + my_off);
+        const unsigned long long pj = (unsigned long long)(j_slots + (unsigned long long)cur * TILE_SLOT + my_off);
+        unsigned plo = (unsigned)praw, qlo = (unsigned)pj;  // the cursors' low words (see park_if)
+        const unsigned phi = (unsigned)(praw >> 32), qhi = (unsigned)(pj >> 32);
         // (coefficient positions in groups of eight: a group in which no block of the tile has an outlier -- the high
         // frequencies of a smooth field -- is skipped by a warp-uniform branch)
 #pragma unroll
@@ -732,7 +746,7 @@ __device__ __forceinline__ void compress_tiles(const CUtensorMap *tmap_in, unsig
             for (int b = 0; b < 8; b++) {
               const int j = 8 * g + b;
               if (j == 0) continue;
-              park_if(praw, pj, x[j], (unsigned)j, (mg >> b) & 1u);
+              park_if(plo, phi, qlo, qhi, x[j], (unsigned)j, mg, 1u << b);
             }
           }
         }
