@@ -385,13 +385,15 @@ def time_field(ctx, torch, binding, x, code, eb, qt, steps, warmup, peak, flush)
     launches = (ctx.launch_count - l0) / steps
     tc = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3 / steps
     td = sum(e[1].elapsed_time(e[2]) for e in ev) / 1e3 / steps
+    med = lambda v: sorted(v)[len(v) // 2]  # noqa: E731  (the means are the reported figures; the medians show a step that a hiccup stretched)
+    tc_med, td_med = med([e[0].elapsed_time(e[1]) for e in ev]), med([e[1].elapsed_time(e[2]) for e in ev])
     p = n_out / n
     bc, bd = bytes_per_element(es, p)
     single_read = n * es > (256 << 20)  # whole fields beyond the single-launch kernels' limit take the single-read path
     if single_read:
         bc = bc - es + es * 16.0 / 4096.0
     return dict(elements=n, algorithm="single-read compress (sample + verify)" if single_read else "single launch per direction, two reads (the second from L2)", dtype="f64" if es == 8 else "f32", mode="qt" if qt else "ec", error_bound=eb, outlier_fraction=p,
-                ms_compress=1e3 * tc, ms_decompress=1e3 * td, compress_gbs=n * es / 1e9 / tc, decompress_gbs=n * es / 1e9 / td,
+                ms_compress=1e3 * tc, ms_decompress=1e3 * td, ms_compress_median=tc_med, ms_decompress_median=td_med, compress_gbs=n * es / 1e9 / tc, decompress_gbs=n * es / 1e9 / td,
                 compress_frac=bc * n / tc / 1e9 / peak, decompress_frac=bd * n / td / 1e9 / peak, launches_per_step=launches,
                 max_abs_err=float((out - x).abs().max().item()), sf=sf), dict(bins=bins, dc=dc, ac=ac, n_out=n_out, sf=sf, qtab=qtab)
 
