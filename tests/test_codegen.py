@@ -59,3 +59,20 @@ def test_committed_header_is_up_to_date():
         finally:
             sys.argv = old
         assert open(tmp).read() == open(path).read(), "run tools/gen_dct64.py and commit the result"
+
+
+def test_constant_table_agrees_with_the_literals():
+    """The double policy reads entry i of dct64_kd, the float policy the literal beside it (A::cst(i, literal)): every use
+    of an index must name the literal the table holds at that index, and every entry must be used."""
+    import re
+
+    path = os.path.join(ROOT, "dctz_b200", "csrc", "dct64_gen.cuh")
+    txt = open(path).read()
+    nk = int(re.search(r"constexpr int DCT64_NK = (\d+);", txt).group(1))
+    body = re.search(r"dct64_kd_host\[DCT64_NK\] = \{(.*?)\};", txt, re.S).group(1)
+    table = [v.strip() for v in body.split(",") if v.strip()]
+    assert len(table) == nk == len(set(table))
+    uses = re.findall(r"A::cst\((\d+), (-?[0-9.eE+-]+)\)", txt)
+    assert len(uses) == 2 * (136 + 114)  # mul + fma of the forward and of the inverse flow graph
+    assert all(table[int(i)] == lit for i, lit in uses)
+    assert {int(i) for i, _ in uses} == set(range(nk))
